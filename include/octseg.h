@@ -1,0 +1,193 @@
+/*
+ * octseg.h — C-ABI of the B200-native hot path of oct_segmentation's hybrid-ensemble
+ * inference (src/predict.py + OCTSegmentationModel.predict + smp network forward).
+ *
+ * The reference has no FFI of its own: its hot path is Python calling torch library ops
+ * (SURVEY.md §8b).  Each entry point below names the reference call it replaces.  Rules:
+ *   - plain C: pointers, sizes, POD structs; no torch / C++ types cross this boundary;
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with `h_`;
+ *   - nothing here allocates device memory, takes ownership or synchronises: work is
+ *     enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative OCTSEG_E* code otherwise; octseg_last_error()
+ *     returns a thread-local message for the last failure;
+ *   - activations are dense NHWC bf16, channel pitch a multiple of 8 (16-byte pixels).
+ */
+#ifndef OCTSEG_H_
+#define OCTSEG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCTSEG_ABI_VERSION 1
+
+enum {
+  OCTSEG_OK = 0,
+  OCTSEG_EINVAL = -1,   /* bad argument / unsupported shape */
+  OCTSEG_ECUDA = -2,    /* CUDA runtime or driver error     */
+  OCTSEG_ENODEV = -3    /* no sm_100 device                 */
+};
+
+enum { OCTSEG_ACT_NONE = 0, OCTSEG_ACT_RELU = 1, OCTSEG_ACT_SWISH = 2, OCTSEG_ACT_SIGMOID = 3 };
+enum { OCTSEG_RES_NONE = 0, OCTSEG_RES_BEFORE_ACT = 1, OCTSEG_RES_AFTER_ACT = 2 };
+enum {
+  OCTSEG_OUT_BF16_NHWC = 0, /* activation tensor                                      */
+  OCTSEG_OUT_F32_NCHW = 1,  /* logits, the dtype/layout smp's forward() returns       */
+  OCTSEG_OUT_U8_NCHW = 2    /* fused `sigmoid(y) > 0.5` (== y > 0): {0,1} bytes       */
+};
+
+#define OCTSEG_MAX_SEG 6
+
+const char* octseg_last_error(void);
+int octseg_abi_version(void);
+/* Number of SMs of the current device (grid sizing); negative on error. */
+int octseg_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core implicit-GEMM convolution (tcgen05 + TMEM + TMA), one launch per fused op.
+ * Replaces torch's conv2d / conv_transpose2d + batch_norm + relu|silu + interpolate(nearest)
+ * + cat + residual add as issued by smp 0.3.3 decoders and the three encoders
+ * (reference call sites: src/models/smp/model.py:70,192 `self.model(x)`).
+ *
+ * GEMM view:  D[pixel, cout] = sum over K-segments/taps/channels  A[pixel+tap, cin] * B[cout, k].
+ * One K-segment = one source tensor of a fused channel concat.  Tiles are TH x TW output
+ * pixels (TH*TW <= 128) by BN output channels; in 4-phase mode (fused nearest-x2 upsample or
+ * ConvTranspose k4 s2 p1) tiles live on the half-resolution grid and each phase (ph,pw) writes
+ * output pixels (2i+ph, 2j+pw).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct octseg_conv_seg {
+  const void* ptr;    /* bf16 NHWC source, first channel of the slice (16-byte aligned)      */
+  int32_t N, H, W;    /* source extent                                                       */
+  int32_t C;          /* channels visible to this segment (tensor-map extent)                */
+  int32_t ldc;        /* channel pitch of the source in elements (multiple of 8)             */
+  int32_t kh, kw;     /* taps                                                                */
+  int32_t mul;        /* source coordinate = mul * tile_origin + off[parity] + tap           */
+  int32_t off_h[2];   /* per row-phase parity (index 0 used when phases == 1)                */
+  int32_t off_w[2];
+  int32_t c_per_tile; /* 0: all tiles read channels [0,C); >0 (grouped conv): tile n reads
+                         channels starting at n*c_per_tile                                   */
+  int32_t cchunks;    /* 64-channel chunks per tap                                           */
+} octseg_conv_seg;
+
+typedef struct octseg_conv_desc {
+  int32_t nseg;
+  octseg_conv_seg seg[OCTSEG_MAX_SEG];
+  int32_t phases;      /* 1 or 4                                                             */
+  int32_t N, Hq, Wq;   /* tile-space extent (output grid, or half of it when phases == 4)    */
+  int32_t TH, TW;      /* tile extent, TH*TW <= 128                                          */
+  int32_t BN;          /* UMMA N: multiple of 16, 16..256                                    */
+  int32_t n_tiles_n;   /* channel tiles (== groups for a grouped conv)                       */
+  int32_t cout_per_tile; /* real output channels each channel tile stores (<= BN, mult. of 8
+                            for bf16 output)                                                 */
+  int32_t Cout;        /* total real output channels                                         */
+  /* packed weights, bf16 [Z][n_tiles_n*BN][Ktot], Ktot = 64 * (k-iterations per tile);
+     Z = phases * (per_image_weights ? N : 1), z = phase + phases*image                      */
+  const void* weight;
+  int32_t Ktot;
+  int32_t per_image_weights;
+  const float* bias;   /* fp32 [n_tiles_n*BN] (zero padded)                                  */
+  int32_t act;         /* OCTSEG_ACT_*                                                       */
+  int32_t res_mode;    /* OCTSEG_RES_*                                                       */
+  const void* res;     /* bf16 NHWC residual at output resolution, or NULL                   */
+  int32_t res_ldc;
+  void* out;
+  int32_t out_mode;    /* OCTSEG_OUT_*                                                       */
+  int32_t out_H, out_W;/* output extent in pixels                                            */
+  int32_t out_ldc;     /* NHWC: channel pitch; NCHW: number of channel planes                */
+  int32_t out_c_off;   /* first output channel written                                       */
+} octseg_conv_desc;
+
+typedef struct octseg_conv_plan octseg_conv_plan;
+
+/* Builds TMA descriptors + launch geometry.  `*plan` is host memory owned by the library
+   until octseg_conv_plan_destroy. */
+int octseg_conv_plan_create(const octseg_conv_desc* desc, octseg_conv_plan** plan);
+int octseg_conv_plan_destroy(octseg_conv_plan* plan);
+int octseg_conv_run(const octseg_conv_plan* plan, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CUDA-core kernels for the HBM-bound / tiny-K layers.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Network stem: dense kxk conv from the 3-channel network input (torch conv2d on
+   `images_tensor`, model.py:189-192) + folded BN + act -> bf16 NHWC.
+   Input is addressed by element strides so the NHWC-strided float tensor produced by
+   `torch.Tensor(images.transpose(0,3,1,2))` (model.py:189) and uint8 NHWC frames are read in
+   place.  in_dtype: 0 = f32, 1 = u8.  `mean`/`inv_std` (3 floats each, HOST pointers, may be
+   NULL) apply OCTSegmentationModel.forward's normalisation (model.py:69) on the fly. */
+int octseg_stem_conv(const void* in, int32_t in_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                     int32_t N, int32_t H, int32_t W,
+                     const float* weight /* fp32 [kh][kw][3][Cout] */, const float* bias,
+                     int32_t Cout, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l,
+                     int32_t Ho, int32_t Wo, int32_t act,
+                     const float* h_mean, const float* h_inv_std,
+                     void* out /* bf16 NHWC [N][Ho][Wo][out_ldc] */, int32_t out_ldc, void* stream);
+
+/* torch max_pool2d(kernel 3, stride 2, padding 1) of torchvision ResNet (bf16 NHWC). */
+int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C,
+                        int32_t Ho, int32_t Wo, void* stream);
+
+/* Depthwise kxk conv (efficientnet_pytorch MBConvBlock._depthwise_conv with static "same"
+   padding) + folded BN + swish; optionally accumulates the squeeze-excite channel sums
+   (adaptive_avg_pool2d numerator) into `pool_sum` fp32 [N][C] (must be zeroed by caller). */
+int octseg_dwconv(const void* in, const float* weight /* fp32 [kh][kw][C] */, const float* bias,
+                  void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
+                  int32_t pad_t, int32_t pad_l, int32_t Ho, int32_t Wo, int32_t act,
+                  float* pool_sum, void* stream);
+
+/* Squeeze-excite gate: s = sigmoid(W2 · swish(W1 · mean + b1) + b2), fp32 [N][C]. */
+int octseg_se_gate(const float* pool_sum, float inv_hw, const float* w1 /* [Cr][C] */, const float* b1,
+                   const float* w2 /* [C][Cr] */, const float* b2, float* gate,
+                   int32_t N, int32_t C, int32_t Cr, void* stream);
+
+/* Per-image gate folded into the project 1x1 weights:
+   out[n][row][k] = bf16(w[row][k] * gate[n][k]) for k < C, 0 for padded k. */
+int octseg_scale_weights(const float* w /* fp32 [rows][Ktot] */, const float* gate /* [N][C] */,
+                         void* out /* bf16 [N][rows][Ktot] */, int32_t N, int32_t rows, int32_t Ktot,
+                         int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pre-processing: preprocessing_img (src/data/utils.py:159-166): RGB->BGR + cv2.resize
+ * INTER_LINEAR (uint8, 11-bit fixed point) of a uint8 HWC frame, written as the uint8 NHWC
+ * network input (N,S,S,3).  Bit-exact vs cv2.
+ * ------------------------------------------------------------------------------------------ */
+/* xofs/yofs: int32 [S] left/top source index; xalpha/ybeta: int16 [S][2] 11-bit coefficients,
+   computed by the caller with cv2's float32 rule (fx=(float)((dx+0.5)*scale-0.5); see
+   oct_segmentation_b200/prepost.py).  All four are DEVICE pointers. */
+int octseg_preprocess_resize_bgr(const uint8_t* src /* [N][Hs][Ws][3] RGB */, int32_t N, int32_t Hs,
+                                 int32_t Ws, uint8_t* dst /* [N][S][S][3] BGR */, int32_t S,
+                                 const int32_t* xofs, const int16_t* xalpha, const int32_t* yofs,
+                                 const int16_t* ybeta, int32_t area_fast_2x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Post-processing: threshold (model.py:195) + cv2.resize INTER_NEAREST (predict.py:92-96) +
+ * class routing (predict.py:97-100, MODELS_META) + priority label map (data/utils.py:231-233)
+ * + per-class pixel count (analysis.py:199) in one pass over the output grid.
+ *   chan[c]: pointer to the {0,1} uint8 plane [N][S_c][S_c] feeding mask channel c (or NULL:
+ *            class absent -> zeros), c = class id - 1 (LM, FC, LC, VV).
+ *   h_lut[c]: DEVICE int32 [Ho + Wo]: source row for each output row, then source column for
+ *            each output column (cv2 rule sx = min(floor(x * (1/(dst/src))), src-1))
+ *   mask   : uint8 [N][Ho][Wo][4] {0,1}      (the reference's float64 HxWx4 array, as bytes)
+ *   label  : uint8 [N][Ho][Wo] 0 = background, else highest-priority class id (later class in
+ *            `order` wins), or NULL
+ *   counts : int32 [N][4] non-zero pixels per class (zeroed by caller)
+ * ------------------------------------------------------------------------------------------ */
+int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h_S,
+                       const int32_t* const* h_lut, const int32_t* h_order,
+                       int32_t n_order, int32_t N, int32_t Ho, int32_t Wo, uint8_t* mask,
+                       uint8_t* label, int32_t* counts, void* stream);
+
+/* calculate_object_thickness (src/app/tools/analysis.py:60-130): 360 rays from the image
+   centre; per ray the last radius inside the object before the first exit.
+   mask: uint8 [N][H][W][4] (non-zero = object); radii: int32 [N][4][360] (0 = ray missed). */
+/* cos_sin: DEVICE double [720] = cos(radians(a)) for a in 0..359, then sin(...) (host libm
+   values, so x = int(cx + r*cos) truncates exactly like the reference's Python floats). */
+int octseg_radial_thickness(const uint8_t* mask, int32_t N, int32_t H, int32_t W, const double* cos_sin,
+                            int32_t* radii, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTSEG_H_ */

@@ -1,0 +1,583 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: TMA -> shared memory (128B swizzle) ->
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> epilogue (bias, residual, activation) -> global.
+//
+// Replaces, for the smp 0.3.3 graphs the reference runs (src/models/smp/model.py:70,192):
+// conv2d / conv_transpose2d(k4,s2,p1) + eval-mode batch_norm (folded) + relu|swish +
+// F.interpolate(scale_factor=2, mode="nearest") + torch.cat + residual add.
+//
+// Layout: activations NHWC bf16.  A-operand tiles are TH x TW output pixels (<=128 rows) by 64
+// input channels, fetched per filter tap as one shifted 4-D TMA box (zero fill outside the image
+// = conv padding).  B tiles are BN x 64 slices of the packed weight matrix.  The K loop runs over
+// (source tensor of the fused concat) x (tap) x (64-channel chunk).
+//
+// Nearest-x2 upsample + 3x3 conv and ConvTranspose(k4,s2,p1) are executed as four output-phase
+// sub-problems on the half-resolution grid (weights pre-combined per phase on the host).
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2-5 = epilogue (one TMEM lane quarter each).  Accumulators are double-buffered in TMEM so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstring>
+#include <new>
+
+#include "common.h"
+
+namespace octseg {
+
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kSpinLimit = 1u << 26;  // turns a pipeline deadlock into a trap, not a hang
+
+struct SegK {
+  int C, kh, kw, mul;
+  int off_h[2], off_w[2];
+  int c_per_tile, cchunks;
+};
+
+struct __align__(64) ConvKParams {
+  CUtensorMap tmA[OCTSEG_MAX_SEG];
+  CUtensorMap tmB;
+  SegK seg[OCTSEG_MAX_SEG];
+  int nseg, phases, N, Hq, Wq, TH, TW, tiles_h, tiles_w;
+  int BN, n_tiles_n, cout_per_tile, Cout;
+  int per_image_weights, act, res_mode, out_mode;
+  int k_iters, nstages, total_tiles;
+  uint32_t stage_tx_bytes;
+  const float* bias;
+  const __nv_bfloat16* res;
+  int res_ldc;
+  void* out;
+  int out_H, out_W, out_ldc, out_c_off;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);  // start address
+  d |= static_cast<uint64_t>(1) << 16;                 // leading byte offset (unused for SW128 K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;         // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;                 // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == OCTSEG_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == OCTSEG_ACT_SWISH) return x / (1.f + __expf(-x));
+  if (act == OCTSEG_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  return x;
+}
+
+struct TileCoord {
+  int n_tile, tw, th, n, ph, pw, phase;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int t) {
+  TileCoord c;
+  c.n_tile = t % p.n_tiles_n;
+  t /= p.n_tiles_n;
+  c.tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  c.th = t % p.tiles_h;
+  t /= p.tiles_h;
+  c.n = t % p.N;
+  c.phase = t / p.N;
+  c.ph = c.phase >> 1;
+  c.pw = c.phase & 1;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nst = p.nstages;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t smemA = smem0;
+  const uint32_t smemB = smem0 + nst * kABytes;
+  const uint32_t bars = smemB + nst * b_bytes;  // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
+  const uint32_t bar_tfull = bars + 16 * kMaxStages, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.TH * p.TW < 128) {
+    // rows the TMA box never writes must still hold finite values for the MMA
+    uint4* z = reinterpret_cast<uint4*>(smem_gen);
+    const int n16 = nst * kABytes / 16;
+    for (int i = threadIdx.x; i < n16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&p.tmA[s]);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int brow = tc.n_tile * p.BN;
+        const int bz = tc.phase + p.phases * (p.per_image_weights ? tc.n : 0);
+        int kofs = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const SegK& sg = p.seg[s];
+          const int h0 = sg.mul * tc.th * p.TH + sg.off_h[tc.ph];
+          const int w0 = sg.mul * tc.tw * p.TW + sg.off_w[tc.pw];
+          const int cbase = sg.c_per_tile * tc.n_tile;
+          for (int ty = 0; ty < sg.kh; ++ty) {
+            for (int tx = 0; tx < sg.kw; ++tx) {
+              for (int cc = 0; cc < sg.cchunks; ++cc) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                mbar_arrive_expect_tx(bar_full + 8 * stage, p.stage_tx_bytes);
+                tma_load_4d(smemA + stage * kABytes, &p.tmA[s], bar_full + 8 * stage, cbase + cc * 64,
+                            w0 + tx, h0 + ty, tc.n);
+                tma_load_3d(smemB + stage * b_bytes, &p.tmB, bar_full + 8 * stage, kofs, brow, bz);
+                kofs += 64;
+                if (++stage == nst) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.BN >> 3) << 17) |
+                             (static_cast<uint32_t>(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.BN);
+        for (int k = 0; k < p.k_iters; ++k) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_desc(smemA + stage * kABytes);
+          const uint64_t bdesc = make_sw128_desc(smemB + stage * b_bytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // 4 x (K=16) per 64-channel chunk: +32 B inside the swizzle atom
+            tc_mma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == nst) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int th_l = row / p.TW, tw_l = row - th_l * p.TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int i = tc.th * p.TH + th_l, j = tc.tw * p.TW + tw_l;
+      const bool valid = (row < p.TH * p.TW) && (i < p.Hq) && (j < p.Wq);
+      const int oh = (p.phases == 4) ? 2 * i + tc.ph : i;
+      const int ow = (p.phases == 4) ? 2 * j + tc.pw : j;
+      const int ch0 = tc.n_tile * p.cout_per_tile;  // first real channel of this tile
+      const int nvalid = min(p.cout_per_tile, p.Cout - ch0);
+      const size_t pix = (static_cast<size_t>(tc.n) * p.out_H + oh) * p.out_W + ow;
+      const float* bias = p.bias + tc.n_tile * p.BN;
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
+      for (int c0 = 0; c0 < nvalid; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (!valid) {
+          // row outside the image / tile: nothing to store
+        } else if (p.out_mode == OCTSEG_OUT_BF16_NHWC) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ldc + p.out_c_off + ch0 + c0;
+          const __nv_bfloat16* r = p.res ? p.res + pix * p.res_ldc + ch0 + c0 : nullptr;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c0 + g * 8 < nvalid) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 8 + 4));
+              float x[8];
+              x[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+              x[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+              x[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+              x[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+              x[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+              x[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+              x[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+              x[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+              float rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              if (r) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + g * 8));
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(r2[e]);
+                  rr[2 * e] = f.x;
+                  rr[2 * e + 1] = f.y;
+                }
+              }
+              uint4 ov;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float y0 = x[2 * e], y1 = x[2 * e + 1];
+                if (p.res_mode == OCTSEG_RES_BEFORE_ACT) {
+                  y0 += rr[2 * e];
+                  y1 += rr[2 * e + 1];
+                }
+                y0 = apply_act(y0, p.act);
+                y1 = apply_act(y1, p.act);
+                if (p.res_mode == OCTSEG_RES_AFTER_ACT) {
+                  y0 += rr[2 * e];
+                  y1 += rr[2 * e + 1];
+                }
+                o2[e] = __floats2bfloat162_rn(y0, y1);
+              }
+              *reinterpret_cast<uint4*>(o + g * 8) = ov;
+            }
+          }
+        } else {
+          // NCHW planes: lanes of a warp are consecutive pixels -> coalesced per channel plane
+          const size_t plane = static_cast<size_t>(p.out_H) * p.out_W;
+          const size_t base = (static_cast<size_t>(tc.n) * p.out_ldc + p.out_c_off + ch0 + c0) * plane +
+                              static_cast<size_t>(oh) * p.out_W + ow;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (c0 + e < nvalid) {
+              const float y = apply_act(__uint_as_float(v[e]) + __ldg(bias + c0 + e), p.act);
+              if (p.out_mode == OCTSEG_OUT_F32_NCHW)
+                reinterpret_cast<float*>(p.out)[base + e * plane] = y;
+              else
+                reinterpret_cast<uint8_t*>(p.out)[base + e * plane] = y > 0.f ? 1 : 0;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr,
+                      const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(OCTSEG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                  reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                  reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(OCTSEG_ECUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, static_cast<int>(r));
+  return OCTSEG_OK;
+}
+
+}  // namespace octseg
+
+struct octseg_conv_plan {
+  octseg::ConvKParams kp;
+  int grid;
+  size_t smem;
+};
+
+using namespace octseg;
+
+extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_plan** out_plan) {
+  if (!d || !out_plan) return fail(OCTSEG_EINVAL, "null argument");
+  if (d->nseg < 1 || d->nseg > OCTSEG_MAX_SEG) return fail(OCTSEG_EINVAL, "nseg=%d out of range", d->nseg);
+  if (d->phases != 1 && d->phases != 4) return fail(OCTSEG_EINVAL, "phases must be 1 or 4");
+  if (d->BN < 16 || d->BN > 256 || d->BN % 16) return fail(OCTSEG_EINVAL, "BN=%d must be a multiple of 16 in [16,256]", d->BN);
+  if (d->TH < 1 || d->TW < 1 || d->TH * d->TW > 128) return fail(OCTSEG_EINVAL, "tile %dx%d exceeds 128 pixels", d->TH, d->TW);
+  if (d->cout_per_tile < 1 || d->cout_per_tile > d->BN) return fail(OCTSEG_EINVAL, "cout_per_tile=%d vs BN=%d", d->cout_per_tile, d->BN);
+  if (d->out_mode == OCTSEG_OUT_BF16_NHWC &&
+      (d->cout_per_tile % 8 || d->out_ldc % 8 || d->out_c_off % 8 || d->Cout % 8))
+    return fail(OCTSEG_EINVAL, "bf16 NHWC output needs channel counts/pitches that are multiples of 8");
+  if (d->res && (d->res_ldc % 8 || d->out_mode != OCTSEG_OUT_BF16_NHWC))
+    return fail(OCTSEG_EINVAL, "residual needs bf16 NHWC output and a pitch that is a multiple of 8");
+  if ((reinterpret_cast<uintptr_t>(d->weight) & 15) || (reinterpret_cast<uintptr_t>(d->out) & 15) ||
+      (reinterpret_cast<uintptr_t>(d->bias) & 15) || (reinterpret_cast<uintptr_t>(d->res) & 15))
+    return fail(OCTSEG_EINVAL, "weight/out/bias/res pointers must be 16-byte aligned");
+
+  octseg_conv_plan* pl = new (std::nothrow) octseg_conv_plan;
+  if (!pl) return fail(OCTSEG_EINVAL, "out of host memory");
+  std::memset(pl, 0, sizeof(*pl));
+  ConvKParams& kp = pl->kp;
+
+  int k_iters = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const octseg_conv_seg& sg = d->seg[s];
+    if (sg.mul < 1 || sg.mul > 2 || sg.kh < 1 || sg.kw < 1 || sg.cchunks < 1 || sg.ldc % 8 ||
+        (reinterpret_cast<uintptr_t>(sg.ptr) & 15) || sg.N != d->N) {
+      delete pl;
+      return fail(OCTSEG_EINVAL, "segment %d: bad geometry (mul=%d kh=%d kw=%d cchunks=%d ldc=%d N=%d)", s, sg.mul,
+                  sg.kh, sg.kw, sg.cchunks, sg.ldc, sg.N);
+    }
+    const uint64_t dims[4] = {static_cast<uint64_t>(sg.C), static_cast<uint64_t>(sg.W), static_cast<uint64_t>(sg.H),
+                              static_cast<uint64_t>(sg.N)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(sg.ldc) * 2, static_cast<uint64_t>(sg.W) * sg.ldc * 2,
+                                 static_cast<uint64_t>(sg.H) * sg.W * sg.ldc * 2};
+    const uint32_t box[4] = {64u, static_cast<uint32_t>(d->TW * sg.mul), static_cast<uint32_t>(d->TH * sg.mul), 1u};
+    const uint32_t estr[4] = {1u, static_cast<uint32_t>(sg.mul), static_cast<uint32_t>(sg.mul), 1u};
+    int rc = encode_map(&kp.tmA[s], sg.ptr, 4, dims, strides, box, estr, "A");
+    if (rc) {
+      delete pl;
+      return rc;
+    }
+    SegK& k = kp.seg[s];
+    k.C = sg.C;
+    k.kh = sg.kh;
+    k.kw = sg.kw;
+    k.mul = sg.mul;
+    k.off_h[0] = sg.off_h[0];
+    k.off_h[1] = sg.off_h[1];
+    k.off_w[0] = sg.off_w[0];
+    k.off_w[1] = sg.off_w[1];
+    k.c_per_tile = sg.c_per_tile;
+    k.cchunks = sg.cchunks;
+    k_iters += sg.kh * sg.kw * sg.cchunks;
+  }
+  if (k_iters * 64 != d->Ktot) {
+    delete pl;
+    return fail(OCTSEG_EINVAL, "Ktot=%d does not match 64 * k-iterations (%d)", d->Ktot, k_iters);
+  }
+  {
+    const uint64_t rows = static_cast<uint64_t>(d->n_tiles_n) * d->BN;
+    const uint64_t Z = static_cast<uint64_t>(d->phases) * (d->per_image_weights ? d->N : 1);
+    const uint64_t dims[3] = {static_cast<uint64_t>(d->Ktot), rows, Z};
+    const uint64_t strides[2] = {static_cast<uint64_t>(d->Ktot) * 2, rows * d->Ktot * 2};
+    const uint32_t box[3] = {64u, static_cast<uint32_t>(d->BN), 1u};
+    const uint32_t estr[3] = {1u, 1u, 1u};
+    int rc = encode_map(&kp.tmB, d->weight, 3, dims, strides, box, estr, "B");
+    if (rc) {
+      delete pl;
+      return rc;
+    }
+  }
+  kp.nseg = d->nseg;
+  kp.phases = d->phases;
+  kp.N = d->N;
+  kp.Hq = d->Hq;
+  kp.Wq = d->Wq;
+  kp.TH = d->TH;
+  kp.TW = d->TW;
+  kp.tiles_h = cdiv(d->Hq, d->TH);
+  kp.tiles_w = cdiv(d->Wq, d->TW);
+  kp.BN = d->BN;
+  kp.n_tiles_n = d->n_tiles_n;
+  kp.cout_per_tile = d->cout_per_tile;
+  kp.Cout = d->Cout;
+  kp.per_image_weights = d->per_image_weights;
+  kp.act = d->act;
+  kp.res_mode = d->res ? d->res_mode : OCTSEG_RES_NONE;
+  kp.out_mode = d->out_mode;
+  kp.k_iters = k_iters;
+  kp.stage_tx_bytes = static_cast<uint32_t>(d->TH * d->TW * 128 + d->BN * 128);
+  kp.bias = d->bias;
+  kp.res = static_cast<const __nv_bfloat16*>(d->res);
+  kp.res_ldc = d->res_ldc;
+  kp.out = d->out;
+  kp.out_H = d->out_H;
+  kp.out_W = d->out_W;
+  kp.out_ldc = d->out_ldc;
+  kp.out_c_off = d->out_c_off;
+  kp.total_tiles = d->phases * d->N * kp.tiles_h * kp.tiles_w * d->n_tiles_n;
+
+  const int stage_bytes = kABytes + d->BN * 128;
+  const int budget = 227 * 1024 - 1024 - 512;
+  int nst = budget / stage_bytes;
+  if (nst > kMaxStages) nst = kMaxStages;
+  if (nst < 2) {
+    delete pl;
+    return fail(OCTSEG_EINVAL, "tile does not fit shared memory");
+  }
+  kp.nstages = nst;
+  pl->smem = static_cast<size_t>(nst) * stage_bytes + 1024 + 512;
+  int sms = octseg_sm_count();
+  if (sms <= 0) {
+    delete pl;
+    return sms;
+  }
+  pl->grid = kp.total_tiles < sms ? kp.total_tiles : sms;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      delete pl;
+      return fail(OCTSEG_ECUDA, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  *out_plan = pl;
+  return OCTSEG_OK;
+}
+
+extern "C" int octseg_conv_plan_destroy(octseg_conv_plan* plan) {
+  delete plan;
+  return OCTSEG_OK;
+}
+
+extern "C" int octseg_conv_run(const octseg_conv_plan* plan, void* stream) {
+  if (!plan) return fail(OCTSEG_EINVAL, "null plan");
+  if (plan->kp.total_tiles <= 0) return OCTSEG_OK;
+  conv_tc_kernel<<<plan->grid, kThreads, plan->smem, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  return check_launch("conv_tc_kernel");
+}

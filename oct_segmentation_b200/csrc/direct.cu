@@ -1,0 +1,374 @@
+// CUDA-core kernels for the layers that are HBM-bound or have a tiny contraction:
+// network stems (Cin = 3), max-pool, depthwise conv (+ squeeze-excite pooling), SE gate,
+// per-image SE-scaled projection weights.  Activations are NHWC bf16, 8 channels (16 bytes)
+// per thread access.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "common.h"
+
+namespace octseg {
+
+__device__ __forceinline__ float act_f(float x, int act) {
+  if (act == OCTSEG_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == OCTSEG_ACT_SWISH) return x / (1.f + __expf(-x));
+  if (act == OCTSEG_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  return x;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __bfloat1622float2(h[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------ stem
+// One block = 16x16 output pixels; the input patch and the whole filter bank sit in shared
+// memory; each thread owns one pixel and CO output channels in registers.
+struct StemParams {
+  const void* in;
+  int in_dtype;
+  long long sn, sc, sh, sw;
+  int N, H, W;
+  const float* weight;
+  const float* bias;
+  int k, stride, pad_t, pad_l, Ho, Wo, act;
+  float mean[3], inv_std[3];
+  int normalize;
+  __nv_bfloat16* out;
+  int out_ldc;
+};
+
+template <int CO>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
+  extern __shared__ float smem[];
+  const int taps = p.k * p.k * 3;
+  float* wsm = smem;               // [taps][CO]
+  float* patch = smem + taps * CO; // [ph][pw][3]
+  const int pdim = 15 * p.stride + p.k;
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * 16, ox0 = blockIdx.x * 16;
+  const int iy0 = oy0 * p.stride - p.pad_t, ix0 = ox0 * p.stride - p.pad_l;
+
+  for (int i = threadIdx.x; i < taps * CO; i += 256) wsm[i] = p.weight[i];
+  for (int i = threadIdx.x; i < pdim * pdim * 3; i += 256) {
+    const int c = i % 3, x = (i / 3) % pdim, y = i / (3 * pdim);
+    const int iy = iy0 + y, ix = ix0 + x;
+    float v = 0.f;
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+      const long long off = n * p.sn + c * p.sc + iy * p.sh + ix * p.sw;
+      v = p.in_dtype == 0 ? reinterpret_cast<const float*>(p.in)[off]
+                          : static_cast<float>(reinterpret_cast<const uint8_t*>(p.in)[off]);
+      if (p.normalize) v = (v - p.mean[c]) * p.inv_std[c];
+    }
+    patch[i] = v;
+  }
+  __syncthreads();
+
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  for (int ky = 0; ky < p.k; ++ky) {
+    for (int kx = 0; kx < p.k; ++kx) {
+      const float* pp = patch + ((ty * p.stride + ky) * pdim + tx * p.stride + kx) * 3;
+      const float* ww = wsm + (ky * p.k + kx) * 3 * CO;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = pp[c];
+        const float4* w4 = reinterpret_cast<const float4*>(ww + c * CO);
+#pragma unroll
+        for (int g = 0; g < CO / 4; ++g) {
+          const float4 w = w4[g];
+          acc[4 * g + 0] = fmaf(v, w.x, acc[4 * g + 0]);
+          acc[4 * g + 1] = fmaf(v, w.y, acc[4 * g + 1]);
+          acc[4 * g + 2] = fmaf(v, w.z, acc[4 * g + 2]);
+          acc[4 * g + 3] = fmaf(v, w.w, acc[4 * g + 3]);
+        }
+      }
+    }
+  }
+  if (oy < p.Ho && ox < p.Wo) {
+    __nv_bfloat16* o = p.out + ((static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox) * p.out_ldc;
+#pragma unroll
+    for (int g = 0; g < CO / 8; ++g) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = act_f(acc[g * 8 + e] + __ldg(p.bias + g * 8 + e), p.act);
+      *reinterpret_cast<uint4*>(o + g * 8) = pack8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ maxpool
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
+                                    int H, int W, int C8, int Ho, int Wo) {
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = idx % C8;
+    size_t t = idx / C8;
+    const int ox = t % Wo;
+    t /= Wo;
+    const int oy = t % Ho;
+    const int n = t / Ho;
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + ((static_cast<size_t>(n) * H + iy) * W + ix) * C8 + c8);
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+      }
+    }
+    reinterpret_cast<uint4*>(out)[idx] = pack8(m);
+  }
+}
+
+// ------------------------------------------------------------------------------------ depthwise
+// block = 32 channel-groups (256 channels) x 8 pixel lanes; each block walks a strip of output
+// pixels so the squeeze-excite sums reduce in registers -> shared -> one atomic per channel.
+constexpr int kDwPixPerBlock = 256;
+
+__global__ void __launch_bounds__(256) dwconv_kernel(const __nv_bfloat16* __restrict__ in,
+                                                     const float* __restrict__ weight,
+                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                     int H, int W, int C, int k, int stride, int pad_t, int pad_l,
+                                                     int Ho, int Wo, int act, float* __restrict__ pool_sum) {
+  __shared__ float wsm[25 * 256];
+  __shared__ float red[8][256];
+  const int C8 = C >> 3;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int cg = blockIdx.x * 32 + tx;
+  const int n = blockIdx.z;
+  const bool cvalid = cg < C8;
+  const int taps = k * k;
+  for (int i = threadIdx.x; i < taps * 256; i += 256) {
+    const int c = blockIdx.x * 256 + (i & 255);
+    wsm[i] = c < C ? weight[(i >> 8) * C + c] : 0.f;
+  }
+  __syncthreads();
+  float b[8], psum[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    b[e] = cvalid ? __ldg(bias + cg * 8 + e) : 0.f;
+    psum[e] = 0.f;
+  }
+  const int npix = Ho * Wo;
+  const int p0 = blockIdx.y * kDwPixPerBlock;
+  const int p1 = min(p0 + kDwPixPerBlock, npix);
+  const uint4* in4 = reinterpret_cast<const uint4*>(in) + static_cast<size_t>(n) * H * W * C8;
+  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * npix * C8;
+  if (cvalid) {
+    for (int pix = p0 + ty; pix < p1; pix += 8) {
+      const int oy = pix / Wo, ox = pix - oy * Wo;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = b[e];
+      for (int ky = 0; ky < k; ++ky) {
+        const int iy = oy * stride - pad_t + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < k; ++kx) {
+          const int ix = ox * stride - pad_l + kx;
+          if (ix < 0 || ix >= W) continue;
+          const uint4 v = __ldg(in4 + (static_cast<size_t>(iy) * W + ix) * C8 + cg);
+          float f[8];
+          unpack8(v, f);
+          const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * k + kx) * 256 + tx * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * k + kx) * 256 + tx * 8 + 4);
+          acc[0] = fmaf(f[0], w0.x, acc[0]);
+          acc[1] = fmaf(f[1], w0.y, acc[1]);
+          acc[2] = fmaf(f[2], w0.z, acc[2]);
+          acc[3] = fmaf(f[3], w0.w, acc[3]);
+          acc[4] = fmaf(f[4], w1.x, acc[4]);
+          acc[5] = fmaf(f[5], w1.y, acc[5]);
+          acc[6] = fmaf(f[6], w1.z, acc[6]);
+          acc[7] = fmaf(f[7], w1.w, acc[7]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = act_f(acc[e], act);
+      const uint4 o = pack8(acc);
+      out4[static_cast<size_t>(pix) * C8 + cg] = o;
+      if (pool_sum) {
+        // pool what the next layer actually reads (the bf16-rounded activation)
+        float r[8];
+        unpack8(o, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) psum[e] += r[e];
+      }
+    }
+  }
+  if (pool_sum) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[ty][tx * 8 + e] = psum[e];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < C) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
+      atomicAdd(pool_sum + static_cast<size_t>(n) * C + c, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ SE gate
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_sum, float inv_hw,
+                                                      const float* __restrict__ w1, const float* __restrict__ b1,
+                                                      const float* __restrict__ w2, const float* __restrict__ b2,
+                                                      float* __restrict__ gate, int C, int Cr) {
+  extern __shared__ float sm[];
+  float* mean = sm;       // [C]
+  float* hid = sm + C;    // [Cr]
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += 256) mean[c] = pool_sum[static_cast<size_t>(n) * C + c] * inv_hw;
+  __syncthreads();
+  for (int r = warp; r < Cr; r += 8) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w1[static_cast<size_t>(r) * C + c], mean[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s += b1[r];
+      hid[r] = s / (1.f + __expf(-s));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = b2[c];
+    for (int r = 0; r < Cr; ++r) s = fmaf(w2[static_cast<size_t>(c) * Cr + r], hid[r], s);
+    gate[static_cast<size_t>(n) * C + c] = 1.f / (1.f + __expf(-s));
+  }
+}
+
+__global__ void scale_weights_kernel(const float* __restrict__ w, const float* __restrict__ gate,
+                                     __nv_bfloat16* __restrict__ out, int N, int rows, int Ktot, int C) {
+  const size_t per = static_cast<size_t>(rows) * Ktot;
+  const size_t total = per * N;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = idx / per;
+    const size_t r = idx - n * per;
+    const int kk = r % Ktot;
+    const float g = kk < C ? gate[static_cast<size_t>(n) * C + kk] : 0.f;
+    out[idx] = __float2bfloat16_rn(w[r] * g);
+  }
+}
+
+static int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 32;
+  return static_cast<int>(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace octseg
+
+using namespace octseg;
+
+extern "C" int octseg_stem_conv(const void* in, int32_t in_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                                int32_t N, int32_t H, int32_t W, const float* weight, const float* bias,
+                                int32_t Cout, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t Ho,
+                                int32_t Wo, int32_t act, const float* h_mean, const float* h_inv_std, void* out,
+                                int32_t out_ldc, void* stream) {
+  if (Cout != 32 && Cout != 64) return fail(OCTSEG_EINVAL, "stem conv supports Cout 32 or 64, got %d", Cout);
+  if (k > 7 || stride > 2 || out_ldc % 8) return fail(OCTSEG_EINVAL, "stem conv: k<=7, stride<=2, out_ldc%%8==0");
+  if (in_dtype != 0 && in_dtype != 1) return fail(OCTSEG_EINVAL, "stem conv: in_dtype must be 0 (f32) or 1 (u8)");
+  StemParams p;
+  p.in = in;
+  p.in_dtype = in_dtype;
+  p.sn = sn;
+  p.sc = sc;
+  p.sh = sh;
+  p.sw = sw;
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.weight = weight;
+  p.bias = bias;
+  p.k = k;
+  p.stride = stride;
+  p.pad_t = pad_t;
+  p.pad_l = pad_l;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.act = act;
+  p.normalize = (h_mean && h_inv_std) ? 1 : 0;
+  for (int c = 0; c < 3; ++c) {
+    p.mean[c] = p.normalize ? h_mean[c] : 0.f;
+    p.inv_std[c] = p.normalize ? h_inv_std[c] : 1.f;
+  }
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out_ldc = out_ldc;
+  const int pdim = 15 * stride + k;
+  const size_t smem = (static_cast<size_t>(k) * k * 3 * Cout + static_cast<size_t>(pdim) * pdim * 3) * sizeof(float);
+  dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Cout == 64) {
+    OCTSEG_CUDA(cudaFuncSetAttribute(stem_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    stem_conv_kernel<64><<<grid, 256, smem, st>>>(p);
+  } else {
+    OCTSEG_CUDA(cudaFuncSetAttribute(stem_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    stem_conv_kernel<32><<<grid, 256, smem, st>>>(p);
+  }
+  return check_launch("stem_conv_kernel");
+}
+
+extern "C" int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t Ho,
+                                   int32_t Wo, void* stream) {
+  if (C % 8) return fail(OCTSEG_EINVAL, "maxpool: C must be a multiple of 8");
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), N, H, W, C / 8, Ho, Wo);
+  return check_launch("maxpool3x3s2_kernel");
+}
+
+extern "C" int octseg_dwconv(const void* in, const float* weight, const float* bias, void* out, int32_t N, int32_t H,
+                             int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l,
+                             int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, void* stream) {
+  if (C % 8 || k > 5) return fail(OCTSEG_EINVAL, "dwconv: C%%8==0 and k<=5 required (C=%d k=%d)", C, k);
+  dim3 grid(cdiv(C / 8, 32), cdiv(Ho * Wo, kDwPixPerBlock), N);
+  dwconv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), weight, bias, static_cast<__nv_bfloat16*>(out), H, W, C, k, stride,
+      pad_t, pad_l, Ho, Wo, act, pool_sum);
+  return check_launch("dwconv_kernel");
+}
+
+extern "C" int octseg_se_gate(const float* pool_sum, float inv_hw, const float* w1, const float* b1, const float* w2,
+                              const float* b2, float* gate, int32_t N, int32_t C, int32_t Cr, void* stream) {
+  const size_t smem = static_cast<size_t>(C + Cr) * sizeof(float);
+  if (smem > 48 * 1024) return fail(OCTSEG_EINVAL, "se_gate: C+Cr too large");
+  se_gate_kernel<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(pool_sum, inv_hw, w1, b1, w2, b2, gate, C, Cr);
+  return check_launch("se_gate_kernel");
+}
+
+extern "C" int octseg_scale_weights(const float* w, const float* gate, void* out, int32_t N, int32_t rows,
+                                    int32_t Ktot, int32_t C, void* stream) {
+  const size_t total = static_cast<size_t>(N) * rows * Ktot;
+  scale_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, gate, static_cast<__nv_bfloat16*>(out), N, rows, Ktot, C);
+  return check_launch("scale_weights_kernel");
+}

@@ -1,0 +1,278 @@
+"""Host-side planning of one fused tensor-core convolution launch.
+
+Turns a layer description (sources of the fused concat, folded fp32 weights, geometry) into
+the explicit K-segment / tile / packed-weight form that ``octseg_conv_plan_create`` consumes
+(include/octseg.h).  Everything here is shape arithmetic + weight re-layout and runs on CPU;
+``ConvPlan.materialize`` uploads the packed weights and creates the device plan.
+
+Replaces (reference call sites src/models/smp/model.py:70,192): conv2d / conv_transpose2d +
+folded BatchNorm + activation (+ nearest-x2 upsample, channel concat, residual add) of the
+smp 0.3.3 graphs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib
+
+KC = 64  # channels per K-iteration (one 128-byte swizzle atom of bf16)
+
+
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+@dataclass
+class Act:
+    """NHWC bf16 activation: ``t`` has shape (N, H, W, Cp) with Cp = pad8(C); pad channels are 0."""
+    t: torch.Tensor
+    C: int
+
+    @property
+    def N(self): return self.t.shape[0]
+    @property
+    def H(self): return self.t.shape[1]
+    @property
+    def W(self): return self.t.shape[2]
+    @property
+    def Cp(self): return self.t.shape[3]
+
+
+@dataclass
+class SegSpec:
+    """One K-segment (source tensor) in kernel terms; see octseg_conv_seg."""
+    N: int
+    H: int
+    W: int
+    C: int
+    ldc: int
+    kh: int
+    kw: int
+    mul: int
+    off_h: Tuple[int, int]
+    off_w: Tuple[int, int]
+    c_per_tile: int
+    cchunks: int
+
+
+@dataclass
+class ConvGeom:
+    """Everything octseg_conv_desc holds except device pointers."""
+    segs: List[SegSpec]
+    phases: int
+    N: int
+    Hq: int
+    Wq: int
+    TH: int
+    TW: int
+    BN: int
+    n_tiles_n: int
+    cout_per_tile: int
+    Cout: int            # channels written (padded to 8 for bf16 NHWC)
+    Ktot: int
+    out_H: int
+    out_W: int
+    macs: int = 0        # algorithmic MACs of the reference op (dense count, for rooflines)
+
+
+def choose_tile(Hq: int, Wq: int) -> Tuple[int, int]:
+    """TH x TW <= 128 output pixels maximising the useful fraction of the 128-row MMA."""
+    best, best_key = (1, 1), None
+    for tw in range(1, min(Wq, 128) + 1):
+        th = min(Hq, 128 // tw)
+        covered = -(-Hq // th) * th * -(-Wq // tw) * tw
+        eff = (Hq * Wq) / covered * (th * tw) / 128.0
+        key = (round(eff, 6), tw)
+        if best_key is None or key > best_key:
+            best, best_key = (th, tw), key
+    return best
+
+
+def choose_bn(cout_p: int) -> Tuple[int, int]:
+    """(n_tiles_n, BN): BN multiple of 16, <= 256, tiles cover cout_p channels."""
+    n_tiles = -(-cout_p // 256)
+    bn = -(-cout_p // n_tiles)
+    bn = (bn + 15) // 16 * 16
+    return n_tiles, bn
+
+
+def _phase_tap_groups(ph: int, a: int) -> List[int]:
+    """3x3 taps (pad 1) of a conv over a nearest-x2-upsampled tensor that land on low-res
+    offset ``ph - 1 + a`` for output-row parity ``ph``: floor((ph + k - 1) / 2) == ph - 1 + a."""
+    return [k for k in range(3) if (ph + k - 1) // 2 == ph - 1 + a]
+
+
+def plan_conv(srcs: Sequence[Tuple[Tuple[int, int, int, int, int], bool]], weight: torch.Tensor,
+              out_hw: Optional[Tuple[int, int]] = None, stride: int = 1, pad: Tuple[int, int] = (0, 0),
+              groups: int = 1, transposed: bool = False, out_bf16: bool = True) -> Tuple[ConvGeom, torch.Tensor]:
+    """Plan one conv.
+
+    srcs: [((N, H, W, C, ldc), upsampled)] in concat order; ``upsampled`` sources are at half the
+          output resolution and are read through a fused nearest-x2 upsample.
+    weight: fp32 [Cout, Cin_total/groups, kh, kw] (BN folded), or [Cin, Cout, 4, 4] when
+          ``transposed`` (ConvTranspose2d k4 s2 p1).
+    out_hw: output extent; derived from ``pad`` (top, left; assumed symmetric) when omitted.
+          efficientnet_pytorch's static "same" padding is asymmetric, so it passes out_hw.
+    Returns (geometry, packed weights bf16 [phases, n_tiles_n*BN, Ktot]).
+    """
+    w = weight.detach().to(torch.float32).cpu()
+    any_up = any(up for _, up in srcs)
+    N = srcs[0][0][0]
+    if transposed:
+        assert len(srcs) == 1 and groups == 1 and tuple(w.shape[2:]) == (4, 4) and not any_up
+        (_, H, W, cin, _), _ = srcs[0]
+        assert w.shape[0] == cin
+        phases, Hq, Wq, out_H, out_W = 4, H, W, 2 * H, 2 * W
+        macs = N * H * W * cin * w.shape[1] * 16
+    else:
+        cout, cin_g, kh, kw = w.shape
+        cin_total = sum(s[3] for s, _ in srcs)
+        assert cin_g * groups == cin_total, (tuple(w.shape), groups, cin_total)
+        if any_up:
+            assert (kh, kw) == (3, 3) and stride == 1 and tuple(pad) == (1, 1) and groups == 1
+            up_src = next(s for s, up in srcs if up)
+            out_H, out_W = 2 * up_src[1], 2 * up_src[2]
+            for s, up in srcs:
+                assert (s[1], s[2]) == ((out_H // 2, out_W // 2) if up else (out_H, out_W)), 'source extent mismatch'
+            phases, Hq, Wq = 4, out_H // 2, out_W // 2
+        else:
+            (_, H, W, _, _), _ = srcs[0]
+            if out_hw is None:
+                out_hw = ((H + 2 * pad[0] - kh) // stride + 1, (W + 2 * pad[1] - kw) // stride + 1)
+            out_H, out_W = out_hw
+            phases, Hq, Wq = 1, out_H, out_W
+        macs = N * out_H * out_W * cout * cin_g * kh * kw
+    return _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, tuple(pad), groups, transposed, out_bf16, macs)
+
+
+def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transposed, out_bf16, macs):
+    cout = w.shape[1] if transposed else w.shape[0]
+    cout_w = pad8(cout) if out_bf16 else cout          # channels the kernel writes
+    TH, TW = choose_tile(Hq, Wq)
+    if groups > 1:
+        assert len(srcs) == 1 and phases == 1
+        cout_g = cout // groups
+        assert cout_g % 8 == 0, 'grouped conv needs cout/groups % 8 == 0'
+        n_tiles_n, BN, cout_per_tile = groups, (cout_g + 15) // 16 * 16, cout_g
+    else:
+        n_tiles_n, BN = choose_bn(max(cout_w, 16))
+        cout_per_tile = BN
+    rows = n_tiles_n * BN
+
+    segs: List[SegSpec] = []
+    blocks: List[List[torch.Tensor]] = [[] for _ in range(phases)]  # per phase: K column blocks [rows, 64]
+    c_lo = 0
+    for (sN, sH, sW, sC, ldc), up in srcs:
+        assert sN == N
+        if transposed:
+            seg = SegSpec(N, sH, sW, sC, ldc, 2, 2, 1, (-1, 0), (-1, 0), 0, -(-sC // KC))
+        elif up:
+            seg = SegSpec(N, sH, sW, sC, ldc, 2, 2, 1, (-1, 0), (-1, 0), 0, -(-sC // KC))
+        elif phases == 4:
+            # full-resolution skip tensor seen from the half-resolution tile grid
+            seg = SegSpec(N, sH, sW, sC, ldc, 3, 3, 2, (-1, 0), (-1, 0), 0, -(-sC // KC))
+        else:
+            kh, kw = w.shape[2], w.shape[3]
+            cg = sC // groups
+            seg = SegSpec(N, sH, sW, sC, ldc, kh, kw, stride, (-pad[0], -pad[0]), (-pad[1], -pad[1]),
+                          cg if groups > 1 else 0, -(-(cg if groups > 1 else sC) // KC))
+        segs.append(seg)
+
+        for phase in range(phases):
+            ph, pw = phase >> 1, phase & 1
+            for ty in range(seg.kh):
+                for tx in range(seg.kw):
+                    # effective [cout, sC_slice] weight of this tap for this phase
+                    if transposed:
+                        wt = w[:, :, 3 - ph - 2 * ty, 3 - pw - 2 * tx].t()          # [cout, cin]
+                    elif up:
+                        khs, kws = _phase_tap_groups(ph, ty), _phase_tap_groups(pw, tx)
+                        wt = w[:, c_lo:c_lo + sC][:, :, khs][:, :, :, kws].sum(dim=(2, 3))
+                    elif groups > 1:
+                        wt = w[:, :, ty, tx]                                         # [cout, cin_g]
+                    else:
+                        wt = w[:, c_lo:c_lo + sC, ty, tx]
+                    for cc in range(seg.cchunks):
+                        blk = torch.zeros(rows, KC)
+                        if groups > 1:
+                            cg, cout_g = sC // groups, cout // groups
+                            lo, hi = cc * KC, min((cc + 1) * KC, cg)
+                            for g in range(groups):
+                                blk[g * BN:g * BN + cout_g, :hi - lo] = wt[g * cout_g:(g + 1) * cout_g, lo:hi]
+                        else:
+                            lo, hi = cc * KC, min((cc + 1) * KC, sC)
+                            blk[:cout, :hi - lo] = wt[:, lo:hi]
+                        blocks[phase].append(blk)
+        c_lo += sC
+    packed = torch.stack([torch.cat(b, dim=1) for b in blocks]).to(torch.bfloat16).contiguous()
+    Ktot = packed.shape[2]
+    geom = ConvGeom(segs, phases, N, Hq, Wq, TH, TW, BN, n_tiles_n, cout_per_tile, cout_w, Ktot, out_H, out_W,
+                    macs)
+    return geom, packed
+
+
+def pad_bias(bias: Optional[torch.Tensor], geom: ConvGeom, cout: int, groups: int = 1) -> torch.Tensor:
+    """fp32 bias laid out like the packed weight rows: [n_tiles_n * BN], zero padded."""
+    out = torch.zeros(geom.n_tiles_n * geom.BN, dtype=torch.float32)
+    if bias is not None:
+        b = bias.detach().to(torch.float32).cpu()
+        if groups > 1:
+            cg = cout // groups
+            for g in range(groups):
+                out[g * geom.BN:g * geom.BN + cg] = b[g * cg:(g + 1) * cg]
+        else:
+            out[:cout] = b
+    return out
+
+
+class ConvPlan:
+    """Device-resident plan: packed weights + bias + the C-side TMA/launch plan."""
+
+    def __init__(self, geom: ConvGeom, packed: torch.Tensor, bias: torch.Tensor, seg_tensors: Sequence[torch.Tensor],
+                 out: torch.Tensor, out_mode: str = 'bf16_nhwc', act: str = 'none',
+                 res: Optional[torch.Tensor] = None, res_mode: str = 'none', out_c_off: int = 0,
+                 per_image_weights: bool = False, name: str = ''):
+        lib = _lib.load()
+        dev = out.device
+        self.geom, self.name = geom, name
+        self.weight = packed.to(dev) if packed.device != dev else packed
+        self.bias = bias.to(dev)
+        self.keep = (list(seg_tensors), out, res)  # keep buffers alive as long as the plan
+        d = _lib.ConvDesc()
+        d.nseg = len(geom.segs)
+        for i, (sg, t) in enumerate(zip(geom.segs, seg_tensors)):
+            s = d.seg[i]
+            s.ptr = t.data_ptr()
+            s.N, s.H, s.W, s.C, s.ldc = sg.N, sg.H, sg.W, sg.C, sg.ldc
+            s.kh, s.kw, s.mul = sg.kh, sg.kw, sg.mul
+            s.off_h[0], s.off_h[1] = sg.off_h
+            s.off_w[0], s.off_w[1] = sg.off_w
+            s.c_per_tile, s.cchunks = sg.c_per_tile, sg.cchunks
+        d.phases, d.N, d.Hq, d.Wq, d.TH, d.TW = geom.phases, geom.N, geom.Hq, geom.Wq, geom.TH, geom.TW
+        d.BN, d.n_tiles_n, d.cout_per_tile, d.Cout = geom.BN, geom.n_tiles_n, geom.cout_per_tile, geom.Cout
+        d.weight, d.Ktot, d.per_image_weights = self.weight.data_ptr(), geom.Ktot, int(per_image_weights)
+        d.bias = self.bias.data_ptr()
+        d.act, d.res_mode = _lib.ACT[act], _lib.RES[res_mode]
+        d.res = res.data_ptr() if res is not None else None
+        d.res_ldc = res.shape[-1] if res is not None else 0
+        d.out, d.out_mode = out.data_ptr(), _lib.OUT[out_mode]
+        d.out_H, d.out_W = geom.out_H, geom.out_W
+        d.out_ldc = out.shape[-1] if out_mode == 'bf16_nhwc' else out.shape[1]
+        d.out_c_off = out_c_off
+        handle = C.c_void_p()
+        _lib.check(lib.octseg_conv_plan_create(C.byref(d), C.byref(handle)), f'conv_plan_create({name})')
+        self._lib, self._h = lib, handle
+
+    def run(self, stream: Optional[int] = None) -> None:
+        _lib.check(self._lib.octseg_conv_run(self._h, stream if stream is not None else _lib.stream_ptr()),
+                   f'conv_run({self.name})')
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            self._lib.octseg_conv_plan_destroy(h)
+            self._h = None

@@ -1,0 +1,51 @@
+"""CPU: the host planner's packed weights + K-segments reproduce torch's un-fused op sequence
+when walked exactly as the kernel walks them (tests/conv_cases.emulate)."""
+import pytest
+import torch
+
+from oct_segmentation_b200.engine import conv as C
+from tests.conv_cases import CASES, emulate, make_inputs, out_hw, reference
+
+
+def to_nhwc_padded(x):
+    n, c, h, w = x.shape
+    out = torch.zeros(n, h, w, C.pad8(c))
+    out[..., :c] = x.permute(0, 2, 3, 1)
+    return out
+
+
+def plan_case(case, xs, w):
+    srcs = [((case.N, s[1], s[2], s[0], C.pad8(s[0])), s[3]) for s in case.srcs]
+    return C.plan_conv(srcs, w, out_hw=None if (case.transposed or any(s[3] for s in case.srcs)) else out_hw(case),
+                       stride=case.stride, pad=case.pad, groups=case.groups, transposed=case.transposed,
+                       out_bf16=case.out_mode == 'bf16_nhwc')
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: c.name)
+def test_emulated_kernel_matches_torch(case):
+    xs, w, b, res = make_inputs(case)
+    geom, packed = plan_case(case, xs, w)
+    assert geom.TH * geom.TW <= 128 and geom.BN % 16 == 0 and 16 <= geom.BN <= 256
+    assert packed.shape == (geom.phases, geom.n_tiles_n * geom.BN, geom.Ktot)
+    bias_rows = C.pad_bias(b, geom, case.cout, case.groups)
+    xs_nhwc = [x.permute(0, 2, 3, 1).contiguous() for x in xs]
+    res_nhwc = to_nhwc_padded(res) if res is not None else None
+    act = case.act
+    got = emulate(geom, packed, bias_rows, xs_nhwc, act, res_nhwc, case.res_mode)
+    want = reference(case, xs, w, b, res)
+    if case.out_mode == 'u8_nchw':
+        want = reference(case.__class__(**{**case.__dict__, 'out_mode': 'f32_nchw'}), xs, w, b, res)
+    got_nchw = got[..., :case.cout].permute(0, 3, 1, 2)
+    err = (got_nchw - want).norm() / want.norm().clamp_min(1e-6)
+    assert err < 6e-3, f'{case.name}: rel-L2 {err:.3e}'   # only the weights' bf16 rounding differs
+    if geom.Cout > case.cout:                              # pad channels stay zero
+        assert got[..., case.cout:].abs().max() == 0
+
+
+def test_tile_and_bn_choice():
+    assert C.choose_tile(128, 128) == (1, 128)
+    th, tw = C.choose_tile(28, 28)
+    assert th * tw <= 128 and 28 % tw == 0
+    for cout in (16, 64, 168, 392, 784, 1624, 2048, 24):
+        n, bn = C.choose_bn(cout)
+        assert bn % 16 == 0 and bn <= 256 and n * bn >= cout
