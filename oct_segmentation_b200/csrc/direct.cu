@@ -327,13 +327,16 @@ extern "C" int octseg_stem_conv(const void* in, int32_t in_dtype, int64_t sn, in
   const size_t smem = (static_cast<size_t>(k) * k * 3 * Cout + static_cast<size_t>(pdim) * pdim * 3) * sizeof(float);
   dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (Cout == 64) {
+  static bool attr_set = false;  // once per process; not a stream operation, keep it out of graph capture
+  if (!attr_set) {
     OCTSEG_CUDA(cudaFuncSetAttribute(stem_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    stem_conv_kernel<64><<<grid, 256, smem, st>>>(p);
-  } else {
     OCTSEG_CUDA(cudaFuncSetAttribute(stem_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    stem_conv_kernel<32><<<grid, 256, smem, st>>>(p);
+    attr_set = true;
   }
+  if (Cout == 64)
+    stem_conv_kernel<64><<<grid, 256, smem, st>>>(p);
+  else
+    stem_conv_kernel<32><<<grid, 256, smem, st>>>(p);
   return check_launch("stem_conv_kernel");
 }
 

@@ -1,0 +1,179 @@
+"""Op-list builder: turns layer calls into device buffers + C-ABI launches.
+
+A ``Builder`` is used once per (network, batch, resolution, input dtype): lowering code
+(engine/lower.py) calls ``conv`` / ``stem`` / ``maxpool`` / ``dwconv`` / ``se_project`` in
+network order; each call allocates its output activation (NHWC bf16), creates whatever plan the
+kernel needs and appends a closure to ``ops``.  ``run()`` replays the list on the current
+stream; ``CompiledNet`` (engine/network.py) captures that replay in a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib
+from .conv import Act, ConvPlan, pad8, pad_bias, plan_conv
+
+
+def fold_bn(w: torch.Tensor, bn: Optional[torch.nn.BatchNorm2d], conv_bias: Optional[torch.Tensor] = None,
+            out_dim: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm folded into the preceding conv in fp32:
+    w' = w*g/sqrt(v+eps);  b' = (b - mean)*g/sqrt(v+eps) + beta."""
+    w = w.detach().float().cpu()
+    cout = w.shape[out_dim]
+    b = conv_bias.detach().float().cpu() if conv_bias is not None else torch.zeros(cout)
+    if bn is None:
+        return w, b
+    scale = bn.weight.detach().float().cpu() / torch.sqrt(bn.running_var.detach().float().cpu() + bn.eps)
+    shape = [1] * w.dim()
+    shape[out_dim] = cout
+    return w * scale.view(shape), (b - bn.running_mean.detach().float().cpu()) * scale + bn.bias.detach().float().cpu()
+
+
+class Builder:
+    def __init__(self, device: torch.device, N: int):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.N = N
+        self.ops: List[Callable[[], None]] = []
+        self.op_names: List[str] = []
+        self.macs = 0              # algorithmic MACs of the reference graph (dense count)
+        self.tc_launches = 0
+        self.launches = 0
+        self.act_bytes = 0
+        self._keep: List[object] = []
+
+    # ------------------------------------------------------------------ buffers
+    def new_act(self, H: int, W: int, C: int) -> Act:
+        t = torch.zeros(self.N, H, W, pad8(C), dtype=torch.bfloat16, device=self.device)
+        self.act_bytes += t.numel() * 2
+        return Act(t, C)
+
+    def _add(self, name: str, fn: Callable[[], None]) -> None:
+        self.ops.append(fn)
+        self.op_names.append(name)
+        self.launches += 1
+
+    def run(self) -> None:
+        for op in self.ops:
+            op()
+
+    # ------------------------------------------------------------------ tensor-core conv
+    def conv(self, srcs: Sequence[Tuple[Act, bool]], w: torch.Tensor, b: Optional[torch.Tensor], *, name: str,
+             stride: int = 1, pad: Tuple[int, int] = (0, 0), groups: int = 1, transposed: bool = False,
+             act: str = 'none', res: Optional[Act] = None, res_mode: str = 'none',
+             out_hw: Optional[Tuple[int, int]] = None, out_mode: str = 'bf16_nhwc',
+             out_tensor: Optional[torch.Tensor] = None) -> Optional[Act]:
+        spec = [((a.N, a.H, a.W, a.C, a.Cp), up) for a, up in srcs]
+        geom, packed = plan_conv(spec, w, out_hw=out_hw, stride=stride, pad=pad, groups=groups,
+                                 transposed=transposed, out_bf16=(out_mode == 'bf16_nhwc'))
+        cout = w.shape[1] if transposed else w.shape[0]
+        bias_rows = pad_bias(b, geom, cout, groups)
+        out_act = None
+        if out_mode == 'bf16_nhwc':
+            out_act = self.new_act(geom.out_H, geom.out_W, cout)
+            out_t = out_act.t
+        else:
+            out_t = out_tensor
+            assert out_t is not None and tuple(out_t.shape) == (self.N, cout, geom.out_H, geom.out_W)
+        plan = ConvPlan(geom, packed, bias_rows, [a.t for a, _ in srcs], out_t, out_mode=out_mode, act=act,
+                        res=res.t if res is not None else None, res_mode=res_mode, name=name)
+        self._keep.append(plan)
+        self.macs += geom.macs
+        self.tc_launches += 1
+        self._add(name, plan.run)
+        return out_act
+
+    # ------------------------------------------------------------------ CUDA-core kernels
+    def stem(self, x: torch.Tensor, in_dtype: str, w: torch.Tensor, b: torch.Tensor, *, name: str, k: int,
+             stride: int, pad: Tuple[int, int], out_hw: Tuple[int, int], act: str,
+             mean: Optional[Sequence[float]] = None, std: Optional[Sequence[float]] = None) -> Act:
+        """x: logical (N,3,H,W) view of the static input buffer (any strides)."""
+        N, _, H, W = x.shape
+        cout = w.shape[0]
+        out = self.new_act(out_hw[0], out_hw[1], cout)
+        wk = w.detach().float().permute(2, 3, 1, 0).contiguous().to(self.device)   # [kh][kw][3][Cout]
+        bk = b.detach().float().contiguous().to(self.device)
+        sn, sc, sh, sw = x.stride()
+        mean_a = (C.c_float * 3)(*mean) if mean is not None else None
+        istd_a = (C.c_float * 3)(*[1.0 / s for s in std]) if std is not None else None
+        self._keep += [wk, bk, x]
+        lib, dt = self.lib, {'f32': 0, 'u8': 1}[in_dtype]
+        a = _lib.ACT[act]
+
+        def op():
+            _lib.check(lib.octseg_stem_conv(x.data_ptr(), dt, sn, sc, sh, sw, N, H, W, wk.data_ptr(), bk.data_ptr(),
+                                            cout, k, stride, pad[0], pad[1], out_hw[0], out_hw[1], a, mean_a, istd_a,
+                                            out.t.data_ptr(), out.Cp, _lib.stream_ptr()), name)
+        self.macs += N * out_hw[0] * out_hw[1] * cout * 3 * k * k
+        self._add(name, op)
+        return out
+
+    def maxpool(self, x: Act, *, name: str) -> Act:
+        Ho, Wo = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
+        out = self.new_act(Ho, Wo, x.C)
+        lib = self.lib
+
+        def op():
+            _lib.check(lib.octseg_maxpool3x3s2(x.t.data_ptr(), out.t.data_ptr(), x.N, x.H, x.W, x.Cp, Ho, Wo,
+                                               _lib.stream_ptr()), name)
+        self._add(name, op)
+        return out
+
+    def dwconv(self, x: Act, w: torch.Tensor, b: torch.Tensor, *, name: str, k: int, stride: int,
+               pad: Tuple[int, int], out_hw: Tuple[int, int], act: str, pool: Optional[torch.Tensor]) -> Act:
+        assert x.C % 8 == 0
+        out = self.new_act(out_hw[0], out_hw[1], x.C)
+        wk = w.detach().float().reshape(x.C, k, k).permute(1, 2, 0).contiguous().to(self.device)  # [kh][kw][C]
+        bk = b.detach().float().contiguous().to(self.device)
+        self._keep += [wk, bk]
+        lib, a = self.lib, _lib.ACT[act]
+
+        def op():
+            if pool is not None:
+                pool.zero_()
+            _lib.check(lib.octseg_dwconv(x.t.data_ptr(), wk.data_ptr(), bk.data_ptr(), out.t.data_ptr(), x.N, x.H,
+                                         x.W, x.C, k, stride, pad[0], pad[1], out_hw[0], out_hw[1], a,
+                                         pool.data_ptr() if pool is not None else None, _lib.stream_ptr()), name)
+        self.macs += x.N * out_hw[0] * out_hw[1] * x.C * k * k
+        self._add(name, op)
+        return out
+
+    def se_project(self, x: Act, pool: torch.Tensor, w1, b1, w2, b2, wp: torch.Tensor, bp: torch.Tensor, *,
+                   name: str, res: Optional[Act]) -> Act:
+        """Squeeze-excite gate folded into the projection 1x1: per-image weights
+        bf16(w[:, k] * gate[n, k]) feed the tensor-core conv (octseg_scale_weights)."""
+        N, C_mid, cr = x.N, x.C, w1.shape[0]
+        dev = self.device
+        w1d = w1.detach().float().reshape(cr, C_mid).contiguous().to(dev)
+        b1d = b1.detach().float().contiguous().to(dev)
+        w2d = w2.detach().float().reshape(C_mid, cr).contiguous().to(dev)
+        b2d = b2.detach().float().contiguous().to(dev)
+        gate = torch.empty(N, C_mid, dtype=torch.float32, device=dev)
+        spec = [((N, x.H, x.W, x.C, x.Cp), False)]
+        geom, packed32 = plan_conv(spec, wp, out_hw=(x.H, x.W), packed_dtype=torch.float32)
+        rows, Ktot = packed32.shape[1], packed32.shape[2]
+        base = packed32[0].contiguous().to(dev)                                    # fp32 [rows][Ktot]
+        wn = torch.zeros(N, rows, Ktot, dtype=torch.bfloat16, device=dev)
+        cout = wp.shape[0]
+        out = self.new_act(x.H, x.W, cout)
+        plan = ConvPlan(geom, wn, pad_bias(bp, geom, cout), [x.t], out.t, act='none',
+                        res=res.t if res is not None else None, res_mode='before_act' if res is not None else 'none',
+                        per_image_weights=True, name=name)
+        self._keep += [plan, w1d, b1d, w2d, b2d, gate, base, wn]
+        lib, inv_hw = self.lib, 1.0 / float(x.H * x.W)
+
+        def op():
+            st = _lib.stream_ptr()
+            _lib.check(lib.octseg_se_gate(pool.data_ptr(), inv_hw, w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(),
+                                          b2d.data_ptr(), gate.data_ptr(), N, C_mid, cr, st), name + '.se_gate')
+            _lib.check(lib.octseg_scale_weights(base.data_ptr(), gate.data_ptr(), wn.data_ptr(), N, rows, Ktot,
+                                                C_mid, st), name + '.scale_weights')
+            plan.run(st)
+        self.macs += geom.macs + N * 2 * C_mid * cr
+        self.tc_launches += 1
+        self._add(name, op)
+        self.launches += 2
+        return out

@@ -3,7 +3,7 @@
 Turns a layer description (sources of the fused concat, folded fp32 weights, geometry) into
 the explicit K-segment / tile / packed-weight form that ``octseg_conv_plan_create`` consumes
 (include/octseg.h).  Everything here is shape arithmetic + weight re-layout and runs on CPU;
-``ConvPlan.materialize`` uploads the packed weights and creates the device plan.
+``ConvPlan`` uploads the packed weights and creates the device plan.
 
 Replaces (reference call sites src/models/smp/model.py:70,192): conv2d / conv_transpose2d +
 folded BatchNorm + activation (+ nearest-x2 upsample, channel concat, residual add) of the
@@ -108,7 +108,8 @@ def _phase_tap_groups(ph: int, a: int) -> List[int]:
 
 def plan_conv(srcs: Sequence[Tuple[Tuple[int, int, int, int, int], bool]], weight: torch.Tensor,
               out_hw: Optional[Tuple[int, int]] = None, stride: int = 1, pad: Tuple[int, int] = (0, 0),
-              groups: int = 1, transposed: bool = False, out_bf16: bool = True) -> Tuple[ConvGeom, torch.Tensor]:
+              groups: int = 1, transposed: bool = False, out_bf16: bool = True,
+              packed_dtype: torch.dtype = torch.bfloat16) -> Tuple[ConvGeom, torch.Tensor]:
     """Plan one conv.
 
     srcs: [((N, H, W, C, ldc), upsampled)] in concat order; ``upsampled`` sources are at half the
@@ -146,10 +147,12 @@ def plan_conv(srcs: Sequence[Tuple[Tuple[int, int, int, int, int], bool]], weigh
             out_H, out_W = out_hw
             phases, Hq, Wq = 1, out_H, out_W
         macs = N * out_H * out_W * cout * cin_g * kh * kw
-    return _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, tuple(pad), groups, transposed, out_bf16, macs)
+    return _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, tuple(pad), groups, transposed, out_bf16, macs,
+                 packed_dtype)
 
 
-def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transposed, out_bf16, macs):
+def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transposed, out_bf16, macs,
+          packed_dtype=torch.bfloat16):
     cout = w.shape[1] if transposed else w.shape[0]
     cout_w = pad8(cout) if out_bf16 else cout          # channels the kernel writes
     TH, TW = choose_tile(Hq, Wq)
@@ -208,7 +211,7 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
                             blk[:cout, :hi - lo] = wt[:, lo:hi]
                         blocks[phase].append(blk)
         c_lo += sC
-    packed = torch.stack([torch.cat(b, dim=1) for b in blocks]).to(torch.bfloat16).contiguous()
+    packed = torch.stack([torch.cat(b, dim=1) for b in blocks]).to(packed_dtype).contiguous()
     Ktot = packed.shape[2]
     geom = ConvGeom(segs, phases, N, Hq, Wq, TH, TW, BN, n_tiles_n, cout_per_tile, cout_w, Ktot, out_H, out_W,
                     macs)

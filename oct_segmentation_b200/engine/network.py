@@ -1,0 +1,74 @@
+"""CompiledNet: one network lowered for a fixed (batch, H, W, input dtype) on one GPU.
+
+Owns the static input buffer, every activation buffer, the packed weights and the kernel
+plans; the op list is captured once into a CUDA graph and replayed per batch.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib
+from .builder import Builder
+from .lower import DECODER_LOWERING, ENCODER_LOWERING, lower_head
+
+
+class CompiledNet:
+    def __init__(self, model, N: int, H: int, W: int, device, in_dtype: str = 'f32', out_mode: str = 'f32_nchw',
+                 norm: Optional[Tuple[Sequence[float], Sequence[float]]] = None, use_graph: bool = True):
+        if H % 32 or W % 32:
+            raise RuntimeError(f'Wrong input shape height={H}, width={W}. Expected image height and width '
+                               f'divisible by 32.')
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.OctsegError('the octseg engine runs on CUDA (sm_100a) only; there is no CPU path')
+        _lib.load()
+        self.N, self.H, self.W, self.in_dtype, self.out_mode = N, H, W, in_dtype, out_mode
+        classes = model.segmentation_head[0].out_channels
+        with torch.cuda.device(self.device):
+            # static input, stored NHWC; the stem reads it through a logical NCHW view
+            dt = torch.float32 if in_dtype == 'f32' else torch.uint8
+            self.x_nhwc = torch.zeros(N, H, W, 3, dtype=dt, device=self.device)
+            x_view = self.x_nhwc.permute(0, 3, 1, 2)
+            odt = torch.float32 if out_mode == 'f32_nchw' else torch.uint8
+            self.out = torch.zeros(N, classes, H, W, dtype=odt, device=self.device)
+            b = Builder(self.device, N)
+            feats = ENCODER_LOWERING[model.encoder.kind](b, model.encoder, x_view, in_dtype, norm)
+            y = DECODER_LOWERING[model.decoder.kind](b, model.decoder, feats)
+            lower_head(b, model.segmentation_head, y, self.out, out_mode)
+            self.feats, self.dec_out = feats, y        # kept for per-stage parity diagnostics
+        self.builder = b
+        self.macs = b.macs
+        self.launches = b.launches
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = use_graph
+
+    def _capture(self) -> None:
+        with torch.cuda.device(self.device):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.builder.run()                     # warm-up: one-time attribute setup happens here
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.builder.run()
+            self.graph = g
+
+    def run(self) -> torch.Tensor:
+        """Execute on the current contents of ``x_nhwc``; returns the static output buffer."""
+        with torch.cuda.device(self.device):
+            if self.use_graph:
+                if self.graph is None:
+                    self._capture()
+                self.graph.replay()
+            else:
+                self.builder.run()
+        return self.out
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """x: logical NCHW (any strides) of the compiled shape/dtype."""
+        self.x_nhwc.copy_(x.permute(0, 2, 3, 1), non_blocking=True)
+        return self.run()

@@ -1,0 +1,139 @@
+"""ORACLE-side synthetic data (test / bench infrastructure): deterministic OCT-like frames and
+seeded synthetic checkpoints with calibrated BatchNorm statistics.
+
+The reference's trained weights (models/{LM,FC_LC,VV}.dvc) and dataset are not available
+(SURVEY.md §0), so parity and throughput are measured on these.  Frame statistics follow the
+real demo frames (/root/reference/data/demo/input: sepia RGB, circular field of view with ~21.5 %
+zeros outside it); generator per SURVEY.md §8d.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import model_ref, smp_ref
+
+FRAME_SEED = 20251018
+
+# the three shipped networks (eval/training/*/fold_1/config.json in the reference)
+MODEL_CONFIGS = {
+    'LM': {'model_name': 'UnetPlusPlus_resnet101', 'architecture': 'UnetPlusPlus', 'encoder': 'resnet101',
+           'input_size': 512, 'classes': ['Lumen']},
+    'FC_LC': {'model_name': 'LinkNet_efficientnet-b7', 'architecture': 'LinkNet', 'encoder': 'efficientnet-b7',
+              'input_size': 896, 'classes': ['Fibrous cap', 'Lipid core']},
+    'VV': {'model_name': 'Unet_timm-regnetx_064', 'architecture': 'Unet', 'encoder': 'timm-regnetx_064',
+           'input_size': 896, 'classes': ['Vasa vasorum']},
+}
+MODEL_SEEDS = {'LM': 1000, 'FC_LC': 1001, 'VV': 1002}
+
+
+def synthetic_frame(idx: int, size: int = 512) -> np.ndarray:
+    """uint8 RGB (size, size, 3) OCT-like frame, deterministic in ``idx``."""
+    rng = np.random.Generator(np.random.PCG64(FRAME_SEED + idx))
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32)
+    c = (size - 1) / 2.0
+    dx, dy = xx - c, yy - c
+    r = np.sqrt(dx * dx + dy * dy) / size          # 0 .. ~0.7
+    th = np.arctan2(dy, dx)
+    # lumen boundary with low-order angular harmonics
+    r_l = rng.uniform(0.15, 0.30)
+    bound = r_l * np.ones_like(r)
+    for k in range(1, 4):
+        bound += rng.uniform(0.0, 0.03) * np.cos(k * th + rng.uniform(0, 2 * np.pi))
+    inten = np.zeros_like(r)
+    wall = r >= bound
+    inten[wall] = (200.0 * np.exp(-(r[wall] - bound[wall]) / rng.uniform(0.05, 0.12)))
+    inten += 15.0 * (r < bound)                      # blood-free lumen: faint
+    ring = np.abs(r - 0.05) < 0.006                   # catheter ring
+    inten[ring] = 230.0
+    # dark lipid wedge and bright vessel blobs
+    if rng.random() < 0.7:
+        a0, aw = rng.uniform(-np.pi, np.pi), rng.uniform(0.3, 1.2)
+        wedge = (np.abs(np.angle(np.exp(1j * (th - a0)))) < aw / 2) & (r > bound + 0.03) & (r < bound + 0.18)
+        inten[wedge] *= 0.25
+    for _ in range(int(rng.integers(0, 4))):
+        ba, br = rng.uniform(-np.pi, np.pi), rng.uniform(0.32, 0.45)
+        bx, by = c + br * size * np.cos(ba), c + br * size * np.sin(ba)
+        blob = (xx - bx) ** 2 + (yy - by) ** 2 < (rng.uniform(0.008, 0.02) * size) ** 2
+        inten[blob] = 180.0
+    speckle = rng.rayleigh(scale=0.8, size=r.shape).astype(np.float32)
+    inten = inten * speckle
+    inten[r > 0.5] = 0.0                              # circular field of view
+    inten = np.clip(inten, 0, 255)
+    rgb = np.stack([inten, 0.45 * inten, 0.08 * inten], axis=-1)
+    return rgb.astype(np.uint8)
+
+
+def synthetic_frames(start: int, count: int, size: int = 512) -> np.ndarray:
+    return np.stack([synthetic_frame(start + i, size) for i in range(count)])
+
+
+def _randomize_bn(model: nn.Module, gen: torch.Generator) -> None:
+    """BN affine: gamma ~ U(0.5, 1.5), beta ~ N(0, 0.1); the LAST BatchNorm of every residual
+    branch gets gamma ~ U(0.1, 0.3).  A randomly initialised BN network is chaotic (perturbations
+    grow exponentially with depth), which no trained checkpoint is; damped residual branches
+    (cf. zero-init-residual, which timm applies to RegNet) give a well-conditioned stand-in that
+    still exercises every layer."""
+    last = set()
+    for name, m in model.named_modules():
+        cls = type(m).__name__
+        if cls == 'Bottleneck' and hasattr(m, 'bn3'):
+            last.add(name + '.bn3')
+        elif cls == 'BasicBlock':
+            last.add(name + '.bn2')
+        elif cls == 'RegNetBottleneck':
+            last.add(name + '.conv3.bn')
+        elif cls == 'MBConvBlock' and m.stride == 1 and m.cin == m.cout:
+            last.add(name + '._bn2')
+    for name, m in model.named_modules():
+        if isinstance(m, nn.BatchNorm2d):
+            with torch.no_grad():
+                g = torch.rand(m.weight.shape, generator=gen)
+                m.weight.copy_(g * 0.2 + 0.1 if name in last else g + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=gen) * 0.1)
+
+
+@torch.no_grad()
+def calibrate_bn(model: nn.Module, x: torch.Tensor) -> None:
+    """Set BN running statistics from a forward pass so activations stay O(1) through the net."""
+    saved = {}
+    for name, m in model.named_modules():
+        if isinstance(m, nn.BatchNorm2d):
+            saved[name] = m.momentum
+            m.reset_running_stats()
+            m.momentum = None  # cumulative average
+    model.train()
+    model(x)
+    model.eval()
+    for name, m in model.named_modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.momentum = saved[name]
+
+
+def make_model(key: str, calib_size: int = 128, calib_frames: int = 2, logit_gain: float = 1.0) -> model_ref.OCTSegmentationModelRef:
+    """Seeded synthetic checkpoint for 'LM' | 'FC_LC' | 'VV': library-default init, randomised BN
+    affine, BN statistics calibrated on synthetic frames (BGR, 0..255, un-normalised like predict())."""
+    cfg = MODEL_CONFIGS[key]
+    torch.manual_seed(MODEL_SEEDS[key])
+    m = model_ref.OCTSegmentationModelRef(arch=cfg['architecture'], encoder_name=cfg['encoder'],
+                                          model_name=cfg['model_name'], in_channels=3, classes=cfg['classes'],
+                                          encoder_weights=None)
+    gen = torch.Generator().manual_seed(MODEL_SEEDS[key] + 7)
+    _randomize_bn(m.model, gen)
+    frames = synthetic_frames(0, calib_frames, calib_size)[..., ::-1].copy()       # RGB -> BGR
+    x = torch.from_numpy(frames).permute(0, 3, 1, 2).float()
+    calibrate_bn(m.model, x)
+    if logit_gain != 1.0:
+        with torch.no_grad():
+            m.model.segmentation_head[0].weight.mul_(logit_gain)
+    m.eval()
+    return m
+
+
+def save_checkpoint(model: nn.Module, path: str) -> None:
+    """Same container as a pytorch_lightning .ckpt as far as inference reads it."""
+    torch.save({'state_dict': model.state_dict(), 'epoch': 0, 'global_step': 0,
+                'pytorch-lightning_version': '2.2.1'}, path)

@@ -1,0 +1,109 @@
+"""GPU parity of the three lowered networks (through the engine + C-ABI kernels) against the fp32
+PyTorch oracle on the same seeded synthetic checkpoint and frames.
+
+Two references on the same seeded synthetic checkpoint + frames:
+  (1) the engine's storage precision replayed with torch ops (tests/cpu_builder.Bf16Builder:
+      bf16 weights/activations, fp32 accumulate): kernels must match it to rel-L2 <= 1e-2 at the
+      logits -- this is the kernel-correctness bar;
+  (2) the fp32 oracle (oracle/smp_ref.py): logits rel-L2 <= 0.12.  The synthetic checkpoints are
+      BN-calibrated random networks, which amplify rounding noise far more than a trained net
+      (CPU simulation of pure bf16 storage gives 0.04-0.08); masks must agree on
+      every pixel whose |logit| exceeds 4x the measured logit RMS error.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oct_segmentation_b200.model import OCTSegmentationModel
+from oracle import synth
+from tests.cpu_builder import run_lowered
+
+pytestmark = pytest.mark.gpu
+
+SIZES = {'LM': 256, 'VV': 256, 'FC_LC': 256}
+
+
+def rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def build_pair(key):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = synth.make_model(key)
+    cfg = synth.MODEL_CONFIGS[key]
+    ours = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
+                                in_channels=3, classes=cfg['classes'], encoder_weights=None)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    return ref.cuda().eval(), ours.cuda().eval()
+
+
+def frames_bgr(n, size):
+    f = synth.synthetic_frames(100, n, size)[..., ::-1].copy()
+    return f
+
+
+@pytest.mark.parametrize('key', ['LM', 'VV', 'FC_LC'])
+def test_network_matches_oracle(key):
+    ref, ours = build_pair(key)
+    size = SIZES[key]
+    fr = frames_bgr(2, size)
+    x = torch.from_numpy(fr).cuda().permute(0, 3, 1, 2).float()          # NHWC-strided, like predict()
+    with torch.no_grad():
+        feats_ref = ref.model.encoder(x)
+        dec_ref = ref.model.decoder(*feats_ref)
+        want = ref.model.segmentation_head(dec_ref)
+        sim, sim_feats, sim_dec = run_lowered(ours.model, x, bf16=True, return_stages=True)
+        got = ours.model(x)
+    torch.cuda.synchronize()
+    net = ours.model.compiled(2, size, size, x.device, 'f32', 'f32_nchw')
+    rep32, rep16 = [], []
+    for i, (a, r, s) in enumerate(zip(net.feats, feats_ref[1:], sim_feats), start=1):
+        g = a.t[..., :a.C].permute(0, 3, 1, 2)
+        rep32.append(f'f{i}:{rel_l2(g, r):.1e}')
+        rep16.append(f'f{i}:{rel_l2(g, s):.1e}')
+    g = net.dec_out.t[..., :net.dec_out.C].permute(0, 3, 1, 2)
+    e32, e16 = rel_l2(got, want), rel_l2(got, sim)
+    rep32 += [f'dec:{rel_l2(g, dec_ref):.1e}', f'logits:{e32:.1e}']
+    rep16 += [f'dec:{rel_l2(g, sim_dec):.1e}', f'logits:{e16:.1e}']
+    print(f'\n{key} vs fp32 oracle : ' + ' '.join(rep32))
+    print(f'{key} vs bf16 replay : ' + ' '.join(rep16))
+    assert got.shape == want.shape and got.dtype == torch.float32
+    assert torch.isfinite(got).all()
+    assert e16 <= 1e-2, f'{key}: logits vs bf16-storage replay rel-L2 {e16:.3e} ({" ".join(rep16)})'
+    assert e32 <= 0.12, f'{key}: logits vs fp32 oracle rel-L2 {e32:.3e} ({" ".join(rep32)})'
+    rms = (got - want).pow(2).mean().sqrt()
+    conf = want.abs() > 4 * rms
+    assert conf.float().mean() > 0.5
+    agree = ((got > 0) == (want > 0))[conf].float().mean().item()
+    assert agree >= 0.9995, f'{key}: confident-pixel mask agreement {agree:.5f}'
+
+
+def test_forward_normalises_like_reference():
+    """OCTSegmentationModel.forward = (x - mean)/std then net (model.py:65-71)."""
+    ref, ours = build_pair('LM')
+    x = torch.from_numpy(frames_bgr(1, 128)).cuda().permute(0, 3, 1, 2).float()
+    with torch.no_grad():
+        want = ref(x)
+        got = ours(x)
+    assert rel_l2(got, want) <= 0.2       # off-calibration input scale: wiring check only (see test_lowering_cpu)
+
+
+def test_predict_matches_reference_predict():
+    """predict(): uint8 NHWC in, {0,1} float32 NHWC out, identical masks away from the zero crossing."""
+    ref, ours = build_pair('VV')
+    fr = frames_bgr(2, 128)
+    want = ref.predict(fr, 'cuda')
+    got = ours.predict(fr, 'cuda')
+    assert got.shape == want.shape == (2, 128, 128, 1) and got.dtype == np.float32
+    assert set(np.unique(got)) <= {0.0, 1.0}
+    with torch.no_grad():
+        logits = ref.model(torch.from_numpy(fr).cuda().permute(0, 3, 1, 2).float()).permute(0, 2, 3, 1).cpu().numpy()
+    conf = np.abs(logits) > 0.3 * logits.std()
+    assert (got[conf] == want[conf]).mean() >= 0.9995
+
+
+def test_shape_not_divisible_by_32_raises():
+    _, ours = build_pair('VV')
+    with pytest.raises(RuntimeError):
+        ours.model(torch.zeros(1, 3, 100, 128, device='cuda'))
