@@ -1,0 +1,163 @@
+"""Host side of the pre/post-processing kernels (csrc/prepost.cu): index/coefficient tables built
+with the exact arithmetic cv2 uses, and thin wrappers around the C-ABI calls.
+
+  preprocess   <- preprocessing_img, /root/reference/src/data/utils.py:159-166
+  postprocess  <- /root/reference/src/predict.py:92-100 (+ MODELS_META :23-28),
+                  src/data/utils.py:231-233 (priority merge), src/app/tools/analysis.py:199 (count)
+  quantities   <- src/app/tools/analysis.py:155,189,199-200 (ratio, presence, area)
+  thickness    <- src/app/tools/analysis.py:60-130 (radial scan)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from functools import lru_cache
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CLASS_NAMES = ['Lumen', 'Fibrous cap', 'Lipid core', 'Vasa vasorum']
+
+
+def linear_tables(src: int, dst: int) -> Tuple[np.ndarray, np.ndarray]:
+    """cv2.resize INTER_LINEAR tables for uint8: source index floor(fx) and 11-bit fixed-point
+    weights, fx = (float)((dx + 0.5) * (double)src/dst - 0.5); weights rounded half-to-even like
+    saturate_cast<short>.  Horizontal border handling (sx<0 / sx>=src-1 -> weight (2048, 0)) is
+    applied by `horizontal_tables`; the vertical pass clamps rows instead (as cv2 does)."""
+    scale = float(src) / float(dst)
+    fx = ((np.arange(dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+    sx = np.floor(fx).astype(np.int32)
+    fr = (fx - sx.astype(np.float32)).astype(np.float32)
+    a0 = np.rint((np.float32(1.0) - fr) * np.float32(2048.0)).astype(np.int16)
+    a1 = np.rint(fr * np.float32(2048.0)).astype(np.int16)
+    return sx, np.stack([a0, a1], axis=1)
+
+
+def horizontal_tables(src: int, dst: int) -> Tuple[np.ndarray, np.ndarray]:
+    sx, a = linear_tables(src, dst)
+    edge = (sx < 0) | (sx >= src - 1)
+    a = a.copy()
+    a[edge] = (2048, 0)
+    return np.clip(sx, 0, src - 1).astype(np.int32), a
+
+
+def nearest_table(src: int, dst: int) -> np.ndarray:
+    """cv2.resize INTER_NEAREST: min(floor(dx * (1 / ((double)dst/src))), src - 1)."""
+    inv = 1.0 / (float(dst) / float(src))
+    return np.minimum(np.floor(np.arange(dst, dtype=np.float64) * inv).astype(np.int64), src - 1).astype(np.int32)
+
+
+@lru_cache(maxsize=64)
+def _resize_luts(Hs: int, Ws: int, S: int, device: str):
+    xo, xa = horizontal_tables(Ws, S)
+    yo, yb = linear_tables(Hs, S)
+    dev = torch.device(device)
+    return (torch.from_numpy(xo).to(dev), torch.from_numpy(xa.reshape(-1)).to(dev),
+            torch.from_numpy(yo).to(dev), torch.from_numpy(yb.reshape(-1)).to(dev))
+
+
+@lru_cache(maxsize=64)
+def _nearest_lut(S: int, Ho: int, Wo: int, device: str) -> torch.Tensor:
+    lut = np.concatenate([nearest_table(S, Ho), nearest_table(S, Wo)])
+    return torch.from_numpy(lut).to(torch.device(device))
+
+
+@lru_cache(maxsize=4)
+def _cos_sin(device: str) -> torch.Tensor:
+    cs = [math.cos(math.radians(a)) for a in range(360)] + [math.sin(math.radians(a)) for a in range(360)]
+    return torch.tensor(cs, dtype=torch.float64, device=torch.device(device))
+
+
+def preprocess(frames_rgb: torch.Tensor, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """frames_rgb: uint8 CUDA tensor (N, Hs, Ws, 3) -> uint8 (N, S, S, 3) BGR, bit-exact vs
+    cv2.resize(cv2.cvtColor(img, COLOR_RGB2BGR), (S, S))."""
+    assert frames_rgb.is_cuda and frames_rgb.dtype == torch.uint8 and frames_rgb.is_contiguous()
+    N, Hs, Ws, _ = frames_rgb.shape
+    if out is None:
+        out = torch.empty(N, S, S, 3, dtype=torch.uint8, device=frames_rgb.device)
+    lib = _lib.load()
+    area2x = int(Hs == 2 * S and Ws == 2 * S)
+    xo, xa, yo, yb = _resize_luts(Hs, Ws, S, str(frames_rgb.device))
+    with torch.cuda.device(frames_rgb.device):
+        _lib.check(lib.octseg_preprocess_resize_bgr(frames_rgb.data_ptr(), N, Hs, Ws, out.data_ptr(), S,
+                                                    xo.data_ptr(), xa.data_ptr(), yo.data_ptr(), yb.data_ptr(),
+                                                    area2x, _lib.stream_ptr()), 'preprocess_resize_bgr')
+    return out
+
+
+def postprocess(planes: Dict[int, torch.Tensor], order: Sequence[int], Ho: int, Wo: int, N: int, device,
+                mask: Optional[torch.Tensor] = None, label: Optional[torch.Tensor] = None,
+                counts: Optional[torch.Tensor] = None):
+    """planes[c]: uint8 CUDA (N, S_c, S_c) {0,1} plane feeding mask channel c (= class id - 1).
+    order: class channel indices in cfg.classes order (later wins in the label map).
+    Returns (mask uint8 [N,Ho,Wo,4], label uint8 [N,Ho,Wo], counts int32 [N,4])."""
+    dev = torch.device(device)
+    lib = _lib.load()
+    if mask is None:
+        mask = torch.empty(N, Ho, Wo, 4, dtype=torch.uint8, device=dev)
+    if label is None:
+        label = torch.empty(N, Ho, Wo, dtype=torch.uint8, device=dev)
+    if counts is None:
+        counts = torch.zeros(N, 4, dtype=torch.int32, device=dev)
+    else:
+        counts.zero_()
+    chan = (C.c_void_p * 4)()
+    luts = (C.c_void_p * 4)()
+    sizes = (C.c_int32 * 4)()
+    keep = []
+    for c in range(4):
+        p = planes.get(c)
+        if p is None:
+            chan[c], luts[c], sizes[c] = None, None, 0
+            continue
+        assert p.is_cuda and p.dtype == torch.uint8 and p.is_contiguous() and p.shape[0] == N and p.shape[1] == p.shape[2]
+        S = p.shape[1]
+        lut = _nearest_lut(S, Ho, Wo, str(dev))
+        keep.append(lut)
+        chan[c], luts[c], sizes[c] = p.data_ptr(), lut.data_ptr(), S
+    ordr = (C.c_int32 * 4)(*(list(order) + [0] * (4 - len(order))))
+    with torch.cuda.device(dev):
+        _lib.check(lib.octseg_postprocess(chan, sizes, luts, ordr, len(order), N, Ho, Wo, mask.data_ptr(),
+                                          label.data_ptr(), counts.data_ptr(), _lib.stream_ptr()), 'postprocess')
+    return mask, label, counts
+
+
+def radial_thickness(mask: torch.Tensor) -> torch.Tensor:
+    """mask: uint8 CUDA (N, H, W, 4), non-zero = object -> int32 (N, 4, 360) per-ray radii."""
+    assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+    N, H, W, _ = mask.shape
+    radii = torch.empty(N, 4, 360, dtype=torch.int32, device=mask.device)
+    with torch.cuda.device(mask.device):
+        _lib.check(_lib.load().octseg_radial_thickness(mask.data_ptr(), N, H, W, _cos_sin(str(mask.device)).data_ptr(),
+                                                       radii.data_ptr(), _lib.stream_ptr()), 'radial_thickness')
+    return radii
+
+
+def dicom_ratio(h: int) -> int:
+    return int(h * 150 // 1000)
+
+
+def quantities_from_counts(counts: np.ndarray, H: int, W: int, ratio: int, radii: Optional[np.ndarray] = None) -> List[Dict]:
+    """Per-frame, per-class table from the device reductions (host side, cheap):
+    present <=> 0 < nnz < H*W (== np.unique(ch).shape[0] == 2, analysis.py:189);
+    area = sqrt(nnz // ratio) (analysis.py:199-200); radial thickness median/min over rays that hit."""
+    rows = []
+    for n in range(counts.shape[0]):
+        row = {}
+        for c, name in enumerate(CLASS_NAMES):
+            nnz = int(counts[n, c])
+            q = {'nnz': nnz, 'present': 0 < nnz < H * W}
+            if q['present']:
+                q['area'] = pow(nnz // ratio, 0.5)
+            if radii is not None:
+                r = radii[n, c]
+                r = r[r > 0]
+                q['thickness_median'] = float(np.median(r)) if r.size else 0
+                q['thickness_min'] = int(r.min()) if r.size else 0
+                q['thickness_max'] = int(r.max()) if r.size else 0
+            row[name] = q
+        rows.append(row)
+    return rows

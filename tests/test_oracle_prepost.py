@@ -1,0 +1,100 @@
+"""CPU: the pre/post oracle (oracle/prepost_ref.py) pinned against (a) cv2 itself, (b) outputs of the
+reference's own functions run in the build container (tests/golden/make_golden.py), (c) the
+reference's mask -> mask_color fixture pairs; and the product's host-side tables against the oracle."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from oct_segmentation_b200 import prepost as P
+from oracle import prepost_ref as R
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def unpack(packed, shape):
+    h, w = int(shape[0]), int(shape[1])
+    return (np.unpackbits(packed)[:h * w * 4].reshape(h, w, 4) * 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize('src,dst', [(250, 96), (250, 160), (250, 125), (1000, 512), (1000, 896), (750, 512), (512, 896), (1024, 512)])
+def test_resize_linear_matches_cv2(src, dst):
+    rng = np.random.default_rng(src * 7 + dst)
+    img = rng.integers(0, 256, (src, src, 3), dtype=np.uint8)
+    want = cv2.resize(img, (dst, dst))
+    got = R.resize_linear_u8(img, (dst, dst))
+    assert np.array_equal(got, want)
+
+
+def test_preprocess_matches_reference_function_output():
+    d = np.load(os.path.join(G, 'demo_frame_small.npz'))
+    for S in (96, 160, 125):
+        want = d[f'pre{S}']                       # produced by the reference's preprocessing_img
+        assert np.array_equal(R.preprocess_frame(d['rgb'], S), want)
+        assert np.array_equal(R.resize_linear_u8(d['rgb'][..., ::-1], (S, S)), want)
+
+
+@pytest.mark.parametrize('src,dst', [(512, 1000), (896, 1000), (1024, 1000), (128, 300), (96, 250)])
+def test_nearest_index_matches_cv2(src, dst):
+    ramp = np.arange(src, dtype=np.float32)[None, :].repeat(2, 0)
+    want = cv2.resize(ramp, (dst, 2), interpolation=cv2.INTER_NEAREST)[0].astype(np.int32)
+    assert np.array_equal(R.nearest_index(src, dst), want)
+    assert np.array_equal(P.nearest_table(src, dst), want)
+    if dst == 1000:
+        assert np.array_equal(want, (np.arange(dst) * src) // dst)      # SURVEY App. E integer rule
+
+
+@pytest.mark.parametrize('src,dst', [(250, 96), (1000, 512), (1000, 896), (750, 896)])
+def test_product_linear_tables_match_oracle(src, dst):
+    xo, xa = P.linear_tables(src, dst)
+    ro, ra = R.linear_coeffs(src, dst)
+    assert np.array_equal(xo, ro) and np.array_equal(xa, ra)
+
+
+def test_color_mask_matches_reference_fixture_pairs():
+    d = np.load(os.path.join(G, 'colorize_pairs.npz'))
+    for packed, want in zip(d['packed'], d['colors']):
+        m = unpack(packed, d['shape'])
+        assert np.array_equal(R.color_mask(m), want)
+        lab = R.label_map(m)
+        # priority VV > LC > FC > LM where channels overlap
+        assert (lab[m[:, :, 3] != 0] == 4).all()
+        assert (lab[(m[:, :, 2] != 0) & (m[:, :, 3] == 0)] == 3).all()
+
+
+def test_quantities_match_reference_function_outputs():
+    d = np.load(os.path.join(G, 'masks_app_demo.npz'))
+    q = np.load(os.path.join(G, 'quantities_ref.npz'))
+    ratio = int(q['ratio'])
+    assert ratio == R.dicom_ratio(750)
+    for k, packed in enumerate(d['packed']):
+        m = unpack(packed, d['shape'])
+        assert np.array_equal([R.area_count(m[:, :, c]) for c in range(4)], d['counts'][d['keep_idx'][k]])
+        for c in range(4):
+            ch = np.ascontiguousarray(m[:, :, c])
+            present, nnz, area, cmed, cmin, rmed, rmin, rmax = q['q'][k, c]
+            assert R.class_present(ch) == bool(present) and R.area_count(ch) == int(nnz)
+            assert R.area_value(ch, ratio) == area
+            t = R.thickness_contour(ch)
+            assert t['median'] == cmed and t['min'] == cmin
+            if k < 3:                                   # the pure-Python radial scan is slow
+                radii = R.radial_radii(ch)
+                hits = q['radii_hits'][k, c]
+                assert np.array_equal(radii[radii > 0], hits[hits >= 0])
+                rt = R.radial_thickness(ch)
+                assert rt['median'] == rmed and rt['min'] == rmin and rt['max'] == rmax
+
+
+def test_object_id_tracking():
+    assert R.object_ids([True, True, False, True, False, False, True, True]) == [0, 0, 1, 2, 2]
+    assert R.object_ids([False, False]) == []
+
+
+def test_quantities_from_counts_host_logic():
+    counts = np.array([[0, 150 * 4 + 7, 1000 * 1000, 12345]])
+    rows = P.quantities_from_counts(counts, 1000, 1000, 150)
+    r = rows[0]
+    assert not r['Lumen']['present'] and not r['Lipid core']['present']       # empty / full channel
+    assert r['Fibrous cap']['present'] and r['Fibrous cap']['area'] == 2.0
+    assert r['Vasa vasorum']['area'] == pow(12345 // 150, 0.5)

@@ -1,0 +1,119 @@
+"""GPU parity (bit-exact) of the pre/post-processing kernels through the C-ABI against the CPU
+oracle, cv2 and the reference-generated goldens."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oct_segmentation_b200 import prepost as P
+from oracle import prepost_ref as R
+from oracle import synth
+from tests.test_oracle_prepost import G, unpack
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('src,dst', [(250, 96), (250, 125), (512, 512), (1000, 512), (1000, 896), (1024, 512), (750, 896)])
+def test_preprocess_bit_exact_vs_cv2(src, dst):
+    rng = np.random.default_rng(src + dst)
+    frames = rng.integers(0, 256, (3, src, src, 3), dtype=np.uint8)
+    got = P.preprocess(torch.from_numpy(frames).cuda(), dst).cpu().numpy()
+    for f, g in zip(frames, got):
+        assert np.array_equal(g, cv2.resize(cv2.cvtColor(f, cv2.COLOR_RGB2BGR), (dst, dst)))
+
+
+def test_preprocess_real_frame_matches_reference_output():
+    d = np.load(os.path.join(G, 'demo_frame_small.npz'))
+    x = torch.from_numpy(d['rgb'][None].copy()).cuda()
+    for S in (96, 160, 125):
+        assert np.array_equal(P.preprocess(x, S)[0].cpu().numpy(), d[f'pre{S}'])
+
+
+def oracle_post(planes_np, order_names, Ho, Wo):
+    """predict.py:92-100 per frame with cv2, then label map + counts with numpy."""
+    meta = {'Lumen': ('LM', 0), 'Lipid core': ('FC_LC', 0), 'Fibrous cap': ('FC_LC', 1), 'Vasa vasorum': ('VV', 0)}
+    N = next(iter(planes_np.values())).shape[0]
+    masks, labels, counts = [], [], []
+    for n in range(N):
+        mask = np.zeros((Ho, Wo, 4))
+        for name in order_names:
+            mdir, idx = meta[name]
+            pm = planes_np[mdir][n].astype(np.float32)              # (S, S, C) like predict() returns
+            rm = cv2.resize(pm, (Wo, Ho), interpolation=cv2.INTER_NEAREST)
+            if rm.ndim > 2:
+                rm = rm[:, :, idx]
+            mask[:, :, R.CLASS_NAMES.index(name)] = rm
+        masks.append(mask.astype(np.uint8))
+        labels.append(R.label_map(mask, order_names))
+        counts.append([R.area_count(mask[:, :, c]) for c in range(4)])
+    return np.stack(masks), np.stack(labels), np.array(counts)
+
+
+@pytest.mark.parametrize('Ho,S_lm,S_big,order', [
+    (1000, 512, 896, ['Lumen', 'Fibrous cap', 'Lipid core', 'Vasa vasorum']),
+    (250, 128, 224, ['Lumen', 'Fibrous cap', 'Lipid core', 'Vasa vasorum']),
+    (333, 96, 160, ['Vasa vasorum', 'Lumen']),                      # subset + different paint order
+])
+def test_postprocess_bit_exact(Ho, S_lm, S_big, order):
+    rng = np.random.default_rng(Ho)
+    N = 2
+
+    def blobs(S, C):
+        yy, xx = np.mgrid[0:S, 0:S]
+        out = np.zeros((N, S, S, C), np.uint8)
+        for n in range(N):
+            for c in range(C):
+                cx, cy, r = rng.uniform(0.3, 0.7) * S, rng.uniform(0.3, 0.7) * S, rng.uniform(0.1, 0.3) * S
+                out[n, :, :, c] = ((xx - cx) ** 2 + (yy - cy) ** 2 < r * r) ^ (rng.random((S, S)) < 0.02)
+        return out
+    planes_np = {'LM': blobs(S_lm, 1), 'FC_LC': blobs(S_big, 2), 'VV': blobs(S_big, 1)}
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v.transpose(0, 3, 1, 2))).cuda() for k, v in planes_np.items()}
+    # routing of predict.py:23-28: class channel -> (model, model channel)
+    route = {0: dev['LM'][:, 0], 1: dev['FC_LC'][:, 1], 2: dev['FC_LC'][:, 0], 3: dev['VV'][:, 0]}
+    planes = {c: route[c].contiguous() for c in range(4) if R.CLASS_NAMES[c] in order}
+    mask, label, counts = P.postprocess(planes, [R.CLASS_NAMES.index(n) for n in order], Ho, Ho, N, 'cuda')
+    wm, wl, wc = oracle_post(planes_np, order, Ho, Ho)
+    assert np.array_equal(mask.cpu().numpy(), wm)
+    assert np.array_equal(label.cpu().numpy(), wl)
+    assert np.array_equal(counts.cpu().numpy(), wc)
+
+
+def test_counts_and_radial_thickness_match_reference_goldens():
+    d = np.load(os.path.join(G, 'masks_app_demo.npz'))
+    q = np.load(os.path.join(G, 'quantities_ref.npz'))
+    masks = np.stack([unpack(p, d['shape']) for p in d['packed']])           # (12, 750, 750, 4) {0,255}
+    dev = torch.from_numpy(masks).cuda()
+    radii = P.radial_thickness(dev).cpu().numpy()
+    counts = (dev != 0).sum(dim=(1, 2)).cpu().numpy()
+    assert np.array_equal(counts, d['counts'][d['keep_idx']])
+    rows = P.quantities_from_counts(counts, 750, 750, int(q['ratio']), radii)
+    for k in range(masks.shape[0]):
+        for c, name in enumerate(R.CLASS_NAMES):
+            present, nnz, area, _, _, rmed, rmin, rmax = q['q'][k, c]
+            hits = q['radii_hits'][k, c]
+            r = radii[k, c]
+            assert np.array_equal(r[r > 0], hits[hits >= 0]), (k, name)
+            row = rows[k][name]
+            assert row['present'] == bool(present) and row['nnz'] == int(nnz)
+            if present:
+                assert row['area'] == area
+            assert row['thickness_median'] == rmed and row['thickness_min'] == rmin and row['thickness_max'] == rmax
+
+
+def test_postprocess_full_size_properties():
+    """At BASELINE's full output size: counts equal the mask's own popcount, label obeys the priority
+    rule, and upscaling a plane by the nearest LUT preserves its bounding rows/cols."""
+    N, Ho = 4, 1000
+    g = torch.Generator(device='cuda').manual_seed(5)
+    planes = {c: (torch.rand(N, S, S, device='cuda', generator=g) < 0.3).to(torch.uint8)
+              for c, S in zip(range(4), (512, 896, 896, 896))}
+    mask, label, counts = P.postprocess(planes, [0, 1, 2, 3], Ho, Ho, N, 'cuda')
+    assert torch.equal(counts.long(), mask.long().sum(dim=(1, 2)))
+    want = torch.zeros_like(label)
+    for c in range(4):
+        want[mask[..., c] != 0] = c + 1
+    assert torch.equal(label, want)
+    lut = torch.from_numpy(P.nearest_table(512, Ho)).cuda().long()
+    assert torch.equal(mask[..., 0], planes[0][:, lut][:, :, lut])
