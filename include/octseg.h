@@ -165,8 +165,10 @@ int octseg_preprocess_resize_bgr(const uint8_t* src /* [N][Hs][Ws][3] RGB */, in
  * Post-processing: threshold (model.py:195) + cv2.resize INTER_NEAREST (predict.py:92-96) +
  * class routing (predict.py:97-100, MODELS_META) + priority label map (data/utils.py:231-233)
  * + per-class pixel count (analysis.py:199) in one pass over the output grid.
- *   chan[c]: pointer to the {0,1} uint8 plane [N][S_c][S_c] feeding mask channel c (or NULL:
- *            class absent -> zeros), c = class id - 1 (LM, FC, LC, VV).
+ *   chan[c]: pointer to the {0,1} uint8 planes [N][S_c][S_c] feeding mask channel c (or NULL:
+ *            class absent -> zeros), c = class id - 1 (LM, FC, LC, VV); h_img_stride[c] = bytes
+ *            between consecutive frames' planes (S_c*S_c when dense; C*S_c*S_c when the plane is
+ *            one channel of a network's NCHW output).
  *   h_lut[c]: DEVICE int32 [Ho + Wo]: source row for each output row, then source column for
  *            each output column (cv2 rule sx = min(floor(x * (1/(dst/src))), src-1))
  *   mask   : uint8 [N][Ho][Wo][4] {0,1}      (the reference's float64 HxWx4 array, as bytes)
@@ -174,7 +176,7 @@ int octseg_preprocess_resize_bgr(const uint8_t* src /* [N][Hs][Ws][3] RGB */, in
  *            `order` wins), or NULL
  *   counts : int32 [N][4] non-zero pixels per class (zeroed by caller)
  * ------------------------------------------------------------------------------------------ */
-int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h_S,
+int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h_S, const int64_t* h_img_stride,
                        const int32_t* const* h_lut, const int32_t* h_order,
                        int32_t n_order, int32_t N, int32_t Ho, int32_t Wo, uint8_t* mask,
                        uint8_t* label, int32_t* counts, void* stream);

@@ -86,7 +86,8 @@ def load() -> C.CDLL:
         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.octseg_postprocess.argtypes = [
-        C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
+        C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+        C.POINTER(C.c_int32), C.c_int32,
         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.octseg_radial_thickness.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]

@@ -56,6 +56,7 @@ __global__ void preprocess_resize_bgr_kernel(const uint8_t* __restrict__ src, in
 struct PostParams {
   const uint8_t* chan[4];
   const int* lut[4];
+  long long img_stride[4];
   int S[4];
   int order[4];
   int n_order;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256) postprocess_kernel(const PostParams p) {
       if (!p.chan[c]) continue;
       const int S = p.S[c];
       const int sy = p.lut[c][y];
-      const uint8_t* row = p.chan[c] + (static_cast<size_t>(n) * S + sy) * S;
+      const uint8_t* row = p.chan[c] + static_cast<size_t>(n) * p.img_stride[c] + static_cast<size_t>(sy) * S;
       const int* lx = p.lut[c] + p.Ho;
 #pragma unroll
       for (int px = 0; px < 4; ++px) {
@@ -181,8 +182,8 @@ extern "C" int octseg_preprocess_resize_bgr(const uint8_t* src, int32_t N, int32
   return check_launch("preprocess_resize_bgr_kernel");
 }
 
-extern "C" int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h_S, const int32_t* const* h_lut,
-                                  const int32_t* h_order, int32_t n_order, int32_t N, int32_t Ho, int32_t Wo,
+extern "C" int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h_S, const int64_t* h_img_stride,
+                                  const int32_t* const* h_lut, const int32_t* h_order, int32_t n_order, int32_t N, int32_t Ho, int32_t Wo,
                                   uint8_t* mask, uint8_t* label, int32_t* counts, void* stream) {
   if (!h_chan || !h_S || !h_lut || !mask || !counts) return fail(OCTSEG_EINVAL, "postprocess: null argument");
   if (n_order < 0 || n_order > 4) return fail(OCTSEG_EINVAL, "postprocess: n_order out of range");
@@ -191,6 +192,7 @@ extern "C" int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h
     p.chan[c] = h_chan[c];
     p.lut[c] = h_lut[c];
     p.S[c] = h_S[c];
+    p.img_stride[c] = h_img_stride ? h_img_stride[c] : static_cast<long long>(h_S[c]) * h_S[c];
     if (p.chan[c] && !p.lut[c]) return fail(OCTSEG_EINVAL, "postprocess: class %d has no LUT", c);
   }
   for (int k = 0; k < 4; ++k) p.order[k] = k < n_order ? h_order[k] : 0;

@@ -39,6 +39,7 @@ class Builder:
         self.N = N
         self.ops: List[Callable[[], None]] = []
         self.op_names: List[str] = []
+        self.op_macs: List[Optional[int]] = []   # algorithmic MACs of tensor-core launches, None otherwise
         self.macs = 0              # algorithmic MACs of the reference graph (dense count)
         self.tc_launches = 0
         self.launches = 0
@@ -51,9 +52,10 @@ class Builder:
         self.act_bytes += t.numel() * 2
         return Act(t, C)
 
-    def _add(self, name: str, fn: Callable[[], None]) -> None:
+    def _add(self, name: str, fn: Callable[[], None], tc_macs: Optional[int] = None) -> None:
         self.ops.append(fn)
         self.op_names.append(name)
+        self.op_macs.append(tc_macs)
         self.launches += 1
 
     def run(self) -> None:
@@ -83,7 +85,7 @@ class Builder:
         self._keep.append(plan)
         self.macs += geom.macs
         self.tc_launches += 1
-        self._add(name, plan.run)
+        self._add(name, plan.run, tc_macs=geom.macs)
         return out_act
 
     # ------------------------------------------------------------------ CUDA-core kernels
@@ -165,15 +167,15 @@ class Builder:
         self._keep += [plan, w1d, b1d, w2d, b2d, gate, base, wn]
         lib, inv_hw = self.lib, 1.0 / float(x.H * x.W)
 
-        def op():
+        def gate_op():
             st = _lib.stream_ptr()
             _lib.check(lib.octseg_se_gate(pool.data_ptr(), inv_hw, w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(),
                                           b2d.data_ptr(), gate.data_ptr(), N, C_mid, cr, st), name + '.se_gate')
             _lib.check(lib.octseg_scale_weights(base.data_ptr(), gate.data_ptr(), wn.data_ptr(), N, rows, Ktot,
                                                 C_mid, st), name + '.scale_weights')
-            plan.run(st)
         self.macs += geom.macs + N * 2 * C_mid * cr
         self.tc_launches += 1
-        self._add(name, op)
-        self.launches += 2
+        self._add(name + '.se', gate_op)
+        self.launches += 1                      # gate_op is two launches
+        self._add(name, plan.run, tc_macs=geom.macs)
         return out

@@ -1,0 +1,188 @@
+"""Predict entry point — same functions, arguments and config keys as
+/root/reference/src/predict.py (MODELS_META :23-28, load_model :31-50, preprocess_images :53-58,
+segment :61-101, main :109-149) and the helpers it imports from src/data/utils.py
+(data_processing :169-192, save_results :195-235), executed on the octseg B200 engine.
+
+Differences that do not change results: frames go through the GPU in batches
+(`cfg.batch_size`), each model runs once per frame even when it serves two classes, and resize /
+threshold / routing / label map / pixel counts are CUDA kernels (bit-exact vs cv2, see tests).
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+import sys
+import time
+from glob import glob
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import config as cfgmod
+from . import prepost as P
+from .model import CLASS_COLORS_RGB, CLASS_IDS, OCTSegmentationModel
+from .pipeline import MODELS_META, EnsemblePipeline
+
+log = logging.getLogger(__name__)
+log.setLevel(logging.INFO)
+
+PROJECT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BACKGROUND_RGB = (128, 128, 128)
+
+
+def pick_device(option: str) -> str:
+    """/root/reference/src/models/smp/utils.py:250-266."""
+    if option == 'auto':
+        return 'cuda' if torch.cuda.is_available() else 'cpu'
+    elif option in ['cpu', 'cuda']:
+        return option
+    else:
+        raise ValueError("Invalid device option. Please specify 'cpu', 'cuda', or 'auto'.")
+
+
+def load_model(model_dir: str, device: str) -> Tuple[OCTSegmentationModel, Dict]:
+    """Load a segmentation model from checkpoint (config.json + weights.ckpt)."""
+    with open(f'{model_dir}/config.json', 'r') as file:
+        model_cfg = json.load(file)
+    model = OCTSegmentationModel.load_from_checkpoint(
+        checkpoint_path=f'{model_dir}/weights.ckpt',
+        encoder_weights=None,
+        arch=model_cfg['architecture'],
+        encoder_name=model_cfg['encoder'],
+        model_name=model_cfg['model_name'],
+        in_channels=3,
+        classes=model_cfg['classes'],
+        map_location='cuda:0' if device == 'cuda' else device,
+    )
+    model.eval()
+    return model, model_cfg
+
+
+def preprocess_images(images: List[Image.Image], input_size: int, device: str = 'cuda') -> np.ndarray:
+    """(N, S, S, 3) uint8 BGR, identical to [preprocessing_img(img, S) for img in images] but resized
+    by the CUDA kernel."""
+    frames = np.stack([np.array(img.convert('RGB') if img.mode != 'RGB' else img) for img in images])
+    dev = torch.device('cuda:0' if device == 'cuda' else device)
+    return P.preprocess(torch.from_numpy(frames).to(dev), input_size).cpu().numpy()
+
+
+def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Sequence[int], classes: Sequence[str],
+            models_dir: str, device: str, batch_size: int = 16, models: Dict = None,
+            quantities: List = None) -> List[np.ndarray]:
+    """Perform segmentation for given images using specified models; fills and returns ``masks``
+    (the caller's float64 HxWx4 arrays), channel CLASS_IDS[name]-1 per requested class."""
+    if device != 'cuda':
+        raise RuntimeError('the B200 build of segment() runs on CUDA only (device resolved to %r)' % device)
+    if not images:
+        return masks
+    dev = torch.device('cuda:0')
+    if models is None:
+        models = {}
+        for class_name in classes:
+            mdir = MODELS_META[class_name]['model_dir']
+            if mdir in models:
+                continue
+            start_load = time.time()
+            models[mdir] = load_model(model_dir=os.path.join(models_dir, mdir), device=device)
+            log.info(f"{models[mdir][1]['architecture']} loaded successfully. Time taken: {time.time() - start_load:.1f} s")
+    frames = np.stack([np.array(img.convert('RGB') if img.mode != 'RGB' else img) for img in images])
+    n = frames.shape[0]
+    batch = min(batch_size, n)
+    pipe = EnsemblePipeline(models, classes, output_size, dev, batch, src_hw=frames.shape[1:3],
+                            thickness=quantities is not None)
+    for lo in range(0, n, batch):
+        hi = min(lo + batch, n)
+        mask, label, counts, radii = pipe.run_host(frames[lo:hi])
+        for i in range(lo, hi):
+            for class_name in classes:
+                idx = CLASS_IDS[class_name] - 1
+                masks[i][:, :, idx] = mask[i - lo, :, :, idx]
+        if quantities is not None:
+            ratio = P.dicom_ratio(pipe.Ho)
+            quantities.extend(P.quantities_from_counts(counts, pipe.Ho, pipe.Wo, ratio, radii))
+    return masks
+
+
+def data_processing(data_path: str, save_dir: str, output_size: Sequence[int]):
+    """src/data/utils.py:169-192: open every image, PIL-resize (bicubic) to output_size, allocate the
+    float64 HxWx4 mask.  File order is sorted (the reference's glob order is unspecified)."""
+    os.makedirs(save_dir, exist_ok=True)
+    if os.path.isfile(data_path):
+        images_path = [data_path]
+    else:
+        images_path = sorted(glob(f'{data_path}/*.[pj][np][ge]*'))
+    images, masks, image_names = [], [], []
+    for img_path in images_path:
+        img = Image.open(img_path).resize(tuple(output_size))
+        masks.append(np.zeros((output_size[0], output_size[1], 4)))
+        images.append(img)
+        image_names.append(os.path.basename(img_path).split('.')[0])
+    return images, masks, image_names
+
+
+def color_mask(mask: np.ndarray, classes: Sequence[str]) -> np.ndarray:
+    """Colour mask of save_results (src/data/utils.py:208,231-233): grey background, classes painted
+    in ``classes`` order so later classes overwrite earlier ones."""
+    out = np.empty(mask.shape[:2] + (3,), np.uint8)
+    out[:] = BACKGROUND_RGB
+    for class_name in classes:
+        out[mask[:, :, CLASS_IDS[class_name] - 1] != 0] = CLASS_COLORS_RGB[class_name]
+    return out
+
+
+def save_results(images, masks, images_name, classes, save_dir: str) -> None:
+    """Writes <name>_mask.png (colour mask, identical to the reference's) and <name>_overlay.png.
+    The overlay is a plain alpha blend of the colour mask; the reference's morphology/Gaussian
+    overlay cosmetics are a listed follow-up, not part of the hot path."""
+    for img, mask, name in zip(images, masks, images_name):
+        cm = color_mask(mask, classes)
+        Image.fromarray(cm).save(f'{save_dir}/{name}_mask.png')
+        base = np.array(img.convert('RGB')).astype(np.float32)
+        fg = (mask[:, :, [CLASS_IDS[c] - 1 for c in classes]] != 0).any(axis=2)
+        over = base.copy()
+        over[fg] = 0.75 * base[fg] + 0.25 * cm[fg].astype(np.float32)
+        Image.fromarray(over.astype(np.uint8)).save(f'{save_dir}/{name}_overlay.png')
+
+
+def main(cfg) -> None:
+    """Main function to perform OCT image segmentation prediction."""
+    log.info(f'Config:\n\n{cfgmod.to_yaml(cfg)}')
+    device = pick_device(option=cfg.device)
+    data_dir = str(os.path.join(PROJECT_DIR, cfg.data_dir))
+    models_dir = str(os.path.join(PROJECT_DIR, cfg.models_dir))
+    save_dir = str(os.path.join(PROJECT_DIR, cfg.save_dir))
+
+    start = time.time()
+    images, masks, images_name = data_processing(data_path=data_dir, save_dir=save_dir, output_size=cfg.output_size)
+    log.info(f'Number of images: {len(images_name)}')
+
+    start_inference = time.time()
+    quantities = [] if cfg.get('quantities', False) else None
+    masks = segment(images=images, masks=masks, output_size=cfg.output_size, classes=cfg.classes,
+                    models_dir=models_dir, device=device, batch_size=int(cfg.get('batch_size', 16)),
+                    quantities=quantities)
+    log.info(f'Prediction time: {time.time() - start_inference:.1f} s')
+
+    save_results(images=images, masks=masks, images_name=images_name, classes=cfg.classes, save_dir=save_dir)
+    if quantities is not None:
+        with open(os.path.join(save_dir, 'quantities.json'), 'w') as f:
+            json.dump(dict(zip(images_name, quantities)), f, indent=1)
+    log.info(f'Overall computation time: {time.time() - start:.1f} s')
+    log.info('Complete')
+
+
+def cli(argv: Sequence[str] = None) -> None:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    cfg = cfgmod.compose(os.path.join(PROJECT_DIR, 'configs'), 'predict', argv)
+    jl = cfg.get('hydra', {}).get('job_logging', {})
+    logging.basicConfig(level=getattr(logging, str(jl.get('level', 'INFO'))),
+                        format=jl.get('format', '[%(asctime)s][%(levelname)s] - %(message)s'),
+                        datefmt=jl.get('datefmt', '%d-%m-%Y %H:%M:%S'), stream=sys.stdout)
+    main(cfg)
+
+
+if __name__ == '__main__':
+    cli()

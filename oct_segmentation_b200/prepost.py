@@ -91,7 +91,8 @@ def preprocess(frames_rgb: torch.Tensor, S: int, out: Optional[torch.Tensor] = N
 def postprocess(planes: Dict[int, torch.Tensor], order: Sequence[int], Ho: int, Wo: int, N: int, device,
                 mask: Optional[torch.Tensor] = None, label: Optional[torch.Tensor] = None,
                 counts: Optional[torch.Tensor] = None):
-    """planes[c]: uint8 CUDA (N, S_c, S_c) {0,1} plane feeding mask channel c (= class id - 1).
+    """planes[c]: uint8 CUDA (N, S_c, S_c) {0,1} plane feeding mask channel c (= class id - 1); may be a
+    channel slice of a network's (N, C, S, S) output (only the frame stride may be non-dense).
     order: class channel indices in cfg.classes order (later wins in the label map).
     Returns (mask uint8 [N,Ho,Wo,4], label uint8 [N,Ho,Wo], counts int32 [N,4])."""
     dev = torch.device(device)
@@ -107,20 +108,23 @@ def postprocess(planes: Dict[int, torch.Tensor], order: Sequence[int], Ho: int, 
     chan = (C.c_void_p * 4)()
     luts = (C.c_void_p * 4)()
     sizes = (C.c_int32 * 4)()
+    strides = (C.c_int64 * 4)()
     keep = []
     for c in range(4):
         p = planes.get(c)
         if p is None:
             chan[c], luts[c], sizes[c] = None, None, 0
             continue
-        assert p.is_cuda and p.dtype == torch.uint8 and p.is_contiguous() and p.shape[0] == N and p.shape[1] == p.shape[2]
         S = p.shape[1]
+        assert p.is_cuda and p.dtype == torch.uint8 and p.shape[0] == N and p.shape[2] == S
+        assert p.stride(2) == 1 and p.stride(1) == S, 'plane rows must be dense'
+        strides[c] = p.stride(0) if N > 1 else S * S
         lut = _nearest_lut(S, Ho, Wo, str(dev))
         keep.append(lut)
         chan[c], luts[c], sizes[c] = p.data_ptr(), lut.data_ptr(), S
     ordr = (C.c_int32 * 4)(*(list(order) + [0] * (4 - len(order))))
     with torch.cuda.device(dev):
-        _lib.check(lib.octseg_postprocess(chan, sizes, luts, ordr, len(order), N, Ho, Wo, mask.data_ptr(),
+        _lib.check(lib.octseg_postprocess(chan, sizes, strides, luts, ordr, len(order), N, Ho, Wo, mask.data_ptr(),
                                           label.data_ptr(), counts.data_ptr(), _lib.stream_ptr()), 'postprocess')
     return mask, label, counts
 

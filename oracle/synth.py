@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import model_ref, smp_ref
 
-FRAME_SEED = 20251018
+from oct_segmentation_b200.synthetic import FRAME_SEED, synthetic_frame, synthetic_frames  # noqa: F401  (shared generator)
 
 # the three shipped networks (eval/training/*/fold_1/config.json in the reference)
 MODEL_CONFIGS = {
@@ -28,47 +28,6 @@ MODEL_CONFIGS = {
            'input_size': 896, 'classes': ['Vasa vasorum']},
 }
 MODEL_SEEDS = {'LM': 1000, 'FC_LC': 1001, 'VV': 1002}
-
-
-def synthetic_frame(idx: int, size: int = 512) -> np.ndarray:
-    """uint8 RGB (size, size, 3) OCT-like frame, deterministic in ``idx``."""
-    rng = np.random.Generator(np.random.PCG64(FRAME_SEED + idx))
-    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32)
-    c = (size - 1) / 2.0
-    dx, dy = xx - c, yy - c
-    r = np.sqrt(dx * dx + dy * dy) / size          # 0 .. ~0.7
-    th = np.arctan2(dy, dx)
-    # lumen boundary with low-order angular harmonics
-    r_l = rng.uniform(0.15, 0.30)
-    bound = r_l * np.ones_like(r)
-    for k in range(1, 4):
-        bound += rng.uniform(0.0, 0.03) * np.cos(k * th + rng.uniform(0, 2 * np.pi))
-    inten = np.zeros_like(r)
-    wall = r >= bound
-    inten[wall] = (200.0 * np.exp(-(r[wall] - bound[wall]) / rng.uniform(0.05, 0.12)))
-    inten += 15.0 * (r < bound)                      # blood-free lumen: faint
-    ring = np.abs(r - 0.05) < 0.006                   # catheter ring
-    inten[ring] = 230.0
-    # dark lipid wedge and bright vessel blobs
-    if rng.random() < 0.7:
-        a0, aw = rng.uniform(-np.pi, np.pi), rng.uniform(0.3, 1.2)
-        wedge = (np.abs(np.angle(np.exp(1j * (th - a0)))) < aw / 2) & (r > bound + 0.03) & (r < bound + 0.18)
-        inten[wedge] *= 0.25
-    for _ in range(int(rng.integers(0, 4))):
-        ba, br = rng.uniform(-np.pi, np.pi), rng.uniform(0.32, 0.45)
-        bx, by = c + br * size * np.cos(ba), c + br * size * np.sin(ba)
-        blob = (xx - bx) ** 2 + (yy - by) ** 2 < (rng.uniform(0.008, 0.02) * size) ** 2
-        inten[blob] = 180.0
-    speckle = rng.rayleigh(scale=0.8, size=r.shape).astype(np.float32)
-    inten = inten * speckle
-    inten[r > 0.5] = 0.0                              # circular field of view
-    inten = np.clip(inten, 0, 255)
-    rgb = np.stack([inten, 0.45 * inten, 0.08 * inten], axis=-1)
-    return rgb.astype(np.uint8)
-
-
-def synthetic_frames(start: int, count: int, size: int = 512) -> np.ndarray:
-    return np.stack([synthetic_frame(start + i, size) for i in range(count)])
 
 
 def _randomize_bn(model: nn.Module, gen: torch.Generator) -> None:

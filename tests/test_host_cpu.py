@@ -1,0 +1,134 @@
+"""CPU: host logic of the boundary — C-ABI exports, config composition, sharding + gloo gather,
+state-dict compatibility, error behaviour of the reference-facing surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oct_segmentation_b200 import _lib, config, parallel, smp
+from oct_segmentation_b200.model import OCTSegmentationModel
+from oct_segmentation_b200 import predict as pred
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'octseg.h')).read()
+    declared = set(re.findall(r'\b(octseg_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().octseg_abi_version() == 1
+
+
+def test_conv_plan_rejects_bad_arguments_without_a_gpu():
+    lib = _lib.load()
+    d = _lib.ConvDesc()
+    d.nseg = 0
+    h = ctypes.c_void_p()
+    assert lib.octseg_conv_plan_create(ctypes.byref(d), ctypes.byref(h)) == -1
+    assert b'nseg' in lib.octseg_last_error()
+    d.nseg, d.phases, d.BN = 1, 3, 64
+    assert lib.octseg_conv_plan_create(ctypes.byref(d), ctypes.byref(h)) == -1
+    assert b'phases' in lib.octseg_last_error()
+
+
+def test_config_composition_and_overrides():
+    cfg = config.compose(os.path.join(ROOT, 'configs'), 'predict', ['device=cpu', 'output_size=[512,512]', 'classes=[Lumen]'])
+    assert cfg.device == 'cpu' and cfg.output_size == [512, 512] and cfg.classes == ['Lumen']
+    assert cfg.data_dir == 'data/demo/input' and cfg.models_dir == 'models' and cfg.save_dir == 'data/demo/output'
+    assert cfg.hydra.job.chdir is False                     # from configs/main.yaml via `defaults`
+    base = config.compose(os.path.join(ROOT, 'configs'), 'predict')
+    assert base.classes == ['Lumen', 'Fibrous cap', 'Lipid core', 'Vasa vasorum'] and base.output_size == [1000, 1000]
+    with pytest.raises(ValueError):
+        config.compose(os.path.join(ROOT, 'configs'), 'predict', ['oops'])
+    with pytest.raises(FileNotFoundError):
+        config.compose(os.path.join(ROOT, 'configs'), 'nope')
+
+
+def test_pick_device_and_errors():
+    assert pred.pick_device('cpu') == 'cpu' and pred.pick_device('cuda') == 'cuda'
+    assert pred.pick_device('auto') in ('cpu', 'cuda')
+    with pytest.raises(ValueError):
+        pred.pick_device('tpu')
+    with pytest.raises(KeyError):
+        smp.create_model('NoSuchArch', 'resnet101')
+    with pytest.raises(KeyError):
+        smp.create_model('Unet', 'resnet18')
+    with pytest.raises(FileNotFoundError):
+        pred.load_model('/nonexistent/dir', 'cpu')
+    assert pred.MODELS_META['Lipid core'] == {'model_dir': 'FC_LC', 'index': 0}
+    assert pred.MODELS_META['Fibrous cap'] == {'model_dir': 'FC_LC', 'index': 1}
+
+
+def test_model_surface_and_cpu_refusal():
+    m = OCTSegmentationModel(arch='Unet', encoder_name='timm-regnetx_064', model_name='x', in_channels=3,
+                             classes=['Vasa vasorum'], encoder_weights=None)
+    assert hasattr(m.model, 'encoder') and hasattr(m.model, 'decoder') and hasattr(m.model, 'segmentation_head')
+    assert set(k.split('.')[0] for k in m.state_dict()) == {'model', 'mean', 'std'}
+    assert m.mean.shape == (1, 3, 1, 1) and abs(m.std[0, 0, 0, 0].item() - 0.229) < 1e-6
+    with pytest.raises(RuntimeError):                        # H, W must be divisible by 32
+        m.model(torch.zeros(1, 3, 100, 128))
+    with pytest.raises(RuntimeError):                        # no CPU fallback
+        m.model(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError):
+        m.predict(np.zeros((1, 64, 64, 3), np.uint8), 'cpu')
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from oracle import synth
+    ref = synth.make_model('VV', calib_size=64, calib_frames=1)
+    synth.save_checkpoint(ref, str(tmp_path / 'weights.ckpt'))
+    cfg = synth.MODEL_CONFIGS['VV']
+    import json
+    json.dump(cfg, open(tmp_path / 'config.json', 'w'))
+    model, got_cfg = pred.load_model(str(tmp_path), 'cpu')
+    assert got_cfg == cfg
+    sd = model.state_dict()
+    for k, v in ref.state_dict().items():
+        assert torch.equal(sd[k], v), k
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 16, 25698):
+        for world in (1, 2, 3, 4, 8):
+            spans = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(10, 2, 2)
+
+
+def _gather_worker(rank, world, n_total, port, q):
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = parallel.shard_range(n_total, rank, world)
+    local = torch.arange(lo, hi, dtype=torch.int32)[:, None] * torch.tensor([[1, 10, 100, 1000]], dtype=torch.int32)
+    table = parallel.gather_table(local, n_total)
+    if rank == 0:
+        q.put(table.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_total', [7, 16])
+def test_gather_table_world_size_2_gloo(n_total):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + n_total
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, n_total, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    table = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(n_total, dtype=np.int32)[:, None] * np.array([[1, 10, 100, 1000]], dtype=np.int32)
+    assert np.array_equal(table, want)           # frame order preserved across ranks == single-rank result

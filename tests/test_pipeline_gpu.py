@@ -1,0 +1,112 @@
+"""GPU: the reference-facing predict path (segment / EnsemblePipeline / src/predict.py main) against
+the oracle restatement of /root/reference/src/predict.py on the same synthetic checkpoints + frames."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oct_segmentation_b200 import predict as pred
+from oct_segmentation_b200 import prepost as P
+from oct_segmentation_b200.model import OCTSegmentationModel
+from oct_segmentation_b200.pipeline import EnsemblePipeline
+from oracle import model_ref, synth
+from oracle import prepost_ref as R
+
+pytestmark = pytest.mark.gpu
+
+CLASSES = ['Lumen', 'Fibrous cap', 'Lipid core', 'Vasa vasorum']
+SMALL = {'LM': 128, 'FC_LC': 160, 'VV': 160}
+
+
+@pytest.fixture(scope='module')
+def model_pairs():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    refs, ours = {}, {}
+    for key, S in SMALL.items():
+        r = synth.make_model(key, calib_size=S, calib_frames=2)
+        cfg = dict(synth.MODEL_CONFIGS[key], input_size=S)
+        o = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
+                                 in_channels=3, classes=cfg['classes'], encoder_weights=None)
+        o.load_state_dict(r.state_dict(), strict=True)
+        refs[key] = (r.cuda().eval(), cfg)
+        ours[key] = (o.cuda().eval(), cfg)
+    return refs, ours
+
+
+def test_segment_matches_reference_segment(model_pairs):
+    refs, ours = model_pairs
+    out_size = [250, 250]
+    frames = synth.synthetic_frames(300, 3, 250)
+    images = [Image.fromarray(f) for f in frames]
+    want = model_ref.segment_with_models(images, [np.zeros((250, 250, 4)) for _ in images], out_size, CLASSES, refs, 'cuda')
+    quantities = []
+    got = pred.segment(images, [np.zeros((250, 250, 4)) for _ in images], out_size, CLASSES, models_dir='', device='cuda',
+                       batch_size=2, models=ours, quantities=quantities)
+    assert len(quantities) == 3
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == w.shape == (250, 250, 4) and g.dtype == np.float64
+        assert set(np.unique(g)) <= {0.0, 1.0}
+        for c, name in enumerate(CLASSES):
+            agree = (g[:, :, c] == w[:, :, c]).mean()
+            inter = ((g[:, :, c] == 1) & (w[:, :, c] == 1)).sum()
+            dice = 2 * inter / max((g[:, :, c] == 1).sum() + (w[:, :, c] == 1).sum(), 1)
+            print(f'frame {i} {name}: pixel agreement {agree:.4f} dice {dice:.4f}')
+            # noise-like synthetic logits: a few % of pixels sit inside the bf16 error band
+            assert agree > 0.93
+            # area counts are bit-exact for whatever mask the GPU produced
+            assert quantities[i][name]['nnz'] == int((g[:, :, c] != 0).sum())
+
+
+def test_pipeline_postprocessing_is_exact_given_the_same_planes(model_pairs):
+    """With the network outputs taken from the GPU, everything after them (nearest resize, routing,
+    label map, counts, radial thickness) equals the CPU oracle bit for bit."""
+    _, ours = model_pairs
+    Ho = 333
+    pipe = EnsemblePipeline(ours, CLASSES, [Ho, Ho], 'cuda:0', 2, src_hw=(250, 250), thickness=True)
+    frames = synth.synthetic_frames(310, 2, 250)
+    mask, label, counts, radii = pipe.run_host(frames)
+    planes = {d: pipe.nets[d].out.cpu().numpy() for d in pipe.model_dirs}           # (N, C, S, S) uint8
+    for n in range(2):
+        model_masks = {d: planes[d][n].transpose(1, 2, 0).astype(np.float32) for d in planes}
+        want = R.route_masks(model_masks, CLASSES, [Ho, Ho], model_ref.MODELS_META)
+        assert np.array_equal(mask[n], want.astype(np.uint8))
+        assert np.array_equal(label[n], R.label_map(want, CLASSES))
+        assert np.array_equal(counts[n], [R.area_count(want[:, :, c]) for c in range(4)])
+        for c in range(4):
+            assert np.array_equal(radii[n, c], R.radial_radii((want[:, :, c] * 255).astype(np.uint8)))
+    # input of each network == cv2 preprocessing of the frames
+    for d in pipe.model_dirs:
+        S = pipe.sizes[d]
+        want_in = np.stack([R.preprocess_frame(f, S) for f in frames])
+        assert np.array_equal(pipe.nets[d].x_nhwc.cpu().numpy(), want_in)
+
+
+def test_predict_main_end_to_end(tmp_path, model_pairs):
+    """src/predict.py main(): models_dir with config.json + weights.ckpt, PNG inputs, PNG + JSON outputs."""
+    refs, _ = model_pairs
+    models_dir, data_dir, save_dir = tmp_path / 'models', tmp_path / 'in', tmp_path / 'out'
+    data_dir.mkdir()
+    for key, (r, cfg) in refs.items():
+        (models_dir / key).mkdir(parents=True)
+        synth.save_checkpoint(r.cpu(), str(models_dir / key / 'weights.ckpt'))
+        json.dump(cfg, open(models_dir / key / 'config.json', 'w'))
+        r.cuda()
+    for i, f in enumerate(synth.synthetic_frames(320, 2, 200)):
+        Image.fromarray(f).save(data_dir / f'frame_{i}.png')
+    from oct_segmentation_b200 import config
+    cfg = config.compose(os.path.join(os.path.dirname(os.path.dirname(__file__)), 'configs'), 'predict',
+                         [f'data_dir={data_dir}', f'models_dir={models_dir}', f'save_dir={save_dir}',
+                          'output_size=[256,256]', 'device=cuda', 'batch_size=2'])
+    pred.main(cfg)
+    for i in range(2):
+        m = np.array(Image.open(save_dir / f'frame_{i}_mask.png'))
+        assert m.shape == (256, 256, 3)
+        colors = {tuple(c) for c in np.unique(m.reshape(-1, 3), axis=0)}
+        assert colors <= {(128, 128, 128), (228, 30, 199), (123, 171, 226), (125, 227, 127), (208, 2, 27)}
+        assert (save_dir / f'frame_{i}_overlay.png').exists()
+    q = json.load(open(save_dir / 'quantities.json'))
+    assert set(q) == {'frame_0', 'frame_1'} and set(q['frame_0']) == set(CLASSES)
