@@ -130,9 +130,9 @@ int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t H, int32_t
                         int32_t Ho, int32_t Wo, void* stream);
 
 /* Depthwise kxk conv (efficientnet_pytorch MBConvBlock._depthwise_conv with static "same"
-   padding) + folded BN + swish; optionally accumulates the squeeze-excite channel sums
+   padding, k in {3,5}, stride in {1,2}) + folded BN + swish; optionally accumulates the squeeze-excite channel sums
    (adaptive_avg_pool2d numerator) into `pool_sum` fp32 [N][C] (must be zeroed by caller). */
-int octseg_dwconv(const void* in, const float* weight /* fp32 [kh][kw][C] */, const float* bias,
+int octseg_dwconv(const void* in, const void* weight /* bf16 [kh][kw][C] */, const float* bias,
                   void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
                   int32_t pad_t, int32_t pad_l, int32_t Ho, int32_t Wo, int32_t act,
                   float* pool_sum, void* stream);

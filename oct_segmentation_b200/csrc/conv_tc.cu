@@ -31,6 +31,7 @@ constexpr int kMaxStages = 8;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
+constexpr int kOutBytes = 128 * 128;  // one 128-row x 64-channel bf16 staging buffer
 constexpr uint32_t kSpinLimit = 1u << 26;  // turns a pipeline deadlock into a trap, not a hang
 
 struct SegK {
@@ -42,11 +43,13 @@ struct SegK {
 struct __align__(64) ConvKParams {
   CUtensorMap tmA[OCTSEG_MAX_SEG];
   CUtensorMap tmB;
+  CUtensorMap tmOut;  // bf16 NHWC output (4-D; 5-D phase-strided view in 4-phase mode)
   SegK seg[OCTSEG_MAX_SEG];
   int nseg, phases, N, Hq, Wq, TH, TW, tiles_h, tiles_w;
   int BN, n_tiles_n, cout_per_tile, Cout;
   int per_image_weights, act, res_mode, out_mode;
   int k_iters, nstages, total_tiles;
+  int use_tma_store;
   uint32_t stage_tx_bytes;
   const float* bias;
   const __nv_bfloat16* res;
@@ -147,11 +150,81 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return d;
 }
 
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// one MUFU per element: sigmoid(x) = 0.5*tanh(x/2) + 0.5, swish(x) = x*sigmoid(x) = h*tanh(h) + h with h = x/2
+// (tanh.approx abs error ~5e-4 of full scale, below the bf16 output rounding)
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == OCTSEG_ACT_RELU) return fmaxf(x, 0.f);
-  if (act == OCTSEG_ACT_SWISH) return x / (1.f + __expf(-x));
-  if (act == OCTSEG_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  if (act == OCTSEG_ACT_SWISH) {
+    const float h = 0.5f * x;
+    return fmaf(h, fast_tanh(h), h);
+  }
+  if (act == OCTSEG_ACT_SIGMOID) return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f);
   return x;
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// bias + residual + activation of 8 consecutive channels of one pixel -> 8 packed bf16
+__device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8, const __nv_bfloat16* r8, int act,
+                                           int res_mode) {
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias8));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias8 + 4));
+  float x[8];
+  x[0] = __uint_as_float(v[0]) + b0.x;
+  x[1] = __uint_as_float(v[1]) + b0.y;
+  x[2] = __uint_as_float(v[2]) + b0.z;
+  x[3] = __uint_as_float(v[3]) + b0.w;
+  x[4] = __uint_as_float(v[4]) + b1.x;
+  x[5] = __uint_as_float(v[5]) + b1.y;
+  x[6] = __uint_as_float(v[6]) + b1.z;
+  x[7] = __uint_as_float(v[7]) + b1.w;
+  float rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r8) {
+    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r8));
+    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(r2[e]);
+      rr[2 * e] = f.x;
+      rr[2 * e + 1] = f.y;
+    }
+  }
+  uint4 ov;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float y0 = x[2 * e], y1 = x[2 * e + 1];
+    if (res_mode == OCTSEG_RES_BEFORE_ACT) {
+      y0 += rr[2 * e];
+      y1 += rr[2 * e + 1];
+    }
+    y0 = apply_act(y0, act);
+    y1 = apply_act(y1, act);
+    if (res_mode == OCTSEG_RES_AFTER_ACT) {
+      y0 += rr[2 * e];
+      y1 += rr[2 * e + 1];
+    }
+    o2[e] = __floats2bfloat162_rn(y0, y1);
+  }
+  return ov;
 }
 
 struct TileCoord {
@@ -179,7 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
   const uint32_t smemA = smem0;
   const uint32_t smemB = smem0 + nst * kABytes;
-  const uint32_t bars = smemB + nst * b_bytes;  // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
+  const uint32_t smemOut = smemB + nst * b_bytes;        // 2 x 16 KB epilogue staging (TMA store source)
+  const uint32_t bars = smemOut + 2 * kOutBytes;         // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
   const uint32_t bar_tfull = bars + 16 * kMaxStages, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
@@ -208,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&p.tmA[s]);
     prefetch_tmap(&p.tmB);
+    if (p.use_tma_store) prefetch_tmap(&p.tmOut);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
@@ -292,9 +367,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    const int epi_tid = static_cast<int>(threadIdx.x) - 64;
     const int th_l = row / p.TW, tw_l = row - th_l * p.TW;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, out_buf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int i = tc.th * p.TH + th_l, j = tc.tw * p.TW + tw_l;
@@ -305,11 +381,49 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int nvalid = min(p.cout_per_tile, p.Cout - ch0);
       const size_t pix = (static_cast<size_t>(tc.n) * p.out_H + oh) * p.out_W + ow;
       const float* bias = p.bias + tc.n_tile * p.BN;
+      const __nv_bfloat16* rrow = (p.res && valid) ? p.res + pix * p.res_ldc + ch0 : nullptr;
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
-      for (int c0 = 0; c0 < nvalid; c0 += 32) {
+
+      // full 64-channel chunks: registers -> swizzled shared tile -> one TMA store per chunk
+      const int n_tma = p.use_tma_store ? (nvalid >> 6) : 0;
+      for (int ck = 0; ck < n_tma; ++ck) {
+        const int c0 = ck * 64;
+        const uint32_t sbuf = smemOut + out_buf * kOutBytes;
+        if (epi_tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer of 2 chunks ago is free
+        epi_bar_sync();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0 + 32 * h, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int cc = c0 + 32 * h + 8 * g;
+            const uint4 ov = epi_pack8(v + 8 * g, bias + cc, rrow ? rrow + cc : nullptr, p.act, p.res_mode);
+            const uint32_t dst = sbuf + row * 128 + (((4 * h + g) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z),
+                         "r"(ov.w)
+                         : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar_sync();
+        if (epi_tid == 0) {
+          const int cch = p.out_c_off + ch0 + c0;
+          if (p.phases == 4)
+            tma_store_5d(&p.tmOut, sbuf, cch, tc.pw, tc.tw * p.TW, tc.ph, tc.n * p.Hq + tc.th * p.TH);
+          else
+            tma_store_4d(&p.tmOut, sbuf, cch, tc.tw * p.TW, tc.th * p.TH, tc.n);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        out_buf ^= 1;
+      }
+
+      // remaining channels (and every non-bf16 output): direct stores from registers
+      for (int c0 = n_tma * 64; c0 < nvalid; c0 += 32) {
         uint32_t v[32];
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
         tmem_ld32(taddr + c0, v);
@@ -318,51 +432,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           // row outside the image / tile: nothing to store
         } else if (p.out_mode == OCTSEG_OUT_BF16_NHWC) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ldc + p.out_c_off + ch0 + c0;
-          const __nv_bfloat16* r = p.res ? p.res + pix * p.res_ldc + ch0 + c0 : nullptr;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (c0 + g * 8 < nvalid) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 8 + 4));
-              float x[8];
-              x[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
-              x[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-              x[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
-              x[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-              x[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
-              x[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-              x[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
-              x[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-              float rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-              if (r) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + g * 8));
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(r2[e]);
-                  rr[2 * e] = f.x;
-                  rr[2 * e + 1] = f.y;
-                }
-              }
-              uint4 ov;
-              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float y0 = x[2 * e], y1 = x[2 * e + 1];
-                if (p.res_mode == OCTSEG_RES_BEFORE_ACT) {
-                  y0 += rr[2 * e];
-                  y1 += rr[2 * e + 1];
-                }
-                y0 = apply_act(y0, p.act);
-                y1 = apply_act(y1, p.act);
-                if (p.res_mode == OCTSEG_RES_AFTER_ACT) {
-                  y0 += rr[2 * e];
-                  y1 += rr[2 * e + 1];
-                }
-                o2[e] = __floats2bfloat162_rn(y0, y1);
-              }
-              *reinterpret_cast<uint4*>(o + g * 8) = ov;
-            }
+            if (c0 + g * 8 < nvalid)
+              *reinterpret_cast<uint4*>(o + g * 8) =
+                  epi_pack8(v + 8 * g, bias + c0 + 8 * g, rrow ? rrow + c0 + 8 * g : nullptr, p.act, p.res_mode);
           }
         } else {
           // NCHW planes: lanes of a warp are consecutive pixels -> coalesced per channel plane
@@ -381,11 +455,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
       }
+      __syncwarp();
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (epi_tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores landed before exit
   }
 
   tc_fence_before();
@@ -540,8 +616,37 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   kp.out_c_off = d->out_c_off;
   kp.total_tiles = d->phases * d->N * kp.tiles_h * kp.tiles_w * d->n_tiles_n;
 
+  kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC && d->cout_per_tile >= 64 &&
+                      (d->phases == 1 || (d->Hq % d->TH == 0 && d->out_H == 2 * d->Hq && d->out_W == 2 * d->Wq)))
+                         ? 1
+                         : 0;
+  if (kp.use_tma_store) {
+    const uint64_t ld = static_cast<uint64_t>(d->out_ldc) * 2;
+    const uint64_t cext = static_cast<uint64_t>(d->out_c_off + d->Cout);
+    int rc;
+    if (d->phases == 1) {
+      const uint64_t dims[4] = {cext, static_cast<uint64_t>(d->out_W), static_cast<uint64_t>(d->out_H),
+                                static_cast<uint64_t>(d->N)};
+      const uint64_t strides[3] = {ld, ld * d->out_W, ld * d->out_W * d->out_H};
+      const uint32_t box[4] = {64u, static_cast<uint32_t>(d->TW), static_cast<uint32_t>(d->TH), 1u};
+      const uint32_t estr[4] = {1u, 1u, 1u, 1u};
+      rc = encode_map(&kp.tmOut, d->out, 4, dims, strides, box, estr, "out");
+    } else {
+      // pixel (2i+ph, 2j+pw) of image n: dims (c, pw, j, ph, n*Hq + i)
+      const uint64_t dims[5] = {cext, 2u, static_cast<uint64_t>(d->Wq), 2u, static_cast<uint64_t>(d->N) * d->Hq};
+      const uint64_t strides[4] = {ld, 2 * ld, ld * d->out_W, 2 * ld * d->out_W};
+      const uint32_t box[5] = {64u, 1u, static_cast<uint32_t>(d->TW), 1u, static_cast<uint32_t>(d->TH)};
+      const uint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+      rc = encode_map(&kp.tmOut, d->out, 5, dims, strides, box, estr, "out(phase)");
+    }
+    if (rc) {
+      delete pl;
+      return rc;
+    }
+  }
+
   const int stage_bytes = kABytes + d->BN * 128;
-  const int budget = 227 * 1024 - 1024 - 512;
+  const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes;
   int nst = budget / stage_bytes;
   if (nst > kMaxStages) nst = kMaxStages;
   if (nst < 2) {
@@ -549,7 +654,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     return fail(OCTSEG_EINVAL, "tile does not fit shared memory");
   }
   kp.nstages = nst;
-  pl->smem = static_cast<size_t>(nst) * stage_bytes + 1024 + 512;
+  pl->smem = static_cast<size_t>(nst) * stage_bytes + 2 * kOutBytes + 1024 + 512;
   int sms = octseg_sm_count();
   if (sms <= 0) {
     delete pl;

@@ -148,90 +148,107 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 }
 
 // ------------------------------------------------------------------------------------ depthwise
-// block = 32 channel-groups (256 channels) x 8 pixel lanes; each block walks a strip of output
-// pixels so the squeeze-excite sums reduce in registers -> shared -> one atomic per channel.
-constexpr int kDwPixPerBlock = 256;
+// HBM-bound.  Work item = 8 channels (16 B) x P consecutive output pixels of one row; items are
+// flattened (pixel-group, channel-group) with the channel group fastest, so a warp always reads
+// consecutive 16-byte chunks whatever C is.  A block owns a contiguous run of pixel groups of one
+// image and a chunk of <= 128 channel groups; squeeze-excite sums go through shared-memory
+// atomics and leave the block as one global atomic per channel.
+constexpr int kDwP = 4;          // output pixels per item
+constexpr int kDwCgChunk = 128;  // channel groups per block column
+constexpr int kDwPgPerBlock = 64;
 
+template <int K, int S>
 __global__ void __launch_bounds__(256) dwconv_kernel(const __nv_bfloat16* __restrict__ in,
-                                                     const float* __restrict__ weight,
+                                                     const __nv_bfloat16* __restrict__ weight,  // [K*K][C] bf16
                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                     int H, int W, int C, int k, int stride, int pad_t, int pad_l,
-                                                     int Ho, int Wo, int act, float* __restrict__ pool_sum) {
-  __shared__ float wsm[25 * 256];
-  __shared__ float red[8][256];
+                                                     int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo,
+                                                     int act, float* __restrict__ pool_sum) {
+  __shared__ float sums[kDwCgChunk * 8];
   const int C8 = C >> 3;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int cg = blockIdx.x * 32 + tx;
+  const int cg0 = blockIdx.x * kDwCgChunk;
+  const int cgc = min(kDwCgChunk, C8 - cg0);
   const int n = blockIdx.z;
-  const bool cvalid = cg < C8;
-  const int taps = k * k;
-  for (int i = threadIdx.x; i < taps * 256; i += 256) {
-    const int c = blockIdx.x * 256 + (i & 255);
-    wsm[i] = c < C ? weight[(i >> 8) * C + c] : 0.f;
+  const int wg = (Wo + kDwP - 1) / kDwP;  // pixel groups per output row
+  const int npg = Ho * wg;
+  const int pg0 = blockIdx.y * kDwPgPerBlock;
+  const int pgc = min(kDwPgPerBlock, npg - pg0);
+  if (pool_sum) {
+    for (int i = threadIdx.x; i < cgc * 8; i += 256) sums[i] = 0.f;
+    __syncthreads();
   }
-  __syncthreads();
-  float b[8], psum[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    b[e] = cvalid ? __ldg(bias + cg * 8 + e) : 0.f;
-    psum[e] = 0.f;
-  }
-  const int npix = Ho * Wo;
-  const int p0 = blockIdx.y * kDwPixPerBlock;
-  const int p1 = min(p0 + kDwPixPerBlock, npix);
   const uint4* in4 = reinterpret_cast<const uint4*>(in) + static_cast<size_t>(n) * H * W * C8;
-  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * npix * C8;
-  if (cvalid) {
-    for (int pix = p0 + ty; pix < p1; pix += 8) {
-      const int oy = pix / Wo, ox = pix - oy * Wo;
-      float acc[8];
+  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * Ho * Wo * C8;
+  const uint4* w4 = reinterpret_cast<const uint4*>(weight);
+  constexpr int WIN = (kDwP - 1) * S + K;
+  const int items = pgc * cgc;
+  for (int it = threadIdx.x; it < items; it += 256) {
+    const int pgl = it / cgc;
+    const int cgl = it - pgl * cgc;
+    const int cg = cg0 + cgl;
+    const int pg = pg0 + pgl;
+    const int oy = pg / wg;
+    const int ox0 = (pg - oy * wg) * kDwP;
+    float acc[kDwP][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = b[e];
-      for (int ky = 0; ky < k; ++ky) {
-        const int iy = oy * stride - pad_t + ky;
-        if (iy < 0 || iy >= H) continue;
-        for (int kx = 0; kx < k; ++kx) {
-          const int ix = ox * stride - pad_l + kx;
-          if (ix < 0 || ix >= W) continue;
-          const uint4 v = __ldg(in4 + (static_cast<size_t>(iy) * W + ix) * C8 + cg);
-          float f[8];
-          unpack8(v, f);
-          const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * k + kx) * 256 + tx * 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * k + kx) * 256 + tx * 8 + 4);
-          acc[0] = fmaf(f[0], w0.x, acc[0]);
-          acc[1] = fmaf(f[1], w0.y, acc[1]);
-          acc[2] = fmaf(f[2], w0.z, acc[2]);
-          acc[3] = fmaf(f[3], w0.w, acc[3]);
-          acc[4] = fmaf(f[4], w1.x, acc[4]);
-          acc[5] = fmaf(f[5], w1.y, acc[5]);
-          acc[6] = fmaf(f[6], w1.z, acc[6]);
-          acc[7] = fmaf(f[7], w1.w, acc[7]);
+    for (int e = 0; e < 8; ++e) {
+      const float b = __ldg(bias + cg * 8 + e);
+#pragma unroll
+      for (int p = 0; p < kDwP; ++p) acc[p][e] = b;
+    }
+    const int ix0 = ox0 * S - pad_l;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * S - pad_t + ky;
+      if (iy < 0 || iy >= H) continue;
+      float wr[K][8];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const uint4 wv = __ldg(w4 + static_cast<size_t>(ky * K + kx) * C8 + cg);
+        unpack8(wv, wr[kx]);
+      }
+      const uint4* row = in4 + static_cast<size_t>(iy) * W * C8 + cg;
+#pragma unroll
+      for (int dx = 0; dx < WIN; ++dx) {
+        const int ix = ix0 + dx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = __ldg(row + static_cast<size_t>(ix) * C8);
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int p = 0; p < kDwP; ++p) {
+          const int kx = dx - p * S;  // compile-time after unrolling
+          if (kx >= 0 && kx < K) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(f[e], wr[kx][e], acc[p][e]);
+          }
         }
       }
+    }
+    float ps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = act_f(acc[e], act);
-      const uint4 o = pack8(acc);
-      out4[static_cast<size_t>(pix) * C8 + cg] = o;
-      if (pool_sum) {
-        // pool what the next layer actually reads (the bf16-rounded activation)
-        float r[8];
-        unpack8(o, r);
+    for (int p = 0; p < kDwP; ++p) {
+      if (ox0 + p < Wo) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) psum[e] += r[e];
+        for (int e = 0; e < 8; ++e) acc[p][e] = act_f(acc[p][e], act);
+        const uint4 o = pack8(acc[p]);
+        out4[(static_cast<size_t>(oy) * Wo + ox0 + p) * C8 + cg] = o;
+        if (pool_sum) {  // pool what the next layer actually reads (the bf16-rounded activation)
+          float r[8];
+          unpack8(o, r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ps[e] += r[e];
+        }
       }
+    }
+    if (pool_sum) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&sums[cgl * 8 + e], ps[e]);
     }
   }
   if (pool_sum) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) red[ty][tx * 8 + e] = psum[e];
     __syncthreads();
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c < C) {
-      float s = 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
-      atomicAdd(pool_sum + static_cast<size_t>(n) * C + c, s);
-    }
+    for (int i = threadIdx.x; i < cgc * 8; i += 256)
+      atomicAdd(pool_sum + static_cast<size_t>(n) * C + cg0 * 8 + i, sums[i]);
   }
 }
 
@@ -349,14 +366,25 @@ extern "C" int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t
   return check_launch("maxpool3x3s2_kernel");
 }
 
-extern "C" int octseg_dwconv(const void* in, const float* weight, const float* bias, void* out, int32_t N, int32_t H,
+extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bias, void* out, int32_t N, int32_t H,
                              int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l,
                              int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, void* stream) {
-  if (C % 8 || k > 5) return fail(OCTSEG_EINVAL, "dwconv: C%%8==0 and k<=5 required (C=%d k=%d)", C, k);
-  dim3 grid(cdiv(C / 8, 32), cdiv(Ho * Wo, kDwPixPerBlock), N);
-  dwconv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), weight, bias, static_cast<__nv_bfloat16*>(out), H, W, C, k, stride,
-      pad_t, pad_l, Ho, Wo, act, pool_sum);
+  if (C % 8) return fail(OCTSEG_EINVAL, "dwconv: C must be a multiple of 8 (C=%d)", C);
+  const int C8 = C / 8;
+  const int wg = cdiv(Wo, kDwP);
+  dim3 grid(cdiv(C8, kDwCgChunk), cdiv(Ho * wg, kDwPgPerBlock), N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* i = static_cast<const __nv_bfloat16*>(in);
+  const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(weight);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+#define OCTSEG_DW(KK, SS) \
+  dwconv_kernel<KK, SS><<<grid, 256, 0, st>>>(i, w, bias, o, H, W, C, pad_t, pad_l, Ho, Wo, act, pool_sum)
+  if (k == 3 && stride == 1) OCTSEG_DW(3, 1);
+  else if (k == 3 && stride == 2) OCTSEG_DW(3, 2);
+  else if (k == 5 && stride == 1) OCTSEG_DW(5, 1);
+  else if (k == 5 && stride == 2) OCTSEG_DW(5, 2);
+  else return fail(OCTSEG_EINVAL, "dwconv: unsupported kernel %d / stride %d", k, stride);
+#undef OCTSEG_DW
   return check_launch("dwconv_kernel");
 }
 

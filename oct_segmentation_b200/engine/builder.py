@@ -128,7 +128,7 @@ class Builder:
                pad: Tuple[int, int], out_hw: Tuple[int, int], act: str, pool: Optional[torch.Tensor]) -> Act:
         assert x.C % 8 == 0
         out = self.new_act(out_hw[0], out_hw[1], x.C)
-        wk = w.detach().float().reshape(x.C, k, k).permute(1, 2, 0).contiguous().to(self.device)  # [kh][kw][C]
+        wk = w.detach().float().reshape(x.C, k, k).permute(1, 2, 0).contiguous().to(torch.bfloat16).to(self.device)  # [kh][kw][C]
         bk = b.detach().float().contiguous().to(self.device)
         self._keep += [wk, bk]
         lib, a = self.lib, _lib.ACT[act]

@@ -105,7 +105,7 @@ class Bf16Builder(CpuBuilder):
         return a
 
     def dwconv(self, x, w, b, **k):
-        a = super().dwconv(x, w, b, **k)
+        a = super().dwconv(x, _r16(w.detach().float()), b, **k)        # the kernel keeps dw weights in bf16
         a.t = _r16(a.t)
         k['pool'].copy_(a.t[..., :a.C].sum(dim=(1, 2)))     # the kernel pools the rounded values
         return a
