@@ -137,16 +137,17 @@ int octseg_dwconv(const void* in, const void* weight /* bf16 [kh][kw][C] */, con
                   int32_t pad_t, int32_t pad_l, int32_t Ho, int32_t Wo, int32_t act,
                   float* pool_sum, void* stream);
 
-/* Squeeze-excite gate: s = sigmoid(W2 · swish(W1 · mean + b1) + b2), fp32 [N][C]. */
-int octseg_se_gate(const float* pool_sum, float inv_hw, const float* w1 /* [Cr][C] */, const float* b1,
-                   const float* w2 /* [C][Cr] */, const float* b2, float* gate,
-                   int32_t N, int32_t C, int32_t Cr, void* stream);
+/* Squeeze-excite (efficientnet_pytorch MBConvBlock: adaptive_avg_pool2d -> _se_reduce -> swish ->
+   _se_expand -> sigmoid -> gate * x), folded into the projection 1x1 conv's weights:
+   hidden[n][r] = swish(w1[r,:] . (pool_sum[n,:] * inv_hw) + b1[r])                 fp32 [N][Cr]     */
+int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1 /* [Cr][C] */, const float* b1,
+                     float* hidden, int32_t N, int32_t C, int32_t Cr, void* stream);
 
-/* Per-image gate folded into the project 1x1 weights:
-   out[n][row][k] = bf16(w[row][k] * gate[n][k]) for k < C, 0 for padded k. */
-int octseg_scale_weights(const float* w /* fp32 [rows][Ktot] */, const float* gate /* [N][C] */,
-                         void* out /* bf16 [N][rows][Ktot] */, int32_t N, int32_t rows, int32_t Ktot,
-                         int32_t C, void* stream);
+/* gate[n][k] = sigmoid(w2[k,:] . hidden[n,:] + b2[k]);  out[n][row][k] = bf16(w[row][k] * gate[n][k])
+   for k < C and 0 for the K padding: per-image weights of the projection conv (B tensor map z = n). */
+int octseg_se_scale_weights(const float* hidden, const float* w2t /* fp32 [Cr][C] */, const float* b2,
+                            const float* w /* fp32 [rows][Ktot] */, void* out /* bf16 [N][rows][Ktot] */,
+                            int32_t N, int32_t rows, int32_t Ktot, int32_t C, int32_t Cr, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pre-processing: preprocessing_img (src/data/utils.py:159-166): RGB->BGR + cv2.resize

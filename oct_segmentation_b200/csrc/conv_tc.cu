@@ -230,16 +230,18 @@ __device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8
 struct TileCoord {
   int n_tile, tw, th, n, ph, pw, phase;
 };
+// Tile order: channel tile fastest (CTAs running together share the A tile in L2), then the four
+// output phases of one spatial tile (they read the same input pixels), then space, then image.
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int t) {
   TileCoord c;
   c.n_tile = t % p.n_tiles_n;
   t /= p.n_tiles_n;
+  c.phase = t % p.phases;
+  t /= p.phases;
   c.tw = t % p.tiles_w;
   t /= p.tiles_w;
   c.th = t % p.tiles_h;
-  t /= p.tiles_h;
-  c.n = t % p.N;
-  c.phase = t / p.N;
+  c.n = t / p.tiles_h;
   c.ph = c.phase >> 1;
   c.pw = c.phase & 1;
   return c;

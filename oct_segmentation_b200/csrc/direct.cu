@@ -12,7 +12,12 @@ namespace octseg {
 
 __device__ __forceinline__ float act_f(float x, int act) {
   if (act == OCTSEG_ACT_RELU) return fmaxf(x, 0.f);
-  if (act == OCTSEG_ACT_SWISH) return x / (1.f + __expf(-x));
+  if (act == OCTSEG_ACT_SWISH) {  // x*sigmoid(x) = h*tanh(h) + h, h = x/2: one MUFU
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  }
   if (act == OCTSEG_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
   return x;
 }
@@ -158,12 +163,12 @@ constexpr int kDwCgChunk = 128;  // channel groups per block column
 constexpr int kDwPgPerBlock = 64;
 
 template <int K, int S>
-__global__ void __launch_bounds__(256) dwconv_kernel(const __nv_bfloat16* __restrict__ in,
+__global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __restrict__ in,
                                                      const __nv_bfloat16* __restrict__ weight,  // [K*K][C] bf16
                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                      int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo,
                                                      int act, float* __restrict__ pool_sum) {
-  __shared__ float sums[kDwCgChunk * 8];
+  __shared__ float sums[8][kDwCgChunk];  // [e][channel group]: conflict-free for consecutive groups
   const int C8 = C >> 3;
   const int cg0 = blockIdx.x * kDwCgChunk;
   const int cgc = min(kDwCgChunk, C8 - cg0);
@@ -173,127 +178,135 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __nv_bfloat16* __rest
   const int pg0 = blockIdx.y * kDwPgPerBlock;
   const int pgc = min(kDwPgPerBlock, npg - pg0);
   if (pool_sum) {
-    for (int i = threadIdx.x; i < cgc * 8; i += 256) sums[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * kDwCgChunk; i += 256) (&sums[0][0])[i] = 0.f;
     __syncthreads();
   }
-  const uint4* in4 = reinterpret_cast<const uint4*>(in) + static_cast<size_t>(n) * H * W * C8;
-  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * Ho * Wo * C8;
-  const uint4* w4 = reinterpret_cast<const uint4*>(weight);
+  // thread -> fixed channel group, strided over pixel groups: bias / SE sums stay in registers
+  const int lanes_pg = 256 / cgc;  // pixel groups processed per sweep
+  const int cgl = threadIdx.x % cgc;
+  const int pgl0 = threadIdx.x / cgc;
+  const bool active = pgl0 < lanes_pg;
+  const int cg = cg0 + cgl;
+  const uint4* in4 = reinterpret_cast<const uint4*>(in) + static_cast<size_t>(n) * H * W * C8 + cg;
+  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * Ho * Wo * C8 + cg;
+  const uint4* w4 = reinterpret_cast<const uint4*>(weight) + cg;
   constexpr int WIN = (kDwP - 1) * S + K;
-  const int items = pgc * cgc;
-  for (int it = threadIdx.x; it < items; it += 256) {
-    const int pgl = it / cgc;
-    const int cgl = it - pgl * cgc;
-    const int cg = cg0 + cgl;
-    const int pg = pg0 + pgl;
-    const int oy = pg / wg;
-    const int ox0 = (pg - oy * wg) * kDwP;
-    float acc[kDwP][8];
+  float bs[8], ps[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float b = __ldg(bias + cg * 8 + e);
+  for (int e = 0; e < 8; ++e) {
+    bs[e] = active ? __ldg(bias + cg * 8 + e) : 0.f;
+    ps[e] = 0.f;
+  }
+  if (active) {
+    for (int pgl = pgl0; pgl < pgc; pgl += lanes_pg) {
+      const int pg = pg0 + pgl;
+      const int oy = pg / wg;
+      const int ox0 = (pg - oy * wg) * kDwP;
+      float acc[kDwP][8];
 #pragma unroll
-      for (int p = 0; p < kDwP; ++p) acc[p][e] = b;
-    }
-    const int ix0 = ox0 * S - pad_l;
+      for (int p = 0; p < kDwP; ++p)
 #pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-      const int iy = oy * S - pad_t + ky;
-      if (iy < 0 || iy >= H) continue;
-      float wr[K][8];
+        for (int e = 0; e < 8; ++e) acc[p][e] = bs[e];
+      const int ix0 = ox0 * S - pad_l;
+      const int iy0 = oy * S - pad_t;
+      const bool interior = ix0 >= 0 && ix0 + WIN <= W && iy0 >= 0 && iy0 + K <= H;
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const uint4 wv = __ldg(w4 + static_cast<size_t>(ky * K + kx) * C8 + cg);
-        unpack8(wv, wr[kx]);
-      }
-      const uint4* row = in4 + static_cast<size_t>(iy) * W * C8 + cg;
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = iy0 + ky;
+        if (!interior && (iy < 0 || iy >= H)) continue;
+        float wr[K][8];
 #pragma unroll
-      for (int dx = 0; dx < WIN; ++dx) {
-        const int ix = ix0 + dx;
-        if (ix < 0 || ix >= W) continue;
-        const uint4 v = __ldg(row + static_cast<size_t>(ix) * C8);
-        float f[8];
-        unpack8(v, f);
+        for (int kx = 0; kx < K; ++kx) unpack8(__ldg(w4 + static_cast<size_t>(ky * K + kx) * C8), wr[kx]);
+        const uint4* row = in4 + static_cast<size_t>(iy) * W * C8;
 #pragma unroll
-        for (int p = 0; p < kDwP; ++p) {
-          const int kx = dx - p * S;  // compile-time after unrolling
-          if (kx >= 0 && kx < K) {
+        for (int dx = 0; dx < WIN; ++dx) {
+          const int ix = ix0 + dx;
+          const uint4 v =
+              (interior || (ix >= 0 && ix < W)) ? __ldg(row + static_cast<size_t>(ix) * C8) : make_uint4(0, 0, 0, 0);
+          float f[8];
+          unpack8(v, f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(f[e], wr[kx][e], acc[p][e]);
+          for (int p = 0; p < kDwP; ++p) {
+            const int kx = dx - p * S;  // compile-time after unrolling
+            if (kx >= 0 && kx < K) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(f[e], wr[kx][e], acc[p][e]);
+            }
           }
         }
       }
-    }
-    float ps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int p = 0; p < kDwP; ++p) {
-      if (ox0 + p < Wo) {
+      for (int p = 0; p < kDwP; ++p) {
+        if (ox0 + p < Wo) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[p][e] = act_f(acc[p][e], act);
-        const uint4 o = pack8(acc[p]);
-        out4[(static_cast<size_t>(oy) * Wo + ox0 + p) * C8 + cg] = o;
-        if (pool_sum) {  // pool what the next layer actually reads (the bf16-rounded activation)
-          float r[8];
-          unpack8(o, r);
+          for (int e = 0; e < 8; ++e) acc[p][e] = act_f(acc[p][e], act);
+          const uint4 o = pack8(acc[p]);
+          out4[(static_cast<size_t>(oy) * Wo + ox0 + p) * C8] = o;
+          if (pool_sum) {  // pool what the next layer actually reads (the bf16-rounded activation)
+            float r[8];
+            unpack8(o, r);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) ps[e] += r[e];
+            for (int e = 0; e < 8; ++e) ps[e] += r[e];
+          }
         }
       }
     }
     if (pool_sum) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&sums[cgl * 8 + e], ps[e]);
+      for (int e = 0; e < 8; ++e) atomicAdd(&sums[e][cgl], ps[e]);
     }
   }
   if (pool_sum) {
     __syncthreads();
     for (int i = threadIdx.x; i < cgc * 8; i += 256)
-      atomicAdd(pool_sum + static_cast<size_t>(n) * C + cg0 * 8 + i, sums[i]);
+      atomicAdd(pool_sum + static_cast<size_t>(n) * C + cg0 * 8 + i, sums[i & 7][i >> 3]);
   }
 }
 
 // ------------------------------------------------------------------------------------ SE gate
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_sum, float inv_hw,
-                                                      const float* __restrict__ w1, const float* __restrict__ b1,
-                                                      const float* __restrict__ w2, const float* __restrict__ b2,
-                                                      float* __restrict__ gate, int C, int Cr) {
-  extern __shared__ float sm[];
-  float* mean = sm;       // [C]
-  float* hid = sm + C;    // [Cr]
-  const int n = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < C; c += 256) mean[c] = pool_sum[static_cast<size_t>(n) * C + c] * inv_hw;
-  __syncthreads();
-  for (int r = warp; r < Cr; r += 8) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w1[static_cast<size_t>(r) * C + c], mean[c], s);
+// hidden[n][r] = swish(W1[r,:] . mean[n,:] + b1[r]); one warp per (image, hidden unit)
+__global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict__ pool_sum, float inv_hw,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        float* __restrict__ hidden, int C, int Cr) {
+  const int n = blockIdx.y;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= Cr) return;
+  const float* m = pool_sum + static_cast<size_t>(n) * C;
+  const float* w = w1 + static_cast<size_t>(r) * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w + c), __ldg(m + c), s);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      s += b1[r];
-      hid[r] = s / (1.f + __expf(-s));
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float s = b2[c];
-    for (int r = 0; r < Cr; ++r) s = fmaf(w2[static_cast<size_t>(c) * Cr + r], hid[r], s);
-    gate[static_cast<size_t>(n) * C + c] = 1.f / (1.f + __expf(-s));
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    s = s * inv_hw + b1[r];
+    hidden[static_cast<size_t>(n) * Cr + r] = s / (1.f + __expf(-s));
   }
 }
 
-__global__ void scale_weights_kernel(const float* __restrict__ w, const float* __restrict__ gate,
-                                     __nv_bfloat16* __restrict__ out, int N, int rows, int Ktot, int C) {
-  const size_t per = static_cast<size_t>(rows) * Ktot;
-  const size_t total = per * N;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int n = idx / per;
-    const size_t r = idx - n * per;
-    const int kk = r % Ktot;
-    const float g = kk < C ? gate[static_cast<size_t>(n) * C + kk] : 0.f;
-    out[idx] = __float2bfloat16_rn(w[r] * g);
+// gate[n][k] = sigmoid(W2[k,:] . hidden[n,:] + b2[k]) for this block's 256 input channels k, then
+// out[n][row][k] = bf16(w[row][k] * gate[n][k]) for every weight row (0 for the K padding).
+__global__ void __launch_bounds__(256) se_scale_weights_kernel(const float* __restrict__ hidden,
+                                                               const float* __restrict__ w2t,  // [Cr][C]
+                                                               const float* __restrict__ b2,
+                                                               const float* __restrict__ w,    // [rows][Ktot]
+                                                               __nv_bfloat16* __restrict__ out, int rows, int Ktot,
+                                                               int C, int Cr) {
+  extern __shared__ float hid[];
+  const int n = blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  for (int r = threadIdx.x; r < Cr; r += 256) hid[r] = hidden[static_cast<size_t>(n) * Cr + r];
+  __syncthreads();
+  if (k >= Ktot) return;
+  float g = 0.f;
+  if (k < C) {
+    float s = b2[k];
+    for (int r = 0; r < Cr; ++r) s = fmaf(__ldg(w2t + static_cast<size_t>(r) * C + k), hid[r], s);
+    g = 1.f / (1.f + __expf(-s));
   }
+  __nv_bfloat16* o = out + static_cast<size_t>(n) * rows * Ktot + k;
+  const float* wk = w + k;
+  for (int row = 0; row < rows; ++row) o[static_cast<size_t>(row) * Ktot] = __float2bfloat16_rn(__ldg(wk + static_cast<size_t>(row) * Ktot) * g);
 }
 
 static int grid_for(size_t total, int block) {
@@ -388,18 +401,18 @@ extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bi
   return check_launch("dwconv_kernel");
 }
 
-extern "C" int octseg_se_gate(const float* pool_sum, float inv_hw, const float* w1, const float* b1, const float* w2,
-                              const float* b2, float* gate, int32_t N, int32_t C, int32_t Cr, void* stream) {
-  const size_t smem = static_cast<size_t>(C + Cr) * sizeof(float);
-  if (smem > 48 * 1024) return fail(OCTSEG_EINVAL, "se_gate: C+Cr too large");
-  se_gate_kernel<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(pool_sum, inv_hw, w1, b1, w2, b2, gate, C, Cr);
-  return check_launch("se_gate_kernel");
+extern "C" int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1, const float* b1, float* hidden,
+                                int32_t N, int32_t C, int32_t Cr, void* stream) {
+  dim3 grid(cdiv(Cr, 8), N);
+  se_hidden_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pool_sum, inv_hw, w1, b1, hidden, C, Cr);
+  return check_launch("se_hidden_kernel");
 }
 
-extern "C" int octseg_scale_weights(const float* w, const float* gate, void* out, int32_t N, int32_t rows,
-                                    int32_t Ktot, int32_t C, void* stream) {
-  const size_t total = static_cast<size_t>(N) * rows * Ktot;
-  scale_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, gate, static_cast<__nv_bfloat16*>(out), N, rows, Ktot, C);
-  return check_launch("scale_weights_kernel");
+extern "C" int octseg_se_scale_weights(const float* hidden, const float* w2t, const float* b2, const float* w, void* out,
+                                       int32_t N, int32_t rows, int32_t Ktot, int32_t C, int32_t Cr, void* stream) {
+  if (Cr > 4096) return fail(OCTSEG_EINVAL, "se_scale_weights: Cr too large");
+  dim3 grid(cdiv(Ktot, 256), N);
+  se_scale_weights_kernel<<<grid, 256, static_cast<size_t>(Cr) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      hidden, w2t, b2, w, static_cast<__nv_bfloat16*>(out), rows, Ktot, C, Cr);
+  return check_launch("se_scale_weights_kernel");
 }
