@@ -68,7 +68,9 @@ typedef struct octseg_conv_seg {
   int32_t off_w[2];
   int32_t c_per_tile; /* 0: all tiles read channels [0,C); >0 (grouped conv): tile n reads
                          channels starting at n*c_per_tile                                   */
-  int32_t cchunks;    /* 64-channel chunks per tap                                           */
+  int32_t cchunks;    /* kc-channel chunks per tap                                           */
+  int32_t kc;         /* chunk width 16 | 32 | 64 (32B / 64B / 128B swizzle); 64/kc consecutive
+                         (tap, chunk) sub-blocks of a segment share one pipeline stage          */
 } octseg_conv_seg;
 
 typedef struct octseg_conv_desc {
@@ -82,12 +84,12 @@ typedef struct octseg_conv_desc {
   int32_t cout_per_tile; /* real output channels each channel tile stores (<= BN, mult. of 8
                             for bf16 output)                                                 */
   int32_t Cout;        /* total real output channels                                         */
-  /* packed weights, bf16 [Z][n_tiles_n*BN][Ktot], Ktot = 64 * (k-iterations per tile);
+  /* packed weights, bf16 [Z][n_tiles_n*BN][Ktot], Ktot = sum over segments of kh*kw*cchunks*kc;
      Z = phases * (per_image_weights ? N : 1), z = phase + phases*image                      */
   const void* weight;
   int32_t Ktot;
   int32_t per_image_weights;
-  const float* bias;   /* fp32 [n_tiles_n*BN] (zero padded)                                  */
+  const float* bias;   /* fp32 [n_tiles_n*BN + 64] (zero padded)                             */
   int32_t act;         /* OCTSEG_ACT_*                                                       */
   int32_t res_mode;    /* OCTSEG_RES_*                                                       */
   const void* res;     /* bf16 NHWC residual at output resolution, or NULL                   */

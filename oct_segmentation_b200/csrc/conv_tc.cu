@@ -38,11 +38,12 @@ struct SegK {
   int C, kh, kw, mul;
   int off_h[2], off_w[2];
   int c_per_tile, cchunks;
+  int kc;  // chunk width (16/32/64 channels): swizzle 32B/64B/128B, 64/kc sub-blocks per stage
 };
 
 struct __align__(64) ConvKParams {
   CUtensorMap tmA[OCTSEG_MAX_SEG];
-  CUtensorMap tmB;
+  CUtensorMap tmB[3];  // weight boxes (kc x BN) for kc = 16, 32, 64
   CUtensorMap tmOut;  // bf16 NHWC output (4-D; 5-D phase-strided view in 4-phase mode)
   SegK seg[OCTSEG_MAX_SEG];
   int nseg, phases, N, Hq, Wq, TH, TW, tiles_h, tiles_w;
@@ -50,7 +51,6 @@ struct __align__(64) ConvKParams {
   int per_image_weights, act, res_mode, out_mode;
   int k_iters, nstages, total_tiles;
   int use_tma_store;
-  uint32_t stage_tx_bytes;
   const float* bias;
   const __nv_bfloat16* res;
   int res_ldc;
@@ -139,16 +139,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+// K-major swizzled shared-memory matrix descriptor.  Rows are kc*2 bytes (32/64/128 = the swizzle
+// span), 8-row groups are 8*kc*2 bytes apart (SBO).  layout_type: 2 = SWIZZLE_128B, 4 = 64B, 6 = 32B.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, int kc) {
+  const uint32_t sbo = static_cast<uint32_t>(kc) * 16u;  // 8 rows * kc * 2 B
+  const uint64_t layout = kc == 64 ? 2 : (kc == 32 ? 4 : 6);
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);  // start address
-  d |= static_cast<uint64_t>(1) << 16;                 // leading byte offset (unused for SW128 K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;         // stride byte offset
+  d |= static_cast<uint64_t>(1) << 16;                 // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;          // stride byte offset
   d |= static_cast<uint64_t>(1) << 46;                 // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(2) << 61;                 // SWIZZLE_128B
+  d |= layout << 61;
   return d;
 }
+__device__ __forceinline__ int kc_index(int kc) { return kc == 64 ? 2 : (kc == 32 ? 1 : 0); }
 
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&p.tmA[s]);
-    prefetch_tmap(&p.tmB);
+    for (int s = 0; s < 3; ++s) prefetch_tmap(&p.tmB[s]);
     if (p.use_tma_store) prefetch_tmap(&p.tmOut);
   }
   if (warp == 1) {
@@ -313,18 +317,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int h0 = sg.mul * tc.th * p.TH + sg.off_h[tc.ph];
           const int w0 = sg.mul * tc.tw * p.TW + sg.off_w[tc.pw];
           const int cbase = sg.c_per_tile * tc.n_tile;
+          const int subs = 64 / sg.kc;                                   // sub-blocks per stage
+          const uint32_t a_sub = 128u * sg.kc * 2u, b_sub = static_cast<uint32_t>(p.BN) * sg.kc * 2u;
+          const uint32_t tx_sub = static_cast<uint32_t>(p.TH * p.TW + p.BN) * sg.kc * 2u;
+          const CUtensorMap* mb = &p.tmB[kc_index(sg.kc)];
+          int in_stage = 0;
           for (int ty = 0; ty < sg.kh; ++ty) {
             for (int tx = 0; tx < sg.kw; ++tx) {
               for (int cc = 0; cc < sg.cchunks; ++cc) {
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                mbar_arrive_expect_tx(bar_full + 8 * stage, p.stage_tx_bytes);
-                tma_load_4d(smemA + stage * kABytes, &p.tmA[s], bar_full + 8 * stage, cbase + cc * 64,
-                            w0 + tx, h0 + ty, tc.n);
-                tma_load_3d(smemB + stage * b_bytes, &p.tmB, bar_full + 8 * stage, kofs, brow, bz);
-                kofs += 64;
-                if (++stage == nst) {
-                  stage = 0;
-                  phase ^= 1;
+                if (in_stage == 0) mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                tma_load_4d(smemA + stage * kABytes + in_stage * a_sub, &p.tmA[s], bar_full + 8 * stage,
+                            cbase + cc * sg.kc, w0 + tx, h0 + ty, tc.n);
+                tma_load_3d(smemB + stage * b_bytes + in_stage * b_sub, mb, bar_full + 8 * stage, kofs, brow, bz);
+                kofs += sg.kc;
+                const bool last = (ty == sg.kh - 1) && (tx == sg.kw - 1) && (cc == sg.cchunks - 1);
+                if (++in_stage == subs || last) {
+                  // the arrive comes after the copies were issued: the phase cannot complete before it
+                  mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub * in_stage);
+                  in_stage = 0;
+                  if (++stage == nst) {
+                    stage = 0;
+                    phase ^= 1;
+                  }
                 }
               }
             }
@@ -346,18 +360,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.BN);
-        for (int k = 0; k < p.k_iters; ++k) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(smemA + stage * kABytes);
-          const uint64_t bdesc = make_sw128_desc(smemB + stage * b_bytes);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)  // 4 x (K=16) per 64-channel chunk: +32 B inside the swizzle atom
-            tc_mma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
-          tc_commit(bar_empty + 8 * stage);
-          if (++stage == nst) {
-            stage = 0;
-            phase ^= 1;
+        uint32_t first = 1;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int kc = p.seg[s].kc;
+          const int subs = 64 / kc, steps = kc / 16;
+          const uint32_t a_sub = 128u * kc * 2u, b_sub = static_cast<uint32_t>(p.BN) * kc * 2u;
+          int nsub = p.seg[s].kh * p.seg[s].kw * p.seg[s].cchunks;
+          while (nsub > 0) {
+            const int n = nsub < subs ? nsub : subs;
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            for (int j = 0; j < n; ++j) {
+              const uint64_t adesc = make_kmajor_desc(smemA + stage * kABytes + j * a_sub, kc);
+              const uint64_t bdesc = make_kmajor_desc(smemB + stage * b_bytes + j * b_sub, kc);
+              for (int t = 0; t < steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
+                tc_mma_bf16(d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+            tc_commit(bar_empty + 8 * stage);
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1;
+            }
+            nsub -= n;
           }
         }
         tc_commit(bar_tfull + 8 * acc);
@@ -390,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
 
       // full 64-channel chunks: registers -> swizzled shared tile -> one TMA store per chunk
-      const int n_tma = p.use_tma_store ? (nvalid >> 6) : 0;
+      const int n_tma = p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0;
       for (int ck = 0; ck < n_tma; ++ck) {
         const int c0 = ck * 64;
         const uint32_t sbuf = smemOut + out_buf * kOutBytes;
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int cc = c0 + 32 * h + 8 * g;
-            const uint4 ov = epi_pack8(v + 8 * g, bias + cc, rrow ? rrow + cc : nullptr, p.act, p.res_mode);
+            const uint4 ov = epi_pack8(v + 8 * g, bias + cc, (rrow && cc < nvalid) ? rrow + cc : nullptr, p.act, p.res_mode);
             const uint32_t dst = sbuf + row * 128 + (((4 * h + g) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z),
                          "r"(ov.w)
@@ -495,13 +521,15 @@ static EncodeTiledFn get_encode_fn() {
 
 static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr,
-                      const char* what) {
+                      const char* what, int kc = 64) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(OCTSEG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                   reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                   reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(OCTSEG_ECUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, static_cast<int>(r));
@@ -539,9 +567,14 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   std::memset(pl, 0, sizeof(*pl));
   ConvKParams& kp = pl->kp;
 
-  int k_iters = 0;
+  int k_iters = 0, k_total = 0;
+  bool kc_used[3] = {false, false, false};
   for (int s = 0; s < d->nseg; ++s) {
     const octseg_conv_seg& sg = d->seg[s];
+    if (sg.kc != 16 && sg.kc != 32 && sg.kc != 64) {
+      delete pl;
+      return fail(OCTSEG_EINVAL, "segment %d: kc=%d must be 16, 32 or 64", s, sg.kc);
+    }
     if (sg.mul < 1 || sg.mul > 2 || sg.kh < 1 || sg.kw < 1 || sg.cchunks < 1 || sg.ldc % 8 ||
         (reinterpret_cast<uintptr_t>(sg.ptr) & 15) || sg.N != d->N) {
       delete pl;
@@ -552,9 +585,10 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
                               static_cast<uint64_t>(sg.N)};
     const uint64_t strides[3] = {static_cast<uint64_t>(sg.ldc) * 2, static_cast<uint64_t>(sg.W) * sg.ldc * 2,
                                  static_cast<uint64_t>(sg.H) * sg.W * sg.ldc * 2};
-    const uint32_t box[4] = {64u, static_cast<uint32_t>(d->TW * sg.mul), static_cast<uint32_t>(d->TH * sg.mul), 1u};
+    const uint32_t box[4] = {static_cast<uint32_t>(sg.kc), static_cast<uint32_t>(d->TW * sg.mul),
+                             static_cast<uint32_t>(d->TH * sg.mul), 1u};
     const uint32_t estr[4] = {1u, static_cast<uint32_t>(sg.mul), static_cast<uint32_t>(sg.mul), 1u};
-    int rc = encode_map(&kp.tmA[s], sg.ptr, 4, dims, strides, box, estr, "A");
+    int rc = encode_map(&kp.tmA[s], sg.ptr, 4, dims, strides, box, estr, "A", sg.kc);
     if (rc) {
       delete pl;
       return rc;
@@ -570,23 +604,34 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     k.off_w[1] = sg.off_w[1];
     k.c_per_tile = sg.c_per_tile;
     k.cchunks = sg.cchunks;
-    k_iters += sg.kh * sg.kw * sg.cchunks;
+    k.kc = sg.kc;
+    const int nsub = sg.kh * sg.kw * sg.cchunks, subs = 64 / sg.kc;
+    k_iters += (nsub + subs - 1) / subs;
+    k_total += nsub * sg.kc;
+    kc_used[sg.kc == 64 ? 2 : (sg.kc == 32 ? 1 : 0)] = true;
   }
-  if (k_iters * 64 != d->Ktot) {
+  if (k_total != d->Ktot) {
     delete pl;
-    return fail(OCTSEG_EINVAL, "Ktot=%d does not match 64 * k-iterations (%d)", d->Ktot, k_iters);
+    return fail(OCTSEG_EINVAL, "Ktot=%d does not match the segments' sum of kh*kw*cchunks*kc (%d)", d->Ktot, k_total);
   }
   {
     const uint64_t rows = static_cast<uint64_t>(d->n_tiles_n) * d->BN;
     const uint64_t Z = static_cast<uint64_t>(d->phases) * (d->per_image_weights ? d->N : 1);
     const uint64_t dims[3] = {static_cast<uint64_t>(d->Ktot), rows, Z};
     const uint64_t strides[2] = {static_cast<uint64_t>(d->Ktot) * 2, rows * d->Ktot * 2};
-    const uint32_t box[3] = {64u, static_cast<uint32_t>(d->BN), 1u};
     const uint32_t estr[3] = {1u, 1u, 1u};
-    int rc = encode_map(&kp.tmB, d->weight, 3, dims, strides, box, estr, "B");
-    if (rc) {
-      delete pl;
-      return rc;
+    for (int i = 0; i < 3; ++i) {
+      const int kc = 16 << i;
+      if (!kc_used[i]) {
+        kp.tmB[i] = kp.tmA[0];  // never dereferenced; keeps the parameter block initialised
+        continue;
+      }
+      const uint32_t box[3] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(d->BN), 1u};
+      int rc = encode_map(&kp.tmB[i], d->weight, 3, dims, strides, box, estr, "B", kc);
+      if (rc) {
+        delete pl;
+        return rc;
+      }
     }
   }
   kp.nseg = d->nseg;
@@ -607,7 +652,6 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   kp.res_mode = d->res ? d->res_mode : OCTSEG_RES_NONE;
   kp.out_mode = d->out_mode;
   kp.k_iters = k_iters;
-  kp.stage_tx_bytes = static_cast<uint32_t>(d->TH * d->TW * 128 + d->BN * 128);
   kp.bias = d->bias;
   kp.res = static_cast<const __nv_bfloat16*>(d->res);
   kp.res_ldc = d->res_ldc;

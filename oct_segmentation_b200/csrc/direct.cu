@@ -158,9 +158,48 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 // consecutive 16-byte chunks whatever C is.  A block owns a contiguous run of pixel groups of one
 // image and a chunk of <= 128 channel groups; squeeze-excite sums go through shared-memory
 // atomics and leave the block as one global atomic per channel.
-constexpr int kDwP = 4;          // output pixels per item
+__host__ __device__ constexpr int dw_p(int K) { return K == 3 ? 4 : 2; }  // output pixels per item (register budget)
 constexpr int kDwCgChunk = 128;  // channel groups per block column
 constexpr int kDwPgPerBlock = 64;
+
+// All loads of one filter row (WIN input vectors + K weight vectors) are issued together before
+// any of them is consumed, so a warp exposes one memory latency per row instead of one per load.
+template <int K, int S, bool CHECK>
+__device__ __forceinline__ void dw_rows(float (&acc)[dw_p(K)][8], const uint4* __restrict__ in4,
+                                        const uint4* __restrict__ w4, int C8, int W, int H, int ix0, int iy0) {
+  constexpr int kDwP = dw_p(K);
+  constexpr int WIN = (kDwP - 1) * S + K;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = iy0 + ky;
+    if (CHECK && (iy < 0 || iy >= H)) continue;
+    const uint4* row = in4 + static_cast<size_t>(iy) * W * C8;
+    uint4 v[WIN], wv[K];
+#pragma unroll
+    for (int dx = 0; dx < WIN; ++dx) {
+      const int ix = ix0 + dx;
+      v[dx] = (!CHECK || (ix >= 0 && ix < W)) ? __ldg(row + static_cast<size_t>(ix) * C8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) wv[kx] = __ldg(w4 + static_cast<size_t>(ky * K + kx) * C8);
+    float wr[K][8];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) unpack8(wv[kx], wr[kx]);
+#pragma unroll
+    for (int dx = 0; dx < WIN; ++dx) {
+      float f[8];
+      unpack8(v[dx], f);
+#pragma unroll
+      for (int p = 0; p < kDwP; ++p) {
+        const int kx = dx - p * S;  // compile-time after unrolling
+        if (kx >= 0 && kx < K) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(f[e], wr[kx][e], acc[p][e]);
+        }
+      }
+    }
+  }
+}
 
 template <int K, int S>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __restrict__ in,
@@ -169,6 +208,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
                                                      int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo,
                                                      int act, float* __restrict__ pool_sum) {
   __shared__ float sums[8][kDwCgChunk];  // [e][channel group]: conflict-free for consecutive groups
+  constexpr int kDwP = dw_p(K);
   const int C8 = C >> 3;
   const int cg0 = blockIdx.x * kDwCgChunk;
   const int cgc = min(kDwCgChunk, C8 - cg0);
@@ -210,31 +250,10 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
       const int ix0 = ox0 * S - pad_l;
       const int iy0 = oy * S - pad_t;
       const bool interior = ix0 >= 0 && ix0 + WIN <= W && iy0 >= 0 && iy0 + K <= H;
-#pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int iy = iy0 + ky;
-        if (!interior && (iy < 0 || iy >= H)) continue;
-        float wr[K][8];
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) unpack8(__ldg(w4 + static_cast<size_t>(ky * K + kx) * C8), wr[kx]);
-        const uint4* row = in4 + static_cast<size_t>(iy) * W * C8;
-#pragma unroll
-        for (int dx = 0; dx < WIN; ++dx) {
-          const int ix = ix0 + dx;
-          const uint4 v =
-              (interior || (ix >= 0 && ix < W)) ? __ldg(row + static_cast<size_t>(ix) * C8) : make_uint4(0, 0, 0, 0);
-          float f[8];
-          unpack8(v, f);
-#pragma unroll
-          for (int p = 0; p < kDwP; ++p) {
-            const int kx = dx - p * S;  // compile-time after unrolling
-            if (kx >= 0 && kx < K) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(f[e], wr[kx][e], acc[p][e]);
-            }
-          }
-        }
-      }
+      if (interior)
+        dw_rows<K, S, false>(acc, in4, w4, C8, W, H, ix0, iy0);
+      else
+        dw_rows<K, S, true>(acc, in4, w4, C8, W, H, ix0, iy0);
 #pragma unroll
       for (int p = 0; p < kDwP; ++p) {
         if (ox0 + p < Wo) {
@@ -384,7 +403,7 @@ extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bi
                              int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, void* stream) {
   if (C % 8) return fail(OCTSEG_EINVAL, "dwconv: C must be a multiple of 8 (C=%d)", C);
   const int C8 = C / 8;
-  const int wg = cdiv(Wo, kDwP);
+  const int wg = cdiv(Wo, dw_p(k));
   dim3 grid(cdiv(C8, kDwCgChunk), cdiv(Ho * wg, kDwPgPerBlock), N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* i = static_cast<const __nv_bfloat16*>(in);

@@ -19,7 +19,20 @@ import torch
 
 from .. import _lib
 
-KC = 64  # channels per K-iteration (one 128-byte swizzle atom of bf16)
+KC = 64  # K elements per pipeline stage (one 128-byte swizzle atom of bf16)
+
+
+def choose_kc(c_eff: int) -> int:
+    """Channel-chunk width of a K-segment: 64 (128B swizzle), 32 (64B) or 16 (32B).  Narrow sources
+    use narrow chunks so neither TMA nor the MMAs spend time on zero padding; 64/kc consecutive
+    (tap, chunk) sub-blocks share one pipeline stage."""
+    if c_eff > 48:
+        return 64
+    if c_eff > 32:
+        return 16
+    if c_eff > 16:
+        return 32
+    return 16
 
 
 def pad8(c: int) -> int:
@@ -57,6 +70,7 @@ class SegSpec:
     off_w: Tuple[int, int]
     c_per_tile: int
     cchunks: int
+    kc: int = 64
 
 
 @dataclass
@@ -172,17 +186,21 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
     for (sN, sH, sW, sC, ldc), up in srcs:
         assert sN == N
         if transposed:
-            seg = SegSpec(N, sH, sW, sC, ldc, 2, 2, 1, (-1, 0), (-1, 0), 0, -(-sC // KC))
+            kc = choose_kc(sC)
+            seg = SegSpec(N, sH, sW, sC, ldc, 2, 2, 1, (-1, 0), (-1, 0), 0, -(-sC // kc), kc)
         elif up:
-            seg = SegSpec(N, sH, sW, sC, ldc, 2, 2, 1, (-1, 0), (-1, 0), 0, -(-sC // KC))
+            kc = choose_kc(sC)
+            seg = SegSpec(N, sH, sW, sC, ldc, 2, 2, 1, (-1, 0), (-1, 0), 0, -(-sC // kc), kc)
         elif phases == 4:
             # full-resolution skip tensor seen from the half-resolution tile grid
-            seg = SegSpec(N, sH, sW, sC, ldc, 3, 3, 2, (-1, 0), (-1, 0), 0, -(-sC // KC))
+            kc = choose_kc(sC)
+            seg = SegSpec(N, sH, sW, sC, ldc, 3, 3, 2, (-1, 0), (-1, 0), 0, -(-sC // kc), kc)
         else:
             kh, kw = w.shape[2], w.shape[3]
             cg = sC // groups
+            kc = choose_kc(cg if groups > 1 else sC)
             seg = SegSpec(N, sH, sW, sC, ldc, kh, kw, stride, (-pad[0], -pad[0]), (-pad[1], -pad[1]),
-                          cg if groups > 1 else 0, -(-(cg if groups > 1 else sC) // KC))
+                          cg if groups > 1 else 0, -(-(cg if groups > 1 else sC) // kc), kc)
         segs.append(seg)
 
         for phase in range(phases):
@@ -200,14 +218,14 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
                     else:
                         wt = w[:, c_lo:c_lo + sC, ty, tx]
                     for cc in range(seg.cchunks):
-                        blk = torch.zeros(rows, KC)
+                        blk = torch.zeros(rows, seg.kc)
                         if groups > 1:
                             cg, cout_g = sC // groups, cout // groups
-                            lo, hi = cc * KC, min((cc + 1) * KC, cg)
+                            lo, hi = cc * seg.kc, min((cc + 1) * seg.kc, cg)
                             for g in range(groups):
                                 blk[g * BN:g * BN + cout_g, :hi - lo] = wt[g * cout_g:(g + 1) * cout_g, lo:hi]
                         else:
-                            lo, hi = cc * KC, min((cc + 1) * KC, sC)
+                            lo, hi = cc * seg.kc, min((cc + 1) * seg.kc, sC)
                             blk[:cout, :hi - lo] = wt[:, lo:hi]
                         blocks[phase].append(blk)
         c_lo += sC
@@ -220,7 +238,7 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
 
 def pad_bias(bias: Optional[torch.Tensor], geom: ConvGeom, cout: int, groups: int = 1) -> torch.Tensor:
     """fp32 bias laid out like the packed weight rows: [n_tiles_n * BN], zero padded."""
-    out = torch.zeros(geom.n_tiles_n * geom.BN, dtype=torch.float32)
+    out = torch.zeros(geom.n_tiles_n * geom.BN + 64, dtype=torch.float32)   # +64: the epilogue reads whole 64-wide chunks
     if bias is not None:
         b = bias.detach().to(torch.float32).cpu()
         if groups > 1:
@@ -254,7 +272,7 @@ class ConvPlan:
             s.kh, s.kw, s.mul = sg.kh, sg.kw, sg.mul
             s.off_h[0], s.off_h[1] = sg.off_h
             s.off_w[0], s.off_w[1] = sg.off_w
-            s.c_per_tile, s.cchunks = sg.c_per_tile, sg.cchunks
+            s.c_per_tile, s.cchunks, s.kc = sg.c_per_tile, sg.cchunks, sg.kc
         d.phases, d.N, d.Hq, d.Wq, d.TH, d.TW = geom.phases, geom.N, geom.Hq, geom.Wq, geom.TH, geom.TW
         d.BN, d.n_tiles_n, d.cout_per_tile, d.Cout = geom.BN, geom.n_tiles_n, geom.cout_per_tile, geom.Cout
         d.weight, d.Ktot, d.per_image_weights = self.weight.data_ptr(), geom.Ktot, int(per_image_weights)

@@ -112,16 +112,16 @@ def emulate(geom: ConvGeom, packed: torch.Tensor, bias_rows: torch.Tensor, xs_nh
                     g = g * (hv[:, None] & wv[None, :])[None, :, :, None]
                     for cc in range(sg.cchunks):
                         for t in range(geom.n_tiles_n):
-                            c0 = sg.c_per_tile * t + cc * 64
-                            a = torch.zeros(N, Hq, Wq, 64)
-                            hi = min(c0 + 64, sg.C)
+                            c0 = sg.c_per_tile * t + cc * sg.kc
+                            a = torch.zeros(N, Hq, Wq, sg.kc)
+                            hi = min(c0 + sg.kc, sg.C)
                             if hi > c0:
                                 a[..., :hi - c0] = g[..., c0:hi]
-                            wt = W[phase, t * geom.BN:(t + 1) * geom.BN, kofs:kofs + 64]
+                            wt = W[phase, t * geom.BN:(t + 1) * geom.BN, kofs:kofs + sg.kc]
                             acc[..., t * geom.BN:(t + 1) * geom.BN] += a @ wt.t()
-                        kofs += 64
+                        kofs += sg.kc
         assert kofs == geom.Ktot
-        acc = acc + bias_rows
+        acc = acc + bias_rows[:rows]
         for t in range(geom.n_tiles_n):
             ch0 = t * geom.cout_per_tile
             nvalid = min(geom.cout_per_tile, geom.Cout - ch0)
@@ -166,4 +166,10 @@ CASES = [
     ConvCase('cin_small_cout24', [(24, 16, 16, False)], 20, k=1, pad=(0, 0)),
     ConvCase('big_k', [(512, 8, 8, True), (256, 16, 16, False), (256, 16, 16, False)], 256),
     ConvCase('wide_2048', [(1024, 8, 8, False)], 2048, k=1, pad=(0, 0), N=1),
+    ConvCase('kc16_3x3', [(16, 32, 32, False)], 16),
+    ConvCase('kc32_3x3', [(32, 24, 24, False)], 32),
+    ConvCase('kc16x3_1x1_48', [(48, 28, 28, False)], 288, k=1, pad=(0, 0), act='swish'),
+    ConvCase('kc_mixed_up', [(32, 16, 16, True), (16, 32, 32, False), (64, 32, 32, False)], 32),
+    ConvCase('kc32_s2', [(24, 32, 32, False)], 40, stride=2),
+    ConvCase('partial_chunk_168', [(32, 16, 16, False)], 168, k=1, pad=(0, 0)),
 ]
