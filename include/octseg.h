@@ -99,6 +99,8 @@ typedef struct octseg_conv_desc {
   int32_t out_H, out_W;/* output extent in pixels                                            */
   int32_t out_ldc;     /* NHWC: channel pitch; NCHW: number of channel planes                */
   int32_t out_c_off;   /* first output channel written                                       */
+  int32_t out_pack;    /* NCHW outputs of a pixel-packed problem: GEMM column c is plane c % out_ldc
+                          of pixel x*out_pack + c / out_ldc (rows are out_W*out_pack wide); 0/1 = off */
 } octseg_conv_desc;
 
 typedef struct octseg_conv_plan octseg_conv_plan;

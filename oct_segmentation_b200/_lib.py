@@ -44,7 +44,7 @@ class ConvDesc(C.Structure):
         ('weight', C.c_void_p), ('Ktot', C.c_int32), ('per_image_weights', C.c_int32),
         ('bias', C.c_void_p), ('act', C.c_int32), ('res_mode', C.c_int32), ('res', C.c_void_p),
         ('res_ldc', C.c_int32), ('out', C.c_void_p), ('out_mode', C.c_int32), ('out_H', C.c_int32),
-        ('out_W', C.c_int32), ('out_ldc', C.c_int32), ('out_c_off', C.c_int32),
+        ('out_W', C.c_int32), ('out_ldc', C.c_int32), ('out_c_off', C.c_int32), ('out_pack', C.c_int32),
     ]
 
 

@@ -55,7 +55,7 @@ struct __align__(64) ConvKParams {
   const __nv_bfloat16* res;
   int res_ldc;
   void* out;
-  int out_H, out_W, out_ldc, out_c_off;
+  int out_H, out_W, out_ldc, out_c_off, out_pack;
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -360,30 +360,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.BN);
-        uint32_t first = 1;
+        uint32_t accum = 0;  // 0 only for the very first MMA of the tile
         for (int s = 0; s < p.nseg; ++s) {
           const int kc = p.seg[s].kc;
-          const int subs = 64 / kc, steps = kc / 16;
-          const uint32_t a_sub = 128u * kc * 2u, b_sub = static_cast<uint32_t>(p.BN) * kc * 2u;
           int nsub = p.seg[s].kh * p.seg[s].kw * p.seg[s].cchunks;
-          while (nsub > 0) {
-            const int n = nsub < subs ? nsub : subs;
-            mbar_wait(bar_full + 8 * stage, phase);
-            tc_fence_after();
-            for (int j = 0; j < n; ++j) {
-              const uint64_t adesc = make_kmajor_desc(smemA + stage * kABytes + j * a_sub, kc);
-              const uint64_t bdesc = make_kmajor_desc(smemB + stage * b_bytes + j * b_sub, kc);
-              for (int t = 0; t < steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
-                tc_mma_bf16(d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, first ? 0u : 1u);
-                first = 0;
+          const uint64_t desc_hi = make_kmajor_desc(0, kc);
+          if (kc == 64) {
+            // hot path: one 64-channel sub-block per stage, four back-to-back MMAs
+            for (; nsub > 0; --nsub) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              const uint64_t adesc = desc_hi | ((smemA + stage * kABytes) >> 4);
+              const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes) >> 4);
+              tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+              tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              accum = 1;
+              tc_commit(bar_empty + 8 * stage);
+              if (++stage == nst) {
+                stage = 0;
+                phase ^= 1;
               }
             }
-            tc_commit(bar_empty + 8 * stage);
-            if (++stage == nst) {
-              stage = 0;
-              phase ^= 1;
+          } else {
+            const int subs = 64 / kc, steps = kc / 16;
+            const uint32_t a_sub = 128u * kc * 2u, b_sub = static_cast<uint32_t>(p.BN) * kc * 2u;
+            while (nsub > 0) {
+              const int n = nsub < subs ? nsub : subs;
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              for (int j = 0; j < n; ++j) {
+                const uint64_t adesc = desc_hi | ((smemA + stage * kABytes + j * a_sub) >> 4);
+                const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes + j * b_sub) >> 4);
+                for (int t = 0; t < steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
+                  tc_mma_bf16(d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
+                  accum = 1;
+                }
+              }
+              tc_commit(bar_empty + 8 * stage);
+              if (++stage == nst) {
+                stage = 0;
+                phase ^= 1;
+              }
+              nsub -= n;
             }
-            nsub -= n;
           }
         }
         tc_commit(bar_tfull + 8 * acc);
@@ -468,17 +489,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         } else {
           // NCHW planes: lanes of a warp are consecutive pixels -> coalesced per channel plane
-          const size_t plane = static_cast<size_t>(p.out_H) * p.out_W;
-          const size_t base = (static_cast<size_t>(tc.n) * p.out_ldc + p.out_c_off + ch0 + c0) * plane +
-                              static_cast<size_t>(oh) * p.out_W + ow;
+          // (pixel-packed problems: column c = plane c % out_ldc of pixel ow*out_pack + c / out_ldc)
+          const int wfull = p.out_W * p.out_pack;
+          const size_t plane = static_cast<size_t>(p.out_H) * wfull;
+          const size_t base = static_cast<size_t>(tc.n) * p.out_ldc * plane + static_cast<size_t>(oh) * wfull +
+                              static_cast<size_t>(ow) * p.out_pack;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             if (c0 + e < nvalid) {
               const float y = apply_act(__uint_as_float(v[e]) + __ldg(bias + c0 + e), p.act);
+              const int c = p.out_c_off + ch0 + c0 + e;
+              const size_t idx = base + static_cast<size_t>(c % p.out_ldc) * plane + c / p.out_ldc;
               if (p.out_mode == OCTSEG_OUT_F32_NCHW)
-                reinterpret_cast<float*>(p.out)[base + e * plane] = y;
+                reinterpret_cast<float*>(p.out)[idx] = y;
               else
-                reinterpret_cast<uint8_t*>(p.out)[base + e * plane] = y > 0.f ? 1 : 0;
+                reinterpret_cast<uint8_t*>(p.out)[idx] = y > 0.f ? 1 : 0;
             }
           }
         }
@@ -660,6 +685,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   kp.out_W = d->out_W;
   kp.out_ldc = d->out_ldc;
   kp.out_c_off = d->out_c_off;
+  kp.out_pack = d->out_pack > 1 ? d->out_pack : 1;
   kp.total_tiles = d->phases * d->N * kp.tiles_h * kp.tiles_w * d->n_tiles_n;
 
   kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC && d->cout_per_tile >= 64 &&

@@ -14,7 +14,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 
 from .. import _lib
-from .conv import Act, ConvPlan, pad8, pad_bias, plan_conv
+from .conv import Act, ConvPlan, pack_conv_weights, pad8, pad_bias, pixel_pack_factor, plan_conv
 
 
 def fold_bn(w: torch.Tensor, bn: Optional[torch.nn.BatchNorm2d], conv_bias: Optional[torch.Tensor] = None,
@@ -68,13 +68,46 @@ class Builder:
              act: str = 'none', res: Optional[Act] = None, res_mode: str = 'none',
              out_hw: Optional[Tuple[int, int]] = None, out_mode: str = 'bf16_nhwc',
              out_tensor: Optional[torch.Tensor] = None) -> Optional[Act]:
+        cout = w.shape[1] if transposed else w.shape[0]
+        bf16_out = out_mode == 'bf16_nhwc'
+        # narrow stride-1 convs: pack f adjacent pixels into one GEMM row (same memory, wider view)
+        f = 0
+        if (not transposed and groups == 1 and stride == 1 and not any(up for _, up in srcs) and out_hw is None
+                and pad[0] == (w.shape[2] - 1) // 2 and pad[1] == (w.shape[3] - 1) // 2):
+            f = pixel_pack_factor([a.Cp for a, _ in srcs], srcs[0][0].W, w.shape[3], pad8(cout) if bf16_out else cout)
+        if f:
+            a0 = srcs[0][0]
+            cout_store = pad8(cout) if bf16_out else cout
+            wp, bp = pack_conv_weights(w, b, [a.C for a, _ in srcs], [a.Cp for a, _ in srcs], f, pad[1], cout_store)
+            views = [a.t.view(a.N, a.H, a.W // f, f * a.Cp) for a, _ in srcs]
+            spec = [((v.shape[0], v.shape[1], v.shape[2], v.shape[3], v.shape[3]), False) for v in views]
+            geom, packed = plan_conv(spec, wp, stride=1, pad=(pad[0], 1 if w.shape[3] > 1 else 0), out_bf16=bf16_out)
+            geom.macs = a0.N * a0.H * a0.W * cout * w.shape[1] * w.shape[2] * w.shape[3]     # dense count of the real op
+            bias_rows = pad_bias(bp, geom, f * cout_store)
+            out_act, res_t = None, None
+            if bf16_out:
+                out_act = self.new_act(a0.H, a0.W, cout)
+                out_t = out_act.t.view(a0.N, a0.H, a0.W // f, f * cout_store)
+                if res is not None:
+                    res_t = res.t.view(a0.N, a0.H, a0.W // f, f * cout_store)
+                plan = ConvPlan(geom, packed, bias_rows, views, out_t, out_mode=out_mode, act=act, res=res_t,
+                                res_mode=res_mode, name=name)
+            else:
+                assert out_tensor is not None and tuple(out_tensor.shape) == (self.N, cout, a0.H, a0.W) and res is None
+                plan = ConvPlan(geom, packed, bias_rows, views, out_tensor, out_mode=out_mode, act=act, name=name,
+                                out_pack=f, out_ldc=cout)
+            self._keep.append(plan)
+            self.macs += geom.macs
+            self.tc_launches += 1
+            self._add(name, plan.run, tc_macs=geom.macs)
+            return out_act
+
         spec = [((a.N, a.H, a.W, a.C, a.Cp), up) for a, up in srcs]
         geom, packed = plan_conv(spec, w, out_hw=out_hw, stride=stride, pad=pad, groups=groups,
-                                 transposed=transposed, out_bf16=(out_mode == 'bf16_nhwc'))
-        cout = w.shape[1] if transposed else w.shape[0]
+                                 transposed=transposed, out_bf16=bf16_out)
         bias_rows = pad_bias(b, geom, cout, groups)
         out_act = None
-        if out_mode == 'bf16_nhwc':
+        if bf16_out:
             out_act = self.new_act(geom.out_H, geom.out_W, cout)
             out_t = out_act.t
         else:

@@ -236,6 +236,48 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
     return geom, packed
 
 
+def pixel_pack_factor(src_cps: Sequence[int], W: int, kw: int, cout_p: int) -> int:
+    """Pixels packed along W per GEMM row for narrow tensors (0 = do not pack).  A pixel of a
+    16-channel tensor is a 32-byte TMA row; packing f adjacent pixels into one f*C-channel
+    "super pixel" (same memory, different view) gives 128-byte rows and an MMA N of f*Cout."""
+    cmax = max(src_cps)
+    if cmax > 32:
+        return 0
+    f = 64 // cmax
+    while f > 1 and (W % f or kw > f + 1 or f * cout_p > 256):
+        f //= 2
+    return f if f > 1 else 0
+
+
+def pack_conv_weights(w: torch.Tensor, b: Optional[torch.Tensor], src_cs: Sequence[int], src_cps: Sequence[int],
+                      f: int, pad_l: int, cout_store: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Weights of the equivalent conv on the packed view.  Input channel (r, ci) of source s is pixel
+    r of the super pixel; output channel (q, co) is pixel q.  Original tap tx maps to super-pixel tap
+    tx' in {0,1,2} (offset tx'-1) with tx = (tx'-1)*f + r - q + pad_l.  cout_store = channels per
+    output pixel in memory (padded for bf16 NHWC, exact for NCHW heads)."""
+    w = w.detach().float().cpu()
+    cout, _, kh, kw = w.shape
+    kwp = 3 if kw > 1 else 1
+    cin_p = sum(f * cp for cp in src_cps)
+    wp = torch.zeros(f * cout_store, cin_p, kh, kwp)
+    base_in, base_w = 0, 0
+    for c, cp in zip(src_cs, src_cps):
+        for q in range(f):
+            for r in range(f):
+                for txp in range(kwp):
+                    tx = (txp - (1 if kwp == 3 else 0)) * f + r - q + pad_l
+                    if 0 <= tx < kw:
+                        wp[q * cout_store:q * cout_store + cout, base_in + r * cp:base_in + r * cp + c, :, txp] = \
+                            w[:, base_w:base_w + c, :, tx]
+        base_in += f * cp
+        base_w += c
+    bp = torch.zeros(f * cout_store)
+    if b is not None:
+        for q in range(f):
+            bp[q * cout_store:q * cout_store + cout] = b.detach().float().cpu()
+    return wp, bp
+
+
 def pad_bias(bias: Optional[torch.Tensor], geom: ConvGeom, cout: int, groups: int = 1) -> torch.Tensor:
     """fp32 bias laid out like the packed weight rows: [n_tiles_n * BN], zero padded."""
     out = torch.zeros(geom.n_tiles_n * geom.BN + 64, dtype=torch.float32)   # +64: the epilogue reads whole 64-wide chunks
@@ -256,7 +298,8 @@ class ConvPlan:
     def __init__(self, geom: ConvGeom, packed: torch.Tensor, bias: torch.Tensor, seg_tensors: Sequence[torch.Tensor],
                  out: torch.Tensor, out_mode: str = 'bf16_nhwc', act: str = 'none',
                  res: Optional[torch.Tensor] = None, res_mode: str = 'none', out_c_off: int = 0,
-                 per_image_weights: bool = False, name: str = ''):
+                 per_image_weights: bool = False, name: str = '', out_pack: int = 1,
+                 out_ldc: Optional[int] = None):
         lib = _lib.load()
         dev = out.device
         self.geom, self.name = geom, name
@@ -282,8 +325,9 @@ class ConvPlan:
         d.res_ldc = res.shape[-1] if res is not None else 0
         d.out, d.out_mode = out.data_ptr(), _lib.OUT[out_mode]
         d.out_H, d.out_W = geom.out_H, geom.out_W
-        d.out_ldc = out.shape[-1] if out_mode == 'bf16_nhwc' else out.shape[1]
+        d.out_ldc = out_ldc if out_ldc is not None else (out.shape[-1] if out_mode == 'bf16_nhwc' else out.shape[1])
         d.out_c_off = out_c_off
+        d.out_pack = out_pack
         handle = C.c_void_p()
         _lib.check(lib.octseg_conv_plan_create(C.byref(d), C.byref(handle)), f'conv_plan_create({name})')
         self._lib, self._h = lib, handle

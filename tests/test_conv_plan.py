@@ -49,3 +49,29 @@ def test_tile_and_bn_choice():
     for cout in (16, 64, 168, 392, 784, 1624, 2048, 24):
         n, bn = C.choose_bn(cout)
         assert bn % 16 == 0 and bn <= 256 and n * bn >= cout
+
+
+@pytest.mark.parametrize('cs,cout,k,W', [([16], 16, 3, 32), ([16], 1, 3, 32), ([32], 32, 3, 24), ([16, 32], 24, 3, 16),
+                                          ([16], 32, 1, 32), ([32], 2, 1, 16), ([24], 20, 3, 16), ([8], 16, 3, 32)])
+def test_pixel_packed_conv_is_the_same_conv(cs, cout, k, W):
+    """Packing f pixels per GEMM row (engine.conv.pack_conv_weights) is an exact re-indexing."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1)
+    cps = [C.pad8(c) for c in cs]
+    xs = [torch.randn(2, c, 12, W, generator=g) for c in cs]
+    w = torch.randn(cout, sum(cs), k, k, generator=g)
+    b = torch.randn(cout, generator=g)
+    want = F.conv2d(torch.cat(xs, 1), w, b, padding=k // 2)
+    cout_store = C.pad8(cout)
+    f = C.pixel_pack_factor(cps, W, k, cout_store)
+    assert f >= 2
+    wp, bp = C.pack_conv_weights(w, b, cs, cps, f, k // 2, cout_store)
+    packed_in = []
+    for x, c, cp in zip(xs, cs, cps):
+        t = torch.zeros(2, 12, W, cp)
+        t[..., :c] = x.permute(0, 2, 3, 1)
+        packed_in.append(t.view(2, 12, W // f, f * cp).permute(0, 3, 1, 2))
+    y = F.conv2d(torch.cat(packed_in, 1), wp, bp, padding=(k // 2, 1 if k > 1 else 0))       # [2, f*cout_store, 12, W/f]
+    y = y.permute(0, 2, 3, 1).reshape(2, 12, W, cout_store)
+    assert torch.allclose(y[..., :cout].permute(0, 3, 1, 2), want, atol=1e-4)
+    assert y[..., cout:].abs().max() == 0 if cout_store > cout else True
