@@ -321,20 +321,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t a_sub = 128u * sg.kc * 2u, b_sub = static_cast<uint32_t>(p.BN) * sg.kc * 2u;
           const uint32_t tx_sub = static_cast<uint32_t>(p.TH * p.TW + p.BN) * sg.kc * 2u;
           const CUtensorMap* mb = &p.tmB[kc_index(sg.kc)];
-          int in_stage = 0;
-          for (int ty = 0; ty < sg.kh; ++ty) {
-            for (int tx = 0; tx < sg.kw; ++tx) {
-              for (int cc = 0; cc < sg.cchunks; ++cc) {
-                if (in_stage == 0) mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                tma_load_4d(smemA + stage * kABytes + in_stage * a_sub, &p.tmA[s], bar_full + 8 * stage,
-                            cbase + cc * sg.kc, w0 + tx, h0 + ty, tc.n);
-                tma_load_3d(smemB + stage * b_bytes + in_stage * b_sub, mb, bar_full + 8 * stage, kofs, brow, bz);
-                kofs += sg.kc;
-                const bool last = (ty == sg.kh - 1) && (tx == sg.kw - 1) && (cc == sg.cchunks - 1);
-                if (++in_stage == subs || last) {
-                  // the arrive comes after the copies were issued: the phase cannot complete before it
-                  mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub * in_stage);
-                  in_stage = 0;
+          if (sg.kc == 64) {
+            // hot path: one 64-channel box pair per stage
+            const CUtensorMap* ma = &p.tmA[s];
+            for (int ty = 0; ty < sg.kh; ++ty) {
+              for (int tx = 0; tx < sg.kw; ++tx) {
+                for (int cc = 0; cc < sg.cchunks; ++cc) {
+                  mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                  mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub);
+                  tma_load_4d(smemA + stage * kABytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0 + tx, h0 + ty, tc.n);
+                  tma_load_3d(smemB + stage * b_bytes, mb, bar_full + 8 * stage, kofs, brow, bz);
+                  kofs += 64;
                   if (++stage == nst) {
                     stage = 0;
                     phase ^= 1;
@@ -342,6 +339,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
               }
             }
+            continue;
+          }
+          int nsub = sg.kh * sg.kw * sg.cchunks;
+          int ty = 0, tx = 0, cc = 0;
+          while (nsub > 0) {
+            const int n = nsub < subs ? nsub : subs;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub * n);
+            for (int j = 0; j < n; ++j) {
+              tma_load_4d(smemA + stage * kABytes + j * a_sub, &p.tmA[s], bar_full + 8 * stage, cbase + cc * sg.kc,
+                          w0 + tx, h0 + ty, tc.n);
+              tma_load_3d(smemB + stage * b_bytes + j * b_sub, mb, bar_full + 8 * stage, kofs, brow, bz);
+              kofs += sg.kc;
+              if (++cc == sg.cchunks) {
+                cc = 0;
+                if (++tx == sg.kw) {
+                  tx = 0;
+                  ++ty;
+                }
+              }
+            }
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1;
+            }
+            nsub -= n;
           }
         }
       }
