@@ -13,8 +13,9 @@
 // Nearest-x2 upsample + 3x3 conv and ConvTranspose(k4,s2,p1) are executed as four output-phase
 // sub-problems on the half-resolution grid (weights pre-combined per phase on the host).
 //
-// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2-5 = epilogue (one TMEM lane quarter each).  Accumulators are double-buffered in TMEM so
+// One persistent CTA per SM, 18 warps: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2-17 = epilogue (4 per TMEM lane quarter, 16 columns of each 64-column chunk each: the
+// epilogue is instruction-latency bound, so it needs several warps per scheduler).  Accumulators are double-buffered in TMEM so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -29,7 +30,11 @@ namespace octseg {
 
 constexpr int kMaxStages = 8;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter -> 4 warps per SM sub-partition
+constexpr int kEpiSplit = kEpiWarps / 4;      // column parts per 64-channel chunk
+constexpr int kEpiPart = 64 / kEpiSplit;      // columns per warp per chunk (16)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kOutBytes = 128 * 128;  // one 128-row x 64-channel bf16 staging buffer
 constexpr uint32_t kSpinLimit = 1u << 26;  // turns a pipeline deadlock into a trap, not a hang
@@ -137,6 +142,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major swizzled shared-memory matrix descriptor.  Rows are kc*2 bytes (32/64/128 = the swizzle
@@ -184,10 +198,13 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
-// bias + residual + activation of 8 consecutive channels of one pixel -> 8 packed bf16
-__device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8, const __nv_bfloat16* r8, int act,
+// bias + residual + activation of 8 consecutive channels of one pixel -> 8 packed bf16.
+// ReLU / identity are one fmaxf against `lo` (0 or -inf); swish is a separate instantiation, so
+// the per-element code has no branches.
+template <bool SWISH>
+__device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8, const __nv_bfloat16* r8, float lo,
                                            int res_mode) {
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias8));
   const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias8 + 4));
@@ -211,21 +228,23 @@ __device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8
       rr[2 * e + 1] = f.y;
     }
   }
+  const float pre = res_mode == OCTSEG_RES_BEFORE_ACT ? 1.f : 0.f;
+  const float post = res_mode == OCTSEG_RES_AFTER_ACT ? 1.f : 0.f;
   uint4 ov;
   __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    float y0 = x[2 * e], y1 = x[2 * e + 1];
-    if (res_mode == OCTSEG_RES_BEFORE_ACT) {
-      y0 += rr[2 * e];
-      y1 += rr[2 * e + 1];
+    float y0 = fmaf(pre, rr[2 * e], x[2 * e]), y1 = fmaf(pre, rr[2 * e + 1], x[2 * e + 1]);
+    if (SWISH) {
+      const float h0 = 0.5f * y0, h1 = 0.5f * y1;
+      y0 = fmaf(h0, fast_tanh(h0), h0);
+      y1 = fmaf(h1, fast_tanh(h1), h1);
+    } else {
+      y0 = fmaxf(y0, lo);
+      y1 = fmaxf(y1, lo);
     }
-    y0 = apply_act(y0, act);
-    y1 = apply_act(y1, act);
-    if (res_mode == OCTSEG_RES_AFTER_ACT) {
-      y0 += rr[2 * e];
-      y1 += rr[2 * e + 1];
-    }
+    y0 = fmaf(post, rr[2 * e], y0);
+    y1 = fmaf(post, rr[2 * e + 1], y1);
     o2[e] = __floats2bfloat162_rn(y0, y1);
   }
   return ov;
@@ -274,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128);
+      mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -437,10 +456,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int part = (warp - 2) >> 2;   // which kEpiPart-column slice of every 64-column chunk
     const int row = q * 32 + lane;
     const int epi_tid = static_cast<int>(threadIdx.x) - 64;
     const int th_l = row / p.TW, tw_l = row - th_l * p.TW;
+    const bool swish = p.act == OCTSEG_ACT_SWISH;
+    const float lo = p.act == OCTSEG_ACT_RELU ? 0.f : -INFINITY;
     int acc = 0;
     uint32_t acc_phase = 0, out_buf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -459,32 +481,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
 
-      // full 64-channel chunks: registers -> swizzled shared tile -> one TMA store per chunk
-      const int n_tma = p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0;
+      // 64-channel chunks: registers -> swizzled shared tile -> one TMA store per chunk.  A partial last
+      // chunk also goes this way when the tile ends at the tensor's channel extent (TMA clips it).
+      const int n_tma =
+          p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0;
       for (int ck = 0; ck < n_tma; ++ck) {
-        const int c0 = ck * 64;
+        const int cp = ck * 64 + part * kEpiPart;
         const uint32_t sbuf = smemOut + out_buf * kOutBytes;
         if (epi_tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer of 2 chunks ago is free
         epi_bar_sync();
+        uint32_t v[kEpiPart];
+        tmem_ld16(taddr + cp, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0 + 32 * h, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cc = c0 + 32 * h + 8 * g;
-            const uint4 ov = epi_pack8(v + 8 * g, bias + cc, (rrow && cc < nvalid) ? rrow + cc : nullptr, p.act, p.res_mode);
-            const uint32_t dst = sbuf + row * 128 + (((4 * h + g) ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z),
-                         "r"(ov.w)
-                         : "memory");
-          }
+        for (int g = 0; g < kEpiPart / 8; ++g) {
+          const int cc = cp + 8 * g;
+          const __nv_bfloat16* r8 = (rrow && cc < nvalid) ? rrow + cc : nullptr;
+          const uint4 ov = swish ? epi_pack8<true>(v + 8 * g, bias + cc, r8, lo, p.res_mode)
+                                 : epi_pack8<false>(v + 8 * g, bias + cc, r8, lo, p.res_mode);
+          const uint32_t dst = sbuf + row * 128 + (((part * (kEpiPart / 8) + g) ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z),
+                       "r"(ov.w)
+                       : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         epi_bar_sync();
         if (epi_tid == 0) {
-          const int cch = p.out_c_off + ch0 + c0;
+          const int cch = p.out_c_off + ch0 + ck * 64;
           if (p.phases == 4)
             tma_store_5d(&p.tmOut, sbuf, cch, tc.pw, tc.tw * p.TW, tc.ph, tc.n * p.Hq + tc.th * p.TH);
           else
@@ -495,20 +518,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
 
       // remaining channels (and every non-bf16 output): direct stores from registers
-      for (int c0 = n_tma * 64; c0 < nvalid; c0 += 32) {
-        uint32_t v[32];
+      for (int c0 = n_tma * 64; c0 < nvalid; c0 += 64) {
+        const int cp = c0 + part * kEpiPart;
+        if (cp >= nvalid) continue;  // warp-uniform
+        uint32_t v[kEpiPart];
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
-        tmem_ld32(taddr + c0, v);
+        tmem_ld16(taddr + cp, v);
         tmem_ld_wait();
         if (!valid) {
           // row outside the image / tile: nothing to store
         } else if (p.out_mode == OCTSEG_OUT_BF16_NHWC) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ldc + p.out_c_off + ch0 + c0;
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ldc + p.out_c_off + ch0 + cp;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (c0 + g * 8 < nvalid)
+          for (int g = 0; g < kEpiPart / 8; ++g) {
+            if (cp + g * 8 < nvalid) {
+              const __nv_bfloat16* r8 = rrow ? rrow + cp + 8 * g : nullptr;
               *reinterpret_cast<uint4*>(o + g * 8) =
-                  epi_pack8(v + 8 * g, bias + c0 + 8 * g, rrow ? rrow + c0 + 8 * g : nullptr, p.act, p.res_mode);
+                  swish ? epi_pack8<true>(v + 8 * g, bias + cp + 8 * g, r8, lo, p.res_mode)
+                        : epi_pack8<false>(v + 8 * g, bias + cp + 8 * g, r8, lo, p.res_mode);
+            }
           }
         } else {
           // NCHW planes: lanes of a warp are consecutive pixels -> coalesced per channel plane
@@ -518,10 +546,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const size_t base = static_cast<size_t>(tc.n) * p.out_ldc * plane + static_cast<size_t>(oh) * wfull +
                               static_cast<size_t>(ow) * p.out_pack;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (c0 + e < nvalid) {
-              const float y = apply_act(__uint_as_float(v[e]) + __ldg(bias + c0 + e), p.act);
-              const int c = p.out_c_off + ch0 + c0 + e;
+          for (int e = 0; e < kEpiPart; ++e) {
+            if (cp + e < nvalid) {
+              const float y = apply_act(__uint_as_float(v[e]) + __ldg(bias + cp + e), p.act);
+              const int c = p.out_c_off + ch0 + cp + e;
               const size_t idx = base + static_cast<size_t>(c % p.out_ldc) * plane + c / p.out_ldc;
               if (p.out_mode == OCTSEG_OUT_F32_NCHW)
                 reinterpret_cast<float*>(p.out)[idx] = y;
