@@ -198,7 +198,9 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ void group_bar_sync(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kEpiThreads / 2) : "memory");
+}
 
 // bias + residual + activation of 8 consecutive channels of one pixel -> 8 packed bf16.
 // ReLU / identity are one fmaxf against `lo` (0 or -inf); swish is a separate instantiation, so
@@ -457,14 +459,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware: warp id % 4)
-    const int part = (warp - 2) >> 2;   // which kEpiPart-column slice of every 64-column chunk
+    const int part = (warp - 2) >> 2;   // direct-store path: which kEpiPart-column slice of every 64-column block
+    const int group = (warp - 2) >> 3;  // TMA-store path: chunk-alternating group (8 warps each)
+    const int half = part & 1;          //                 32-column half of the group's chunk
+    const int gtid = (static_cast<int>(threadIdx.x) - 64) & 255;
     const int row = q * 32 + lane;
-    const int epi_tid = static_cast<int>(threadIdx.x) - 64;
     const int th_l = row / p.TW, tw_l = row - th_l * p.TW;
     const bool swish = p.act == OCTSEG_ACT_SWISH;
     const float lo = p.act == OCTSEG_ACT_RELU ? 0.f : -INFINITY;
     int acc = 0;
-    uint32_t acc_phase = 0, out_buf = 0;
+    uint32_t acc_phase = 0, chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int i = tc.th * p.TH + th_l, j = tc.tw * p.TW + tw_l;
@@ -483,30 +487,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
       // 64-channel chunks: registers -> swizzled shared tile -> one TMA store per chunk.  A partial last
       // chunk also goes this way when the tile ends at the tensor's channel extent (TMA clips it).
+      // The 16 warps form two independent groups (own staging buffer, own named barrier) that take
+      // alternate chunks, so one group's barrier / TMEM / store latency overlaps the other's math.
       const int n_tma =
           p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0;
       for (int ck = 0; ck < n_tma; ++ck) {
-        const int cp = ck * 64 + part * kEpiPart;
-        const uint32_t sbuf = smemOut + out_buf * kOutBytes;
-        if (epi_tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer of 2 chunks ago is free
-        epi_bar_sync();
-        uint32_t v[kEpiPart];
-        tmem_ld16(taddr + cp, v);
+        if (((chunk_ctr + ck) & 1) != static_cast<uint32_t>(group)) continue;  // warp-uniform
+        const int cp = ck * 64 + half * 32;
+        const uint32_t sbuf = smemOut + group * kOutBytes;
+        if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store left the buffer
+        group_bar_sync(group);
+        uint32_t v[32];
+        tmem_ld32(taddr + cp, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < kEpiPart / 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           const int cc = cp + 8 * g;
           const __nv_bfloat16* r8 = (rrow && cc < nvalid) ? rrow + cc : nullptr;
           const uint4 ov = swish ? epi_pack8<true>(v + 8 * g, bias + cc, r8, lo, p.res_mode)
                                  : epi_pack8<false>(v + 8 * g, bias + cc, r8, lo, p.res_mode);
-          const uint32_t dst = sbuf + row * 128 + (((part * (kEpiPart / 8) + g) ^ (row & 7)) << 4);
+          const uint32_t dst = sbuf + row * 128 + (((half * 4 + g) ^ (row & 7)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z),
                        "r"(ov.w)
                        : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        epi_bar_sync();
-        if (epi_tid == 0) {
+        group_bar_sync(group);
+        if (gtid == 0) {
           const int cch = p.out_c_off + ch0 + ck * 64;
           if (p.phases == 4)
             tma_store_5d(&p.tmOut, sbuf, cch, tc.pw, tc.tw * p.TW, tc.ph, tc.n * p.Hq + tc.th * p.TH);
@@ -514,8 +521,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_store_4d(&p.tmOut, sbuf, cch, tc.tw * p.TW, tc.th * p.TH, tc.n);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        out_buf ^= 1;
       }
+      chunk_ctr += n_tma;
 
       // remaining channels (and every non-bf16 output): direct stores from registers
       for (int c0 = n_tma * 64; c0 < nvalid; c0 += 64) {
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (epi_tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores landed before exit
+    if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores landed before exit
   }
 
   tc_fence_before();

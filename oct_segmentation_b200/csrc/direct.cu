@@ -153,136 +153,132 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 }
 
 // ------------------------------------------------------------------------------------ depthwise
-// HBM-bound.  A block owns a TR x TC tile of output pixels for 64 channels (8 channel groups of
-// 16 bytes).  The input tile + halo is staged ONCE in shared memory with cp.async (zero fill = the
-// conv padding), so vertical/horizontal filter reuse never goes back to L2; the fp32 filter bank of
-// the 64 channels sits in shared memory too.  Thread = (channel group, pixel lane); each thread
-// produces P consecutive output pixels per step with the whole filter row held in registers.
-// Squeeze-excite sums: registers -> warp shuffles -> shared atomics -> one global atomic per channel.
-template <int K, int S>
-struct DwCfg {
-  static constexpr int P = (S == 1 && K == 3) ? 4 : 2;  // output pixels per thread step (register budget)
-  static constexpr int TC = S == 1 ? 32 : 16; // tile width  (output pixels)
-  static constexpr int TR = S == 1 ? 8 : 4;   // tile height (output pixels)
-  static constexpr int IR = (TR - 1) * S + K, IC = (TC - 1) * S + K;
-  static constexpr int WIN = (P - 1) * S + K;
-  static constexpr int GROUPS = TR * (TC / P);
-  static constexpr size_t SMEM = static_cast<size_t>(IR) * IC * 128 + K * K * 64 * sizeof(float) + 64 * sizeof(float);
-};
+// HBM-bound.  Work item = 8 channels (16 B) x P consecutive output pixels of one row; items are
+// flattened (pixel-group, channel-group) with the channel group fastest, so a warp always reads
+// consecutive 16-byte chunks whatever C is.  A block owns a contiguous run of pixel groups of one
+// image and a chunk of <= 128 channel groups; squeeze-excite sums go through shared-memory
+// atomics and leave the block as one global atomic per channel.
+__host__ __device__ constexpr int dw_p(int K) { return K == 3 ? 4 : 2; }  // output pixels per item (register budget)
+constexpr int kDwCgChunk = 128;  // channel groups per block column
+constexpr int kDwPgPerBlock = 64;
+
+// All loads of one filter row (WIN input vectors + K weight vectors) are issued together before
+// any of them is consumed, so a warp exposes one memory latency per row instead of one per load.
+template <int K, int S, bool CHECK>
+__device__ __forceinline__ void dw_rows(float (&acc)[dw_p(K)][8], const uint4* __restrict__ in4,
+                                        const uint4* __restrict__ w4, int C8, int W, int H, int ix0, int iy0) {
+  constexpr int kDwP = dw_p(K);
+  constexpr int WIN = (kDwP - 1) * S + K;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = iy0 + ky;
+    if (CHECK && (iy < 0 || iy >= H)) continue;
+    const uint4* row = in4 + static_cast<size_t>(iy) * W * C8;
+    uint4 v[WIN], wv[K];
+#pragma unroll
+    for (int dx = 0; dx < WIN; ++dx) {
+      const int ix = ix0 + dx;
+      v[dx] = (!CHECK || (ix >= 0 && ix < W)) ? __ldg(row + static_cast<size_t>(ix) * C8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) wv[kx] = __ldg(w4 + static_cast<size_t>(ky * K + kx) * C8);
+    float wr[K][8];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) unpack8(wv[kx], wr[kx]);
+#pragma unroll
+    for (int dx = 0; dx < WIN; ++dx) {
+      float f[8];
+      unpack8(v[dx], f);
+#pragma unroll
+      for (int p = 0; p < kDwP; ++p) {
+        const int kx = dx - p * S;  // compile-time after unrolling
+        if (kx >= 0 && kx < K) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(f[e], wr[kx][e], acc[p][e]);
+        }
+      }
+    }
+  }
+}
 
 template <int K, int S>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __restrict__ in,
                                                      const __nv_bfloat16* __restrict__ weight,  // [K*K][C] bf16
                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                      int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo,
-                                                     int tiles_x, int act, float* __restrict__ pool_sum) {
-  using Cfg = DwCfg<K, S>;
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  uint4* tile = reinterpret_cast<uint4*>(dw_smem);                                      // [IR][IC][8]
-  float* wsm = reinterpret_cast<float*>(dw_smem + static_cast<size_t>(Cfg::IR) * Cfg::IC * 128);  // [K*K][64]
-  float* sums = wsm + K * K * 64;                                                       // [64]
+                                                     int act, float* __restrict__ pool_sum) {
+  __shared__ float sums[8][kDwCgChunk];  // [e][channel group]: conflict-free for consecutive groups
+  constexpr int kDwP = dw_p(K);
   const int C8 = C >> 3;
-  const int cg0 = blockIdx.x * 8;
+  const int cg0 = blockIdx.x * kDwCgChunk;
+  const int cgc = min(kDwCgChunk, C8 - cg0);
   const int n = blockIdx.z;
-  const int ty = blockIdx.y / tiles_x, tx = blockIdx.y - ty * tiles_x;
-  const int oy0 = ty * Cfg::TR, ox0 = tx * Cfg::TC;
-  const int iy0 = oy0 * S - pad_t, ix0 = ox0 * S - pad_l;
-  const int cgl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int wg = (Wo + kDwP - 1) / kDwP;  // pixel groups per output row
+  const int npg = Ho * wg;
+  const int pg0 = blockIdx.y * kDwPgPerBlock;
+  const int pgc = min(kDwPgPerBlock, npg - pg0);
+  if (pool_sum) {
+    for (int i = threadIdx.x; i < 8 * kDwCgChunk; i += 256) (&sums[0][0])[i] = 0.f;
+    __syncthreads();
+  }
+  // thread -> fixed channel group, strided over pixel groups: bias / SE sums stay in registers
+  const int lanes_pg = 256 / cgc;  // pixel groups processed per sweep
+  const int cgl = threadIdx.x % cgc;
+  const int pgl0 = threadIdx.x / cgc;
+  const bool active = pgl0 < lanes_pg;
   const int cg = cg0 + cgl;
-  const bool cvalid = cg < C8;
-
-  // ---- stage the input tile (16-byte cp.async, zero fill outside the image / channel range)
-  const uint4* in4 = reinterpret_cast<const uint4*>(in) + static_cast<size_t>(n) * H * W * C8;
-  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
-  for (int idx = threadIdx.x; idx < Cfg::IR * Cfg::IC * 8; idx += 256) {
-    const int pix = idx >> 3;
-    const int r = pix / Cfg::IC, c = pix - r * Cfg::IC;
-    const int iy = iy0 + r, ix = ix0 + c;
-    const bool ok = cvalid && iy >= 0 && iy < H && ix >= 0 && ix < W;
-    const uint4* src = ok ? in4 + (static_cast<size_t>(iy) * W + ix) * C8 + cg : in4;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + idx * 16), "l"(src), "r"(ok ? 16 : 0)
-                 : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = threadIdx.x; i < K * K * 64; i += 256) {
-    const int c = cg0 * 8 + (i & 63);
-    wsm[i] = c < C ? __bfloat162float(weight[static_cast<size_t>(i >> 6) * C + c]) : 0.f;
-  }
-  if (threadIdx.x < 64) sums[threadIdx.x] = 0.f;
+  const uint4* in4 = reinterpret_cast<const uint4*>(in) + static_cast<size_t>(n) * H * W * C8 + cg;
+  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * Ho * Wo * C8 + cg;
+  const uint4* w4 = reinterpret_cast<const uint4*>(weight) + cg;
+  constexpr int WIN = (kDwP - 1) * S + K;
   float bs[8], ps[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    bs[e] = cvalid ? __ldg(bias + cg * 8 + e) : 0.f;
+    bs[e] = active ? __ldg(bias + cg * 8 + e) : 0.f;
     ps[e] = 0.f;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-
-  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * Ho * Wo * C8 + cg;
-  for (int g = pl; g < Cfg::GROUPS; g += 32) {
-    const int pr = g / (Cfg::TC / Cfg::P);
-    const int pc = (g - pr * (Cfg::TC / Cfg::P)) * Cfg::P;
-    float acc[Cfg::P][8];
+  if (active) {
+    for (int pgl = pgl0; pgl < pgc; pgl += lanes_pg) {
+      const int pg = pg0 + pgl;
+      const int oy = pg / wg;
+      const int ox0 = (pg - oy * wg) * kDwP;
+      float acc[kDwP][8];
 #pragma unroll
-    for (int p = 0; p < Cfg::P; ++p)
+      for (int p = 0; p < kDwP; ++p)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[p][e] = bs[e];
-#pragma unroll(K == 3 ? 3 : 1)
-    for (int ky = 0; ky < K; ++ky) {
-      float wr[K][8];
+        for (int e = 0; e < 8; ++e) acc[p][e] = bs[e];
+      const int ix0 = ox0 * S - pad_l;
+      const int iy0 = oy * S - pad_t;
+      const bool interior = ix0 >= 0 && ix0 + WIN <= W && iy0 >= 0 && iy0 + K <= H;
+      if (interior)
+        dw_rows<K, S, false>(acc, in4, w4, C8, W, H, ix0, iy0);
+      else
+        dw_rows<K, S, true>(acc, in4, w4, C8, W, H, ix0, iy0);
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * K + kx) * 64 + cgl * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * K + kx) * 64 + cgl * 8 + 4);
-        wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w;
-        wr[kx][4] = w1.x; wr[kx][5] = w1.y; wr[kx][6] = w1.z; wr[kx][7] = w1.w;
-      }
-      const uint4* row = tile + (static_cast<size_t>(pr * S + ky) * Cfg::IC + pc * S) * 8 + cgl;
+      for (int p = 0; p < kDwP; ++p) {
+        if (ox0 + p < Wo) {
 #pragma unroll
-      for (int dx = 0; dx < Cfg::WIN; ++dx) {
-        float f[8];
-        unpack8(row[dx * 8], f);
+          for (int e = 0; e < 8; ++e) acc[p][e] = act_f(acc[p][e], act);
+          const uint4 o = pack8(acc[p]);
+          out4[(static_cast<size_t>(oy) * Wo + ox0 + p) * C8] = o;
+          if (pool_sum) {  // pool what the next layer actually reads (the bf16-rounded activation)
+            float r[8];
+            unpack8(o, r);
 #pragma unroll
-        for (int p = 0; p < Cfg::P; ++p) {
-          const int kx = dx - p * S;  // compile-time after unrolling
-          if (kx >= 0 && kx < K) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(f[e], wr[kx][e], acc[p][e]);
+            for (int e = 0; e < 8; ++e) ps[e] += r[e];
           }
         }
       }
     }
-    const int oy = oy0 + pr;
+    if (pool_sum) {
 #pragma unroll
-    for (int p = 0; p < Cfg::P; ++p) {
-      const int ox = ox0 + pc + p;
-      if (cvalid && oy < Ho && ox < Wo) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[p][e] = act_f(acc[p][e], act);
-        const uint4 o = pack8(acc[p]);
-        out4[(static_cast<size_t>(oy) * Wo + ox) * C8] = o;
-        if (pool_sum) {  // pool what the next layer actually reads (the bf16-rounded activation)
-          float r[8];
-          unpack8(o, r);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) ps[e] += r[e];
-        }
-      }
+      for (int e = 0; e < 8; ++e) atomicAdd(&sums[e][cgl], ps[e]);
     }
   }
   if (pool_sum) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = ps[e];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((threadIdx.x & 31) < 8) atomicAdd(&sums[cgl * 8 + e], v);
-    }
     __syncthreads();
-    if (threadIdx.x < 64) {
-      const int c = cg0 * 8 + threadIdx.x;
-      if (c < C) atomicAdd(pool_sum + static_cast<size_t>(n) * C + c, sums[threadIdx.x]);
-    }
+    for (int i = threadIdx.x; i < cgc * 8; i += 256)
+      atomicAdd(pool_sum + static_cast<size_t>(n) * C + cg0 * 8 + i, sums[i & 7][i >> 3]);
   }
 }
 
@@ -402,35 +398,26 @@ extern "C" int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t
   return check_launch("maxpool3x3s2_kernel");
 }
 
-template <int K, int S>
-static int launch_dw(const __nv_bfloat16* i, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* o, int N, int H,
-                     int W, int C, int pad_t, int pad_l, int Ho, int Wo, int act, float* pool_sum, cudaStream_t st) {
-  using Cfg = DwCfg<K, S>;
-  static bool attr_set = false;  // once per process; keep it out of graph capture
-  if (!attr_set) {
-    OCTSEG_CUDA(cudaFuncSetAttribute(dwconv_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(Cfg::SMEM)));
-    attr_set = true;
-  }
-  const int tiles_x = cdiv(Wo, Cfg::TC), tiles_y = cdiv(Ho, Cfg::TR);
-  dim3 grid(cdiv(C / 8, 8), tiles_x * tiles_y, N);
-  dwconv_kernel<K, S><<<grid, 256, Cfg::SMEM, st>>>(i, w, bias, o, H, W, C, pad_t, pad_l, Ho, Wo, tiles_x, act, pool_sum);
-  return check_launch("dwconv_kernel");
-}
-
 extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bias, void* out, int32_t N, int32_t H,
                              int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l,
                              int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, void* stream) {
   if (C % 8) return fail(OCTSEG_EINVAL, "dwconv: C must be a multiple of 8 (C=%d)", C);
+  const int C8 = C / 8;
+  const int wg = cdiv(Wo, dw_p(k));
+  dim3 grid(cdiv(C8, kDwCgChunk), cdiv(Ho * wg, kDwPgPerBlock), N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* i = static_cast<const __nv_bfloat16*>(in);
   const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(weight);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-  if (k == 3 && stride == 1) return launch_dw<3, 1>(i, w, bias, o, N, H, W, C, pad_t, pad_l, Ho, Wo, act, pool_sum, st);
-  if (k == 3 && stride == 2) return launch_dw<3, 2>(i, w, bias, o, N, H, W, C, pad_t, pad_l, Ho, Wo, act, pool_sum, st);
-  if (k == 5 && stride == 1) return launch_dw<5, 1>(i, w, bias, o, N, H, W, C, pad_t, pad_l, Ho, Wo, act, pool_sum, st);
-  if (k == 5 && stride == 2) return launch_dw<5, 2>(i, w, bias, o, N, H, W, C, pad_t, pad_l, Ho, Wo, act, pool_sum, st);
-  return fail(OCTSEG_EINVAL, "dwconv: unsupported kernel %d / stride %d", k, stride);
+#define OCTSEG_DW(KK, SS) \
+  dwconv_kernel<KK, SS><<<grid, 256, 0, st>>>(i, w, bias, o, H, W, C, pad_t, pad_l, Ho, Wo, act, pool_sum)
+  if (k == 3 && stride == 1) OCTSEG_DW(3, 1);
+  else if (k == 3 && stride == 2) OCTSEG_DW(3, 2);
+  else if (k == 5 && stride == 1) OCTSEG_DW(5, 1);
+  else if (k == 5 && stride == 2) OCTSEG_DW(5, 2);
+  else return fail(OCTSEG_EINVAL, "dwconv: unsupported kernel %d / stride %d", k, stride);
+#undef OCTSEG_DW
+  return check_launch("dwconv_kernel");
 }
 
 extern "C" int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1, const float* b1, float* hidden,
