@@ -71,6 +71,8 @@ typedef struct octseg_conv_seg {
   int32_t cchunks;    /* kc-channel chunks per tap                                           */
   int32_t kc;         /* chunk width 16 | 32 | 64 (32B / 64B / 128B swizzle); 64/kc consecutive
                          (tap, chunk) sub-blocks of a segment share one pipeline stage          */
+  int32_t wide;       /* 1 (needs kc=64, mul=1, TH=1): load one (TW+kw-1)-pixel box per tap row and
+                         run the kw taps as shifted views of it (kw x less activation traffic)  */
 } octseg_conv_seg;
 
 typedef struct octseg_conv_desc {

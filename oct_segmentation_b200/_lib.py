@@ -32,7 +32,7 @@ class ConvSeg(C.Structure):
         ('ptr', C.c_void_p), ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
         ('ldc', C.c_int32), ('kh', C.c_int32), ('kw', C.c_int32), ('mul', C.c_int32),
         ('off_h', C.c_int32 * 2), ('off_w', C.c_int32 * 2), ('c_per_tile', C.c_int32),
-        ('cchunks', C.c_int32), ('kc', C.c_int32),
+        ('cchunks', C.c_int32), ('kc', C.c_int32), ('wide', C.c_int32),
     ]
 
 

@@ -29,7 +29,7 @@
 namespace octseg {
 
 constexpr int kMaxStages = 8;
-constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kABytes = 136 * 128;  // 136 rows x 64 bf16: 128 MMA rows + up to 8 halo pixels of a wide box
 constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter -> 4 warps per SM sub-partition
 constexpr int kEpiSplit = kEpiWarps / 4;      // column parts per 64-channel chunk
 constexpr int kEpiPart = 64 / kEpiSplit;      // columns per warp per chunk (16)
@@ -44,6 +44,7 @@ struct SegK {
   int off_h[2], off_w[2];
   int c_per_tile, cchunks;
   int kc;  // chunk width (16/32/64 channels): swizzle 32B/64B/128B, 64/kc sub-blocks per stage
+  int wide;  // 1: one (TW + kw - 1)-pixel box per tap ROW; the kw taps are shifted views of it
 };
 
 struct __align__(64) ConvKParams {
@@ -56,6 +57,7 @@ struct __align__(64) ConvKParams {
   int per_image_weights, act, res_mode, out_mode;
   int k_iters, nstages, total_tiles;
   int use_tma_store;
+  int b_stage_bytes;  // bytes of one B stage (kw weight tiles for wide segments)
   const float* bias;
   const __nv_bfloat16* res;
   int res_ldc;
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nst = p.nstages;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.b_stage_bytes);
   const uint32_t smemA = smem0;
   const uint32_t smemB = smem0 + nst * kABytes;
   const uint32_t smemOut = smemB + nst * b_bytes;        // 2 x 16 KB epilogue staging (TMA store source)
@@ -342,6 +344,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t a_sub = 128u * sg.kc * 2u, b_sub = static_cast<uint32_t>(p.BN) * sg.kc * 2u;
           const uint32_t tx_sub = static_cast<uint32_t>(p.TH * p.TW + p.BN) * sg.kc * 2u;
           const CUtensorMap* mb = &p.tmB[kc_index(sg.kc)];
+          if (sg.wide) {
+            // one wide box per (tap row, chunk): the kw taps read it at pixel offsets 0..kw-1
+            const CUtensorMap* ma = &p.tmA[s];
+            const uint32_t tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
+            const uint32_t tx_bytes = static_cast<uint32_t>(p.TW + sg.kw - 1) * 128u + sg.kw * tile_bytes;
+            for (int ty = 0; ty < sg.kh; ++ty) {
+              for (int cc = 0; cc < sg.cchunks; ++cc) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
+                tma_load_4d(smemA + stage * kABytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0, h0 + ty, tc.n);
+                for (int tx = 0; tx < sg.kw; ++tx)
+                  tma_load_3d(smemB + stage * b_bytes + tx * tile_bytes, mb, bar_full + 8 * stage,
+                              kofs + ((ty * sg.kw + tx) * sg.cchunks + cc) * 64, brow, bz);
+                if (++stage == nst) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+            kofs += sg.kh * sg.kw * sg.cchunks * 64;
+            continue;
+          }
           if (sg.kc == 64) {
             // hot path: one 64-channel box pair per stage
             const CUtensorMap* ma = &p.tmA[s];
@@ -409,7 +433,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int kc = p.seg[s].kc;
           int nsub = p.seg[s].kh * p.seg[s].kw * p.seg[s].cchunks;
           const uint64_t desc_hi = make_kmajor_desc(0, kc);
-          if (kc == 64) {
+          if (p.seg[s].wide) {
+            // tap tx = the same A stage read from pixel row tx on (128 B further): the start address is
+            // no longer 1024-byte aligned, so the descriptor's base-offset field carries (addr >> 7) & 7
+            const int kw = p.seg[s].kw;
+            const uint32_t tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
+            for (int st = p.seg[s].kh * p.seg[s].cchunks; st > 0; --st) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              for (int tx = 0; tx < kw; ++tx) {
+                const uint64_t adesc = desc_hi | (static_cast<uint64_t>(tx) << 49) |
+                                       ((smemA + stage * kABytes + tx * 128u) >> 4);
+                const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes + tx * tile_bytes) >> 4);
+                tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                accum = 1;
+              }
+              tc_commit(bar_empty + 8 * stage);
+              if (++stage == nst) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          } else if (kc == 64) {
             // hot path: one 64-channel sub-block per stage, four back-to-back MMAs
             for (; nsub > 0; --nsub) {
               mbar_wait(bar_full + 8 * stage, phase);
@@ -650,7 +698,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   std::memset(pl, 0, sizeof(*pl));
   ConvKParams& kp = pl->kp;
 
-  int k_iters = 0, k_total = 0;
+  int k_iters = 0, k_total = 0, b_tiles = 1;
   bool kc_used[3] = {false, false, false};
   for (int s = 0; s < d->nseg; ++s) {
     const octseg_conv_seg& sg = d->seg[s];
@@ -668,7 +716,13 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
                               static_cast<uint64_t>(sg.N)};
     const uint64_t strides[3] = {static_cast<uint64_t>(sg.ldc) * 2, static_cast<uint64_t>(sg.W) * sg.ldc * 2,
                                  static_cast<uint64_t>(sg.H) * sg.W * sg.ldc * 2};
-    const uint32_t box[4] = {static_cast<uint32_t>(sg.kc), static_cast<uint32_t>(d->TW * sg.mul),
+    if (sg.wide && (sg.kc != 64 || sg.mul != 1 || d->TH != 1 || sg.kw < 2 || d->TW + sg.kw - 1 > 136 ||
+                    sg.c_per_tile != 0 && sg.cchunks != 1)) {
+      delete pl;
+      return fail(OCTSEG_EINVAL, "segment %d: wide boxes need kc=64, mul=1, TH=1, kw>=2 and TW+kw-1<=136", s);
+    }
+    const uint32_t box[4] = {static_cast<uint32_t>(sg.kc),
+                             static_cast<uint32_t>(sg.wide ? d->TW + sg.kw - 1 : d->TW * sg.mul),
                              static_cast<uint32_t>(d->TH * sg.mul), 1u};
     const uint32_t estr[4] = {1u, static_cast<uint32_t>(sg.mul), static_cast<uint32_t>(sg.mul), 1u};
     int rc = encode_map(&kp.tmA[s], sg.ptr, 4, dims, strides, box, estr, "A", sg.kc);
@@ -688,8 +742,10 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     k.c_per_tile = sg.c_per_tile;
     k.cchunks = sg.cchunks;
     k.kc = sg.kc;
+    k.wide = sg.wide ? 1 : 0;
+    if (sg.wide && sg.kw > b_tiles) b_tiles = sg.kw;
     const int nsub = sg.kh * sg.kw * sg.cchunks, subs = 64 / sg.kc;
-    k_iters += (nsub + subs - 1) / subs;
+    k_iters += sg.wide ? sg.kh * sg.cchunks : (nsub + subs - 1) / subs;
     k_total += nsub * sg.kc;
     kc_used[sg.kc == 64 ? 2 : (sg.kc == 32 ? 1 : 0)] = true;
   }
@@ -775,7 +831,8 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     }
   }
 
-  const int stage_bytes = kABytes + d->BN * 128;
+  kp.b_stage_bytes = b_tiles * d->BN * 128;
+  const int stage_bytes = kABytes + kp.b_stage_bytes;
   const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes;
   int nst = budget / stage_bytes;
   if (nst > kMaxStages) nst = kMaxStages;

@@ -20,6 +20,7 @@ import torch
 from .. import _lib
 
 KC = 64  # K elements per pipeline stage (one 128-byte swizzle atom of bf16)
+WIDE_BOXES = True  # allow shifted-view tap reuse (SegSpec.wide)
 
 
 def choose_kc(c_eff: int) -> int:
@@ -71,6 +72,7 @@ class SegSpec:
     c_per_tile: int
     cchunks: int
     kc: int = 64
+    wide: int = 0
 
 
 @dataclass
@@ -231,6 +233,12 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
         c_lo += sC
     packed = torch.stack([torch.cat(b, dim=1) for b in blocks]).to(packed_dtype).contiguous()
     Ktot = packed.shape[2]
+    if TH == 1 and WIDE_BOXES:
+        # activation-traffic saver for L2-bound shapes: the B stage then holds kw weight tiles
+        for sg in segs:
+            if (sg.kc == 64 and sg.mul == 1 and sg.kw >= 2 and TW + sg.kw - 1 <= 136 and sg.kw * BN * 128 <= 48 * 1024
+                    and (sg.c_per_tile == 0 or sg.cchunks == 1)):
+                sg.wide = 1
     geom = ConvGeom(segs, phases, N, Hq, Wq, TH, TW, BN, n_tiles_n, cout_per_tile, cout_w, Ktot, out_H, out_W,
                     macs)
     return geom, packed
@@ -315,7 +323,7 @@ class ConvPlan:
             s.kh, s.kw, s.mul = sg.kh, sg.kw, sg.mul
             s.off_h[0], s.off_h[1] = sg.off_h
             s.off_w[0], s.off_w[1] = sg.off_w
-            s.c_per_tile, s.cchunks, s.kc = sg.c_per_tile, sg.cchunks, sg.kc
+            s.c_per_tile, s.cchunks, s.kc, s.wide = sg.c_per_tile, sg.cchunks, sg.kc, sg.wide
         d.phases, d.N, d.Hq, d.Wq, d.TH, d.TW = geom.phases, geom.N, geom.Hq, geom.Wq, geom.TH, geom.TW
         d.BN, d.n_tiles_n, d.cout_per_tile, d.Cout = geom.BN, geom.n_tiles_n, geom.cout_per_tile, geom.Cout
         d.weight, d.Ktot, d.per_image_weights = self.weight.data_ptr(), geom.Ktot, int(per_image_weights)

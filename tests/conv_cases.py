@@ -172,4 +172,8 @@ CASES = [
     ConvCase('kc_mixed_up', [(32, 16, 16, True), (16, 32, 32, False), (64, 32, 32, False)], 32),
     ConvCase('kc32_s2', [(24, 32, 32, False)], 40, stride=2),
     ConvCase('partial_chunk_168', [(32, 16, 16, False)], 168, k=1, pad=(0, 0)),
+    ConvCase('wide_3x3_64', [(64, 6, 128, False)], 64),
+    ConvCase('wide_3x3_128_w160', [(128, 5, 160, False)], 128),
+    ConvCase('wide_up2x2', [(64, 4, 128, True), (64, 8, 256, False)], 64),
+    ConvCase('wide_grouped', [(128, 6, 128, False)], 128, groups=2),
 ]
