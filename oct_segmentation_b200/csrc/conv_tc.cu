@@ -434,16 +434,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           int nsub = p.seg[s].kh * p.seg[s].kw * p.seg[s].cchunks;
           const uint64_t desc_hi = make_kmajor_desc(0, kc);
           if (p.seg[s].wide) {
-            // tap tx = the same A stage read from pixel row tx on (128 B further): the start address is
-            // no longer 1024-byte aligned, so the descriptor's base-offset field carries (addr >> 7) & 7
+            // tap tx = the same A stage read from pixel row tx on (128 B further).  The 128B swizzle is a
+            // function of the absolute shared-memory address (measured: base-offset field must stay 0),
+            // so a start address that is only 128-byte aligned still decodes what TMA wrote.
             const int kw = p.seg[s].kw;
             const uint32_t tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
             for (int st = p.seg[s].kh * p.seg[s].cchunks; st > 0; --st) {
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
               for (int tx = 0; tx < kw; ++tx) {
-                const uint64_t adesc = desc_hi | (static_cast<uint64_t>(tx) << 49) |
-                                       ((smemA + stage * kABytes + tx * 128u) >> 4);
+                const uint64_t adesc = desc_hi | ((smemA + stage * kABytes + tx * 128u) >> 4);
                 const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes + tx * tile_bytes) >> 4);
                 tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
                 tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
