@@ -103,6 +103,9 @@ typedef struct octseg_conv_desc {
   int32_t out_c_off;   /* first output channel written                                       */
   int32_t out_pack;    /* NCHW outputs of a pixel-packed problem: GEMM column c is plane c % out_ldc
                           of pixel x*out_pack + c / out_ldc (rows are out_W*out_pack wide); 0/1 = off */
+  int32_t d2s;         /* depth-to-space bf16 output: > 0 = channels per output pixel; GEMM column c is
+                          channel c % d2s of pixel (2y + (c/d2s)/2, 2x + (c/d2s)%2) of a tensor twice as
+                          large as the tile grid (fused upsample / ConvTranspose in one pass)        */
 } octseg_conv_desc;
 
 typedef struct octseg_conv_plan octseg_conv_plan;

@@ -29,7 +29,8 @@
 namespace octseg {
 
 constexpr int kMaxStages = 8;
-constexpr int kABytes = 136 * 128;  // 136 rows x 64 bf16: 128 MMA rows + up to 8 halo pixels of a wide box
+constexpr int kABytes = 128 * 128;      // A stage: 128 rows x 64 bf16 ...
+constexpr int kABytesWide = 136 * 128;  // ... or 136 rows when a segment loads wide boxes (8 halo pixels)
 constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter -> 4 warps per SM sub-partition
 constexpr int kEpiSplit = kEpiWarps / 4;      // column parts per 64-channel chunk
 constexpr int kEpiPart = 64 / kEpiSplit;      // columns per warp per chunk (16)
@@ -58,11 +59,12 @@ struct __align__(64) ConvKParams {
   int k_iters, nstages, total_tiles;
   int use_tma_store;
   int b_stage_bytes;  // bytes of one B stage (kw weight tiles for wide segments)
+  int a_stage_bytes;  // kABytes or kABytesWide
   const float* bias;
   const __nv_bfloat16* res;
   int res_ldc;
   void* out;
-  int out_H, out_W, out_ldc, out_c_off, out_pack;
+  int out_H, out_W, out_ldc, out_c_off, out_pack, d2s;
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -280,7 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int nst = p.nstages;
   const uint32_t b_bytes = static_cast<uint32_t>(p.b_stage_bytes);
   const uint32_t smemA = smem0;
-  const uint32_t smemB = smem0 + nst * kABytes;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.a_stage_bytes);
+  const uint32_t smemB = smem0 + nst * a_bytes;
   const uint32_t smemOut = smemB + nst * b_bytes;        // 2 x 16 KB epilogue staging (TMA store source)
   const uint32_t bars = smemOut + 2 * kOutBytes;         // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (p.TH * p.TW < 128) {
     // rows the TMA box never writes must still hold finite values for the MMA
     uint4* z = reinterpret_cast<uint4*>(smem_gen);
-    const int n16 = nst * kABytes / 16;
+    const int n16 = nst * p.a_stage_bytes / 16;
     for (int i = threadIdx.x; i < n16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               for (int cc = 0; cc < sg.cchunks; ++cc) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
-                tma_load_4d(smemA + stage * kABytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0, h0 + ty, tc.n);
+                tma_load_4d(smemA + stage * a_bytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0, h0 + ty, tc.n);
                 for (int tx = 0; tx < sg.kw; ++tx)
                   tma_load_3d(smemB + stage * b_bytes + tx * tile_bytes, mb, bar_full + 8 * stage,
                               kofs + ((ty * sg.kw + tx) * sg.cchunks + cc) * 64, brow, bz);
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int cc = 0; cc < sg.cchunks; ++cc) {
                   mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                   mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub);
-                  tma_load_4d(smemA + stage * kABytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0 + tx, h0 + ty, tc.n);
+                  tma_load_4d(smemA + stage * a_bytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0 + tx, h0 + ty, tc.n);
                   tma_load_3d(smemB + stage * b_bytes, mb, bar_full + 8 * stage, kofs, brow, bz);
                   kofs += 64;
                   if (++stage == nst) {
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub * n);
             for (int j = 0; j < n; ++j) {
-              tma_load_4d(smemA + stage * kABytes + j * a_sub, &p.tmA[s], bar_full + 8 * stage, cbase + cc * sg.kc,
+              tma_load_4d(smemA + stage * a_bytes + j * a_sub, &p.tmA[s], bar_full + 8 * stage, cbase + cc * sg.kc,
                           w0 + tx, h0 + ty, tc.n);
               tma_load_3d(smemB + stage * b_bytes + j * b_sub, mb, bar_full + 8 * stage, kofs, brow, bz);
               kofs += sg.kc;
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
               for (int tx = 0; tx < kw; ++tx) {
-                const uint64_t adesc = desc_hi | ((smemA + stage * kABytes + tx * 128u) >> 4);
+                const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes + tx * 128u) >> 4);
                 const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes + tx * tile_bytes) >> 4);
                 tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
                 tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (; nsub > 0; --nsub) {
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
-              const uint64_t adesc = desc_hi | ((smemA + stage * kABytes) >> 4);
+              const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes) >> 4);
               const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes) >> 4);
               tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
               tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
               for (int j = 0; j < n; ++j) {
-                const uint64_t adesc = desc_hi | ((smemA + stage * kABytes + j * a_sub) >> 4);
+                const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes + j * a_sub) >> 4);
                 const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes + j * b_sub) >> 4);
                 for (int t = 0; t < steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
                   tc_mma_bf16(d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
@@ -588,7 +591,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int g = 0; g < kEpiPart / 8; ++g) {
             if (cp + g * 8 < nvalid) {
               const __nv_bfloat16* r8 = rrow ? rrow + cp + 8 * g : nullptr;
-              *reinterpret_cast<uint4*>(o + g * 8) =
+              __nv_bfloat16* og = o + g * 8;
+              if (p.d2s) {  // depth-to-space: column -> (2x2 sub-pixel, channel) of a tensor twice the tile grid
+                const int col = ch0 + cp + g * 8, sub = col / p.d2s, co = col - sub * p.d2s;
+                const size_t opix = (static_cast<size_t>(tc.n) * 2 * p.out_H + 2 * oh + (sub >> 1)) * (2 * p.out_W) +
+                                    2 * ow + (sub & 1);
+                og = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_ldc + p.out_c_off + co;
+              }
+              *reinterpret_cast<uint4*>(og) =
                   swish ? epi_pack8<true>(v + 8 * g, bias + cp + 8 * g, r8, lo, p.res_mode)
                         : epi_pack8<false>(v + 8 * g, bias + cp + 8 * g, r8, lo, p.res_mode);
             }
@@ -699,6 +709,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   ConvKParams& kp = pl->kp;
 
   int k_iters = 0, k_total = 0, b_tiles = 1;
+  bool any_wide = false;
   bool kc_used[3] = {false, false, false};
   for (int s = 0; s < d->nseg; ++s) {
     const octseg_conv_seg& sg = d->seg[s];
@@ -744,6 +755,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     k.kc = sg.kc;
     k.wide = sg.wide ? 1 : 0;
     if (sg.wide && sg.kw > b_tiles) b_tiles = sg.kw;
+    if (sg.wide) any_wide = true;
     const int nsub = sg.kh * sg.kw * sg.cchunks, subs = 64 / sg.kc;
     k_iters += sg.wide ? sg.kh * sg.cchunks : (nsub + subs - 1) / subs;
     k_total += nsub * sg.kc;
@@ -800,9 +812,14 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   kp.out_ldc = d->out_ldc;
   kp.out_c_off = d->out_c_off;
   kp.out_pack = d->out_pack > 1 ? d->out_pack : 1;
+  kp.d2s = d->d2s;
+  if (d->d2s && (d->d2s % 8 || d->phases != 1 || d->res || d->out_mode != OCTSEG_OUT_BF16_NHWC)) {
+    delete pl;
+    return fail(OCTSEG_EINVAL, "d2s output needs bf16 NHWC, one phase, no residual and d2s %% 8 == 0");
+  }
   kp.total_tiles = d->phases * d->N * kp.tiles_h * kp.tiles_w * d->n_tiles_n;
 
-  kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC && d->cout_per_tile >= 64 &&
+  kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC && d->cout_per_tile >= 64 && d->d2s == 0 &&
                       (d->phases == 1 || (d->Hq % d->TH == 0 && d->out_H == 2 * d->Hq && d->out_W == 2 * d->Wq)))
                          ? 1
                          : 0;
@@ -832,7 +849,8 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   }
 
   kp.b_stage_bytes = b_tiles * d->BN * 128;
-  const int stage_bytes = kABytes + kp.b_stage_bytes;
+  kp.a_stage_bytes = any_wide ? kABytesWide : kABytes;
+  const int stage_bytes = kp.a_stage_bytes + kp.b_stage_bytes;
   const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes;
   int nst = budget / stage_bytes;
   if (nst > kMaxStages) nst = kMaxStages;

@@ -14,7 +14,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 
 from .. import _lib
-from .conv import Act, ConvPlan, pack_conv_weights, pad8, pad_bias, pixel_pack_factor, plan_conv
+from .conv import Act, ConvPlan, d2s_weights, pack_conv_weights, pad8, pad_bias, pixel_pack_factor, plan_conv
 
 
 def fold_bn(w: torch.Tensor, bn: Optional[torch.nn.BatchNorm2d], conv_bias: Optional[torch.Tensor] = None,
@@ -96,6 +96,25 @@ class Builder:
                 assert out_tensor is not None and tuple(out_tensor.shape) == (self.N, cout, a0.H, a0.W) and res is None
                 plan = ConvPlan(geom, packed, bias_rows, views, out_tensor, out_mode=out_mode, act=act, name=name,
                                 out_pack=f, out_ldc=cout)
+            self._keep.append(plan)
+            self.macs += geom.macs
+            self.tc_launches += 1
+            self._add(name, plan.run, tc_macs=geom.macs)
+            return out_act
+
+        # single-source upsample+conv / ConvTranspose with few output channels: one depth-to-space conv
+        # on the half-resolution grid (N = 4*Cout) instead of four N = Cout phase problems
+        if (bf16_out and len(srcs) == 1 and (transposed or srcs[0][1]) and res is None and 4 * pad8(cout) <= 256
+                and groups == 1):
+            a0 = srcs[0][0]
+            cs = pad8(cout)
+            wp, bp = d2s_weights(w, transposed, cs)
+            geom, packed = plan_conv([((a0.N, a0.H, a0.W, a0.C, a0.Cp), False)], wp, pad=(1, 1))
+            cin = w.shape[0] if transposed else w.shape[1]
+            geom.macs = a0.N * a0.H * a0.W * cin * cout * (16 if transposed else 36)   # dense count of the real op
+            out_act = self.new_act(2 * a0.H, 2 * a0.W, cout)
+            plan = ConvPlan(geom, packed, pad_bias(bp, geom, 4 * cs), [a0.t], out_act.t, act=act, name=name,
+                            out_ldc=out_act.Cp, d2s=cs)
             self._keep.append(plan)
             self.macs += geom.macs
             self.tc_launches += 1

@@ -236,7 +236,7 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
     if TH == 1 and WIDE_BOXES:
         # activation-traffic saver for L2-bound shapes: the B stage then holds kw weight tiles
         for sg in segs:
-            if (sg.kc == 64 and sg.mul == 1 and sg.kw >= 2 and TW + sg.kw - 1 <= 136 and sg.kw * BN * 128 <= 48 * 1024
+            if (sg.kc == 64 and sg.mul == 1 and sg.kw >= 2 and TW + sg.kw - 1 <= 136 and BN <= 128
                     and (sg.c_per_tile == 0 or sg.cchunks == 1)):
                 sg.wide = 1
     geom = ConvGeom(segs, phases, N, Hq, Wq, TH, TW, BN, n_tiles_n, cout_per_tile, cout_w, Ktot, out_H, out_W,
@@ -286,6 +286,33 @@ def pack_conv_weights(w: torch.Tensor, b: Optional[torch.Tensor], src_cs: Sequen
     return wp, bp
 
 
+def d2s_weights(w: torch.Tensor, b: Optional[torch.Tensor], transposed: bool, cout_store: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Depth-to-space form of `nearest-x2 upsample + 3x3 conv` (w: [Cout, Cin, 3, 3]) or of
+    ConvTranspose2d(k4,s2,p1) (w: [Cin, Cout, 4, 4]) with a single source: ONE 3x3 conv (pad 1) on the
+    half-resolution tensor whose 4*cout_store output channels, ordered (ph, pw, co), are the 2x2
+    output block of each low-res pixel.  Phase (ph, pw) only uses taps dy in {ph-1, ph}, dx in
+    {pw-1, pw}; the other taps of its rows are zero."""
+    w = w.detach().float().cpu()
+    cout = w.shape[1] if transposed else w.shape[0]
+    cin = w.shape[0] if transposed else w.shape[1]
+    wp = torch.zeros(4 * cout_store, cin, 3, 3)
+    for ph in range(2):
+        for pw in range(2):
+            q = ph * 2 + pw
+            for a in range(2):
+                for bb in range(2):
+                    if transposed:
+                        wt = w[:, :, 3 - ph - 2 * a, 3 - pw - 2 * bb].t()
+                    else:
+                        wt = w[:, :, _phase_tap_groups(ph, a)][:, :, :, _phase_tap_groups(pw, bb)].sum(dim=(2, 3))
+                    wp[q * cout_store:q * cout_store + cout, :, ph + a, pw + bb] = wt
+    bp = torch.zeros(4 * cout_store)
+    if b is not None:
+        for q in range(4):
+            bp[q * cout_store:q * cout_store + cout] = b.detach().float().cpu()
+    return wp, bp
+
+
 def pad_bias(bias: Optional[torch.Tensor], geom: ConvGeom, cout: int, groups: int = 1) -> torch.Tensor:
     """fp32 bias laid out like the packed weight rows: [n_tiles_n * BN], zero padded."""
     out = torch.zeros(geom.n_tiles_n * geom.BN + 64, dtype=torch.float32)   # +64: the epilogue reads whole 64-wide chunks
@@ -307,7 +334,7 @@ class ConvPlan:
                  out: torch.Tensor, out_mode: str = 'bf16_nhwc', act: str = 'none',
                  res: Optional[torch.Tensor] = None, res_mode: str = 'none', out_c_off: int = 0,
                  per_image_weights: bool = False, name: str = '', out_pack: int = 1,
-                 out_ldc: Optional[int] = None):
+                 out_ldc: Optional[int] = None, d2s: int = 0):
         lib = _lib.load()
         dev = out.device
         self.geom, self.name = geom, name
@@ -336,6 +363,7 @@ class ConvPlan:
         d.out_ldc = out_ldc if out_ldc is not None else (out.shape[-1] if out_mode == 'bf16_nhwc' else out.shape[1])
         d.out_c_off = out_c_off
         d.out_pack = out_pack
+        d.d2s = d2s
         handle = C.c_void_p()
         _lib.check(lib.octseg_conv_plan_create(C.byref(d), C.byref(handle)), f'conv_plan_create({name})')
         self._lib, self._h = lib, handle

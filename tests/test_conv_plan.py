@@ -75,3 +75,26 @@ def test_pixel_packed_conv_is_the_same_conv(cs, cout, k, W):
     y = y.permute(0, 2, 3, 1).reshape(2, 12, W, cout_store)
     assert torch.allclose(y[..., :cout].permute(0, 3, 1, 2), want, atol=1e-4)
     assert y[..., cout:].abs().max() == 0 if cout_store > cout else True
+
+
+@pytest.mark.parametrize('transposed,cin,cout', [(False, 32, 16), (True, 16, 16), (True, 20, 12), (False, 24, 40)])
+def test_depth_to_space_form_is_the_same_op(transposed, cin, cout):
+    """engine.conv.d2s_weights: upsample+3x3 conv / ConvTranspose(k4,s2,p1) == one 3x3 conv on the
+    low-res grid with (ph, pw, co)-ordered channels followed by a pixel shuffle."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, cin, 6, 10, generator=g)
+    b = torch.randn(cout, generator=g)
+    if transposed:
+        w = torch.randn(cin, cout, 4, 4, generator=g)
+        want = F.conv_transpose2d(x, w, b, stride=2, padding=1)
+    else:
+        w = torch.randn(cout, cin, 3, 3, generator=g)
+        want = F.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), w, b, padding=1)
+    cs = C.pad8(cout)
+    wp, bp = C.d2s_weights(w, b, transposed, cs)
+    y = F.conv2d(x, wp, bp, padding=1)                                  # [2, 4*cs, 6, 10]
+    y = y.view(2, 2, 2, cs, 6, 10).permute(0, 3, 4, 1, 5, 2).reshape(2, cs, 12, 20)
+    assert torch.allclose(y[:, :cout], want, atol=1e-4)
+    if cs > cout:
+        assert y[:, cout:].abs().max() == 0
