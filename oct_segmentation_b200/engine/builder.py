@@ -108,7 +108,7 @@ class Builder:
                 and groups == 1):
             a0 = srcs[0][0]
             cs = pad8(cout)
-            wp, bp = d2s_weights(w, transposed, cs)
+            wp, bp = d2s_weights(w, b, transposed, cs)
             geom, packed = plan_conv([((a0.N, a0.H, a0.W, a0.C, a0.Cp), False)], wp, pad=(1, 1))
             cin = w.shape[0] if transposed else w.shape[1]
             geom.macs = a0.N * a0.H * a0.W * cin * cout * (16 if transposed else 36)   # dense count of the real op
