@@ -80,16 +80,40 @@ class EnsemblePipeline:
         return self.mask, self.label, self.counts, radii
 
     # ------------------------------------------------------------------ host-to-host step
-    def run_host(self, frames: np.ndarray):
+    def _host_buffers(self):
+        if getattr(self, '_pinned', None) is None:
+            Hs, Ws = self.src_hw
+            self._pinned = {
+                'frames': torch.empty(self.batch, Hs, Ws, 3, dtype=torch.uint8).pin_memory(),
+                'mask': torch.empty(self.batch, self.Ho, self.Wo, 4, dtype=torch.uint8).pin_memory(),
+                'label': torch.empty(self.batch, self.Ho, self.Wo, dtype=torch.uint8).pin_memory(),
+                'counts': torch.empty(self.batch, 4, dtype=torch.int32).pin_memory(),
+                'radii': torch.empty(self.batch, 4, 360, dtype=torch.int32).pin_memory(),
+            }
+        return self._pinned
+
+    def run_host(self, frames: np.ndarray, copy: bool = True):
         """frames: uint8 (n <= batch, Hs, Ws, 3) host array.  Returns host (mask, label, counts[, radii])
-        for the n frames.  H2D and D2H copies are part of this call."""
+        for the n frames.  H2D and D2H copies (through pinned staging buffers, asynchronous, one
+        synchronisation at the end) are part of this call.  With copy=False the returned arrays are
+        views of the pinned buffers, valid until the next call."""
         n = frames.shape[0]
         assert n <= self.batch and tuple(frames.shape[1:3]) == self.src_hw
-        src = torch.from_numpy(frames)
-        self.frames_dev[:n].copy_(src, non_blocking=True)
-        if n < self.batch:
-            self.frames_dev[n:].zero_()
-        mask, label, counts, radii = self.run_device(self.frames_dev)
-        out = (mask[:n].cpu().numpy(), label[:n].cpu().numpy(), counts[:n].cpu().numpy(),
-               radii[:n].cpu().numpy() if radii is not None else None)
-        return out
+        hb = self._host_buffers()
+        hb['frames'][:n].copy_(torch.from_numpy(frames))
+        with torch.cuda.device(self.device):
+            self.frames_dev[:n].copy_(hb['frames'][:n], non_blocking=True)
+            if n < self.batch:
+                self.frames_dev[n:].zero_()
+            mask, label, counts, radii = self.run_device(self.frames_dev)
+            hb['mask'][:n].copy_(mask[:n], non_blocking=True)
+            hb['label'][:n].copy_(label[:n], non_blocking=True)
+            hb['counts'][:n].copy_(counts[:n], non_blocking=True)
+            if radii is not None:
+                hb['radii'][:n].copy_(radii[:n], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        out = [hb['mask'][:n].numpy(), hb['label'][:n].numpy(), hb['counts'][:n].numpy(),
+               hb['radii'][:n].numpy() if radii is not None else None]
+        if copy:
+            out = [o.copy() if o is not None else None for o in out]
+        return tuple(out)
