@@ -153,48 +153,70 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 }
 
 // ------------------------------------------------------------------------------------ depthwise
-// HBM-bound.  Work item = 8 channels (16 B) x P consecutive output pixels of one row; items are
-// flattened (pixel-group, channel-group) with the channel group fastest, so a warp always reads
-// consecutive 16-byte chunks whatever C is.  A block owns a contiguous run of pixel groups of one
-// image and a chunk of <= 128 channel groups; squeeze-excite sums go through shared-memory
-// atomics and leave the block as one global atomic per channel.
-__host__ __device__ constexpr int dw_p(int K) { return K == 3 ? 4 : 2; }  // output pixels per item (register budget)
-constexpr int kDwCgChunk = 128;  // channel groups per block column
-constexpr int kDwPgPerBlock = 64;
+// HBM-bound by nature, instruction-bound in practice, so the inner loop is kept lean:
+//   * work item = 8 channels (16 B) x 4 consecutive output pixels of one row; a thread keeps ONE
+//     channel group for its whole life (bias, SE sums in registers) and strides over pixel groups,
+//     consecutive threads take consecutive 16-byte chunks (coalesced whatever C is);
+//   * the fp32 filter bank of the block's <= 32 channel groups sits in shared memory;
+//   * all input vectors of a filter row are loaded before any is used (one exposed latency per row);
+//   * math is packed fp32x2 (fma.rn.f32x2, sm_100): half the FMA issue slots.
+// Squeeze-excite sums leave the block as one global atomic per channel.
+constexpr int kDwP = 4;          // output pixels per item
+constexpr int kDwCgChunk = 32;   // channel groups per block column (256 channels)
 
-// All loads of one filter row (WIN input vectors + K weight vectors) are issued together before
-// any of them is consumed, so a warp exposes one memory latency per row instead of one per load.
-template <int K, int S, bool CHECK>
-__device__ __forceinline__ void dw_rows(float (&acc)[dw_p(K)][8], const uint4* __restrict__ in4,
-                                        const uint4* __restrict__ w4, int C8, int W, int H, int ix0, int iy0) {
-  constexpr int kDwP = dw_p(K);
-  constexpr int WIN = (kDwP - 1) * S + K;
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// 8 bf16 (uint4) -> four fp32x2 pairs
+__device__ __forceinline__ void bf16x8_to_f32x2(const uint4& v, unsigned long long (&f)[4]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
+  for (int i = 0; i < 4; ++i)
+    f[i] = pack_f32x2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+}
+
+template <int K, int S, bool CHECK>
+__device__ __forceinline__ void dw_rows(unsigned long long (&acc)[kDwP][4], const uint4* __restrict__ in4,
+                                        const float* __restrict__ wsm_cg, int C8, int W, int H, int ix0, int iy0) {
+  constexpr int WIN = (kDwP - 1) * S + K;
+#pragma unroll(K == 3 ? 3 : 1)
   for (int ky = 0; ky < K; ++ky) {
     const int iy = iy0 + ky;
     if (CHECK && (iy < 0 || iy >= H)) continue;
     const uint4* row = in4 + static_cast<size_t>(iy) * W * C8;
-    uint4 v[WIN], wv[K];
+    uint4 v[WIN];
 #pragma unroll
     for (int dx = 0; dx < WIN; ++dx) {
       const int ix = ix0 + dx;
       v[dx] = (!CHECK || (ix >= 0 && ix < W)) ? __ldg(row + static_cast<size_t>(ix) * C8) : make_uint4(0, 0, 0, 0);
     }
+    unsigned long long wr[K][4];
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) wv[kx] = __ldg(w4 + static_cast<size_t>(ky * K + kx) * C8);
-    float wr[K][8];
-#pragma unroll
-    for (int kx = 0; kx < K; ++kx) unpack8(wv[kx], wr[kx]);
+    for (int kx = 0; kx < K; ++kx) {
+      const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wsm_cg + (ky * K + kx) * (kDwCgChunk * 8));
+      const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(wsm_cg + (ky * K + kx) * (kDwCgChunk * 8) + 4);
+      wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w1.x; wr[kx][3] = w1.y;
+    }
 #pragma unroll
     for (int dx = 0; dx < WIN; ++dx) {
-      float f[8];
-      unpack8(v[dx], f);
+      unsigned long long f[4];
+      bf16x8_to_f32x2(v[dx], f);
 #pragma unroll
       for (int p = 0; p < kDwP; ++p) {
         const int kx = dx - p * S;  // compile-time after unrolling
         if (kx >= 0 && kx < K) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(f[e], wr[kx][e], acc[p][e]);
+          for (int e = 0; e < 4; ++e) acc[p][e] = f32x2_fma(f[e], wr[kx][e], acc[p][e]);
         }
       }
     }
@@ -203,63 +225,72 @@ __device__ __forceinline__ void dw_rows(float (&acc)[dw_p(K)][8], const uint4* _
 
 template <int K, int S>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __restrict__ in,
-                                                     const __nv_bfloat16* __restrict__ weight,  // [K*K][C] bf16
-                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                     int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo,
-                                                     int act, float* __restrict__ pool_sum) {
+                                                        const __nv_bfloat16* __restrict__ weight,  // [K*K][C] bf16
+                                                        const float* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ out, int H, int W, int C, int pad_t,
+                                                        int pad_l, int Ho, int Wo, int pg_per_block, int act,
+                                                        float* __restrict__ pool_sum) {
+  __shared__ __align__(16) float wsm[K * K][kDwCgChunk * 8];
   __shared__ float sums[8][kDwCgChunk];  // [e][channel group]: conflict-free for consecutive groups
-  constexpr int kDwP = dw_p(K);
   const int C8 = C >> 3;
   const int cg0 = blockIdx.x * kDwCgChunk;
   const int cgc = min(kDwCgChunk, C8 - cg0);
   const int n = blockIdx.z;
   const int wg = (Wo + kDwP - 1) / kDwP;  // pixel groups per output row
   const int npg = Ho * wg;
-  const int pg0 = blockIdx.y * kDwPgPerBlock;
-  const int pgc = min(kDwPgPerBlock, npg - pg0);
-  if (pool_sum) {
-    for (int i = threadIdx.x; i < 8 * kDwCgChunk; i += 256) (&sums[0][0])[i] = 0.f;
-    __syncthreads();
+  const int pg0 = blockIdx.y * pg_per_block;
+  const int pgc = min(pg_per_block, npg - pg0);
+  for (int i = threadIdx.x; i < K * K * kDwCgChunk * 8; i += 256) {
+    const int tap = i / (kDwCgChunk * 8), cl = i - tap * (kDwCgChunk * 8);
+    const int c = cg0 * 8 + cl;
+    (&wsm[0][0])[i] = c < C ? __bfloat162float(weight[static_cast<size_t>(tap) * C + c]) : 0.f;
   }
-  // thread -> fixed channel group, strided over pixel groups: bias / SE sums stay in registers
-  const int lanes_pg = 256 / cgc;  // pixel groups processed per sweep
+  if (pool_sum)
+    for (int i = threadIdx.x; i < 8 * kDwCgChunk; i += 256) (&sums[0][0])[i] = 0.f;
+  __syncthreads();
+  // thread -> fixed channel group, strided over pixel groups
+  const int lanes_pg = 256 / cgc;
   const int cgl = threadIdx.x % cgc;
   const int pgl0 = threadIdx.x / cgc;
   const bool active = pgl0 < lanes_pg;
   const int cg = cg0 + cgl;
   const uint4* in4 = reinterpret_cast<const uint4*>(in) + static_cast<size_t>(n) * H * W * C8 + cg;
   uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * Ho * Wo * C8 + cg;
-  const uint4* w4 = reinterpret_cast<const uint4*>(weight) + cg;
+  const float* wsm_cg = &wsm[0][0] + cgl * 8;
   constexpr int WIN = (kDwP - 1) * S + K;
-  float bs[8], ps[8];
+  unsigned long long bs[4];
+  float ps[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    bs[e] = active ? __ldg(bias + cg * 8 + e) : 0.f;
-    ps[e] = 0.f;
-  }
+  for (int e = 0; e < 4; ++e)
+    bs[e] = active ? pack_f32x2(__ldg(bias + cg * 8 + 2 * e), __ldg(bias + cg * 8 + 2 * e + 1)) : 0ull;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ps[e] = 0.f;
   if (active) {
     for (int pgl = pgl0; pgl < pgc; pgl += lanes_pg) {
       const int pg = pg0 + pgl;
       const int oy = pg / wg;
       const int ox0 = (pg - oy * wg) * kDwP;
-      float acc[kDwP][8];
+      unsigned long long acc[kDwP][4];
 #pragma unroll
       for (int p = 0; p < kDwP; ++p)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[p][e] = bs[e];
+        for (int e = 0; e < 4; ++e) acc[p][e] = bs[e];
       const int ix0 = ox0 * S - pad_l;
       const int iy0 = oy * S - pad_t;
       const bool interior = ix0 >= 0 && ix0 + WIN <= W && iy0 >= 0 && iy0 + K <= H;
       if (interior)
-        dw_rows<K, S, false>(acc, in4, w4, C8, W, H, ix0, iy0);
+        dw_rows<K, S, false>(acc, in4, wsm_cg, C8, W, H, ix0, iy0);
       else
-        dw_rows<K, S, true>(acc, in4, w4, C8, W, H, ix0, iy0);
+        dw_rows<K, S, true>(acc, in4, wsm_cg, C8, W, H, ix0, iy0);
 #pragma unroll
       for (int p = 0; p < kDwP; ++p) {
         if (ox0 + p < Wo) {
+          float y[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[p][e] = act_f(acc[p][e], act);
-          const uint4 o = pack8(acc[p]);
+          for (int e = 0; e < 4; ++e) unpack_f32x2(acc[p][e], y[2 * e], y[2 * e + 1]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = act_f(y[e], act);
+          const uint4 o = pack8(y);
           out4[(static_cast<size_t>(oy) * Wo + ox0 + p) * C8] = o;
           if (pool_sum) {  // pool what the next layer actually reads (the bf16-rounded activation)
             float r[8];
@@ -403,14 +434,18 @@ extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bi
                              int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, void* stream) {
   if (C % 8) return fail(OCTSEG_EINVAL, "dwconv: C must be a multiple of 8 (C=%d)", C);
   const int C8 = C / 8;
-  const int wg = cdiv(Wo, dw_p(k));
-  dim3 grid(cdiv(C8, kDwCgChunk), cdiv(Ho * wg, kDwPgPerBlock), N);
+  const int npg = Ho * cdiv(Wo, kDwP);
+  const int cols = cdiv(C8, kDwCgChunk);
+  // enough blocks for >= 8 per SM on small feature maps, long strips on large ones
+  int pgb = 64;
+  while (pgb > 8 && static_cast<long long>(cols) * cdiv(npg, pgb) * N < 148 * 8) pgb >>= 1;
+  dim3 grid(cols, cdiv(npg, pgb), N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* i = static_cast<const __nv_bfloat16*>(in);
   const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(weight);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
 #define OCTSEG_DW(KK, SS) \
-  dwconv_kernel<KK, SS><<<grid, 256, 0, st>>>(i, w, bias, o, H, W, C, pad_t, pad_l, Ho, Wo, act, pool_sum)
+  dwconv_kernel<KK, SS><<<grid, 256, 0, st>>>(i, w, bias, o, H, W, C, pad_t, pad_l, Ho, Wo, pgb, act, pool_sum)
   if (k == 3 && stride == 1) OCTSEG_DW(3, 1);
   else if (k == 3 && stride == 2) OCTSEG_DW(3, 2);
   else if (k == 5 && stride == 1) OCTSEG_DW(5, 1);

@@ -54,6 +54,7 @@ def main():
     print(f'eager sum {tot:.3f} ms; top ops:')
     for n, t in rows[:25]:
         print(f'  {t:8.4f} ms  {100 * t / tot:5.1f}%  {n}')
+    json.dump({n: t for n, t in rows}, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', f'ops_{key}.json'), 'w'))
     groups = {}
     for n, t in rows:
         k = 'stem' if ('conv1' == n.split('.')[-1] and n.count('.') == 1) or 'stem' in n else (
