@@ -39,6 +39,20 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 
+// packed fp32x2 math (sm_100 FFMA2): two FMAs per issue slot
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 // ------------------------------------------------------------------------------------ stem
 // One block = 16x16 output pixels; the input patch and the whole filter bank sit in shared
 // memory; each thread owns one pixel and CO output channels in registers.
@@ -84,9 +98,9 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const int oy = oy0 + ty, ox = ox0 + tx;
-  float acc[CO];
+  unsigned long long acc2[CO / 2];
 #pragma unroll
-  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  for (int c = 0; c < CO / 2; ++c) acc2[c] = 0ull;
   for (int ky = 0; ky < p.k; ++ky) {
     for (int kx = 0; kx < p.k; ++kx) {
       const float* pp = patch + ((ty * p.stride + ky) * pdim + tx * p.stride + kx) * 3;
@@ -94,25 +108,34 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float v = pp[c];
-        const float4* w4 = reinterpret_cast<const float4*>(ww + c * CO);
+        const unsigned long long vv = pack_f32x2(v, v);
+        const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(ww + c * CO);
 #pragma unroll
         for (int g = 0; g < CO / 4; ++g) {
-          const float4 w = w4[g];
-          acc[4 * g + 0] = fmaf(v, w.x, acc[4 * g + 0]);
-          acc[4 * g + 1] = fmaf(v, w.y, acc[4 * g + 1]);
-          acc[4 * g + 2] = fmaf(v, w.z, acc[4 * g + 2]);
-          acc[4 * g + 3] = fmaf(v, w.w, acc[4 * g + 3]);
+          const ulonglong2 w = w2[g];
+          acc2[2 * g] = f32x2_fma(vv, w.x, acc2[2 * g]);
+          acc2[2 * g + 1] = f32x2_fma(vv, w.y, acc2[2 * g + 1]);
         }
       }
     }
   }
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO / 2; ++c) unpack_f32x2(acc2[c], acc[2 * c], acc[2 * c + 1]);
   if (oy < p.Ho && ox < p.Wo) {
     __nv_bfloat16* o = p.out + ((static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox) * p.out_ldc;
 #pragma unroll
     for (int g = 0; g < CO / 8; ++g) {
       float f[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = act_f(acc[g * 8 + e] + __ldg(p.bias + g * 8 + e), p.act);
+      for (int e = 0; e < 8; ++e) f[e] = acc[g * 8 + e] + __ldg(p.bias + g * 8 + e);
+      if (p.act == OCTSEG_ACT_RELU) {  // uniform branch: only one activation's code runs
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+      } else if (p.act != OCTSEG_ACT_NONE) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = act_f(f[e], p.act);
+      }
       *reinterpret_cast<uint4*>(o + g * 8) = pack8(f);
     }
   }
@@ -164,19 +187,6 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 constexpr int kDwP = 4;          // output pixels per item
 constexpr int kDwCgChunk = 32;   // channel groups per block column (256 channels)
 
-__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-  unsigned long long d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-  return d;
-}
-__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
 // 8 bf16 (uint4) -> four fp32x2 pairs
 __device__ __forceinline__ void bf16x8_to_f32x2(const uint4& v, unsigned long long (&f)[4]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -288,8 +298,21 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
           float y[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) unpack_f32x2(acc[p][e], y[2 * e], y[2 * e + 1]);
+          if (act == OCTSEG_ACT_SWISH) {  // uniform branch: only one activation's code runs
 #pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] = act_f(y[e], act);
+            for (int e = 0; e < 8; ++e) {
+              const float h = 0.5f * y[e];
+              float t;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+              y[e] = fmaf(h, t, h);
+            }
+          } else if (act == OCTSEG_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+          } else if (act != OCTSEG_ACT_NONE) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = act_f(y[e], act);
+          }
           const uint4 o = pack8(y);
           out4[(static_cast<size_t>(oy) * Wo + ox0 + p) * C8] = o;
           if (pool_sum) {  // pool what the next layer actually reads (the bf16-rounded activation)
