@@ -185,8 +185,7 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 //   * math is packed fp32x2 (fma.rn.f32x2, sm_100): half the FMA issue slots.
 // Squeeze-excite sums leave the block as one global atomic per channel.
 constexpr int kDwP = 4;          // output pixels per item
-constexpr int kDwCgChunk = 16;   // channel groups per block column (128 channels)
-__host__ __device__ constexpr int dw_tile_groups(int K) { return K == 3 ? 8 : 4; }  // tile width in pixel groups
+constexpr int kDwCgChunk = 32;   // channel groups per block column (256 channels)
 
 // 8 bf16 (uint4) -> four fp32x2 pairs
 __device__ __forceinline__ void bf16x8_to_f32x2(const uint4& v, unsigned long long (&f)[4]) {
@@ -239,7 +238,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ weight,  // [K*K][C] bf16
                                                         const float* __restrict__ bias,
                                                         __nv_bfloat16* __restrict__ out, int H, int W, int C, int pad_t,
-                                                        int pad_l, int Ho, int Wo, int tile_rows, int act,
+                                                        int pad_l, int Ho, int Wo, int pg_per_block, int act,
                                                         float* __restrict__ pool_sum) {
   __shared__ __align__(16) float wsm[K * K][kDwCgChunk * 8];
   __shared__ float sums[8][kDwCgChunk];  // [e][channel group]: conflict-free for consecutive groups
@@ -247,13 +246,10 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
   const int cg0 = blockIdx.x * kDwCgChunk;
   const int cgc = min(kDwCgChunk, C8 - cg0);
   const int n = blockIdx.z;
-  // a block owns a 2-D tile (tile_rows x TG pixel groups): the K input rows a pixel group needs are the
-  // rows its vertical neighbours in the tile need, so they are served by L1 instead of L2
-  constexpr int TG = dw_tile_groups(K);
   const int wg = (Wo + kDwP - 1) / kDwP;  // pixel groups per output row
-  const int tiles_x = (wg + TG - 1) / TG;
-  const int tile_y = blockIdx.y / tiles_x, tile_x = blockIdx.y - tile_y * tiles_x;
-  const int pgc = tile_rows * TG;
+  const int npg = Ho * wg;
+  const int pg0 = blockIdx.y * pg_per_block;
+  const int pgc = min(pg_per_block, npg - pg0);
   for (int i = threadIdx.x; i < K * K * kDwCgChunk * 8; i += 256) {
     const int tap = i / (kDwCgChunk * 8), cl = i - tap * (kDwCgChunk * 8);
     const int c = cg0 * 8 + cl;
@@ -281,11 +277,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
   for (int e = 0; e < 8; ++e) ps[e] = 0.f;
   if (active) {
     for (int pgl = pgl0; pgl < pgc; pgl += lanes_pg) {
-      const int r = pgl / TG;
-      const int oy = tile_y * tile_rows + r;
-      const int gx = tile_x * TG + (pgl - r * TG);
-      if (oy >= Ho || gx >= wg) continue;
-      const int ox0 = gx * kDwP;
+      const int pg = pg0 + pgl;
+      const int oy = pg / wg;
+      const int ox0 = (pg - oy * wg) * kDwP;
       unsigned long long acc[kDwP][4];
 #pragma unroll
       for (int p = 0; p < kDwP; ++p)
@@ -463,19 +457,18 @@ extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bi
                              int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, void* stream) {
   if (C % 8) return fail(OCTSEG_EINVAL, "dwconv: C must be a multiple of 8 (C=%d)", C);
   const int C8 = C / 8;
-  const int wg = cdiv(Wo, kDwP);
+  const int npg = Ho * cdiv(Wo, kDwP);
   const int cols = cdiv(C8, kDwCgChunk);
-  const int tg = dw_tile_groups(k);
-  // 8-row tiles on large feature maps; fewer rows when that leaves fewer than ~8 blocks per SM
-  int rows = 8;
-  while (rows > 1 && static_cast<long long>(cols) * cdiv(wg, tg) * cdiv(Ho, rows) * N < 148 * 8) rows >>= 1;
-  dim3 grid(cols, cdiv(wg, tg) * cdiv(Ho, rows), N);
+  // enough blocks for >= 8 per SM on small feature maps, long strips on large ones
+  int pgb = 64;
+  while (pgb > 8 && static_cast<long long>(cols) * cdiv(npg, pgb) * N < 148 * 8) pgb >>= 1;
+  dim3 grid(cols, cdiv(npg, pgb), N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* i = static_cast<const __nv_bfloat16*>(in);
   const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(weight);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
 #define OCTSEG_DW(KK, SS) \
-  dwconv_kernel<KK, SS><<<grid, 256, 0, st>>>(i, w, bias, o, H, W, C, pad_t, pad_l, Ho, Wo, rows, act, pool_sum)
+  dwconv_kernel<KK, SS><<<grid, 256, 0, st>>>(i, w, bias, o, H, W, C, pad_t, pad_l, Ho, Wo, pgb, act, pool_sum)
   if (k == 3 && stride == 1) OCTSEG_DW(3, 1);
   else if (k == 3 && stride == 2) OCTSEG_DW(3, 2);
   else if (k == 5 && stride == 1) OCTSEG_DW(5, 1);
