@@ -96,3 +96,50 @@ def save_checkpoint(model: nn.Module, path: str) -> None:
     """Same container as a pytorch_lightning .ckpt as far as inference reads it."""
     torch.save({'state_dict': model.state_dict(), 'epoch': 0, 'global_step': 0,
                 'pytorch-lightning_version': '2.2.1'}, path)
+
+
+def phantom_targets(start: int, count: int, size: int, n_classes: int) -> np.ndarray:
+    """Structured ground truth for a short fit: class 0 = lumen disk of synthetic frame `idx` (same
+    random stream as the frame generator), class 1 = the 0.08*size thick wall ring around it."""
+    out = np.zeros((count, n_classes, size, size), np.float32)
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32)
+    c = (size - 1) / 2.0
+    dx, dy = xx - c, yy - c
+    r = np.sqrt(dx * dx + dy * dy) / size
+    th = np.arctan2(dy, dx)
+    for i in range(count):
+        rng = np.random.Generator(np.random.PCG64(FRAME_SEED + start + i))
+        bound = rng.uniform(0.15, 0.30) * np.ones_like(r)
+        for k in range(1, 4):
+            bound += rng.uniform(0.0, 0.03) * np.cos(k * th + rng.uniform(0, 2 * np.pi))
+        out[i, 0] = r < bound
+        if n_classes > 1:
+            out[i, 1] = (r >= bound) & (r < bound + 0.08)
+    return out
+
+
+def fit_model(model: 'model_ref.OCTSegmentationModelRef', device, steps: int = 120, size: int = 128, batch: int = 8,
+              lr: float = 2e-3, seed: int = 0) -> float:
+    """Short seeded fit of the WHOLE oracle network on phantom targets (Adam, BCE-with-logits), so
+    that masks are structured and |logit| is large away from object boundaries -- the regime a
+    trained checkpoint is in, and the one in which Dice between two implementations is meaningful
+    (SURVEY.md S7 'hard parts').  Returns the final loss.  Leaves the model in eval mode."""
+    torch.manual_seed(seed)
+    net = model.model.to(device)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=lr)
+    n_classes = len(model.classes)
+    loss_v = float('nan')
+    for step in range(steps):
+        idx = 1000 + step * batch
+        frames = synthetic_frames(idx, batch, size)[..., ::-1].copy()
+        x = torch.from_numpy(frames).to(device).permute(0, 3, 1, 2).float()
+        t = torch.from_numpy(phantom_targets(idx, batch, size, n_classes)).to(device)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(net(x), t)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        loss_v = loss.item()
+    net.eval()
+    model.eval()
+    return loss_v
