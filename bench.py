@@ -275,7 +275,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=16)
+    ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-frames', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
