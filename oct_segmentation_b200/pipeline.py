@@ -53,6 +53,11 @@ class EnsemblePipeline:
             self.sizes[d] = S
             self.nets[d] = model.model.compiled(batch, S, S, self.device, 'u8', 'u8_nchw')
         self.order = [CLASS_IDS[c] - 1 for c in self.classes]
+        # the networks are independent: each gets its own stream so small launches of one overlap the others
+        with torch.cuda.device(self.device):
+            self.streams = {d: torch.cuda.Stream() for d in self.model_dirs}
+            self.ev_in = torch.cuda.Event()
+            self.ev_done = {d: torch.cuda.Event() for d in self.model_dirs}
         Hs, Ws = self.src_hw
         with torch.cuda.device(self.device):
             self.frames_dev = torch.empty(batch, Hs, Ws, 3, dtype=torch.uint8, device=self.device)
@@ -66,14 +71,22 @@ class EnsemblePipeline:
     def run_device(self, frames_dev: torch.Tensor):
         """frames_dev: uint8 CUDA (batch, Hs, Ws, 3) RGB.  Returns device (mask, label, counts[, radii])."""
         class_planes = {}
+        cur = torch.cuda.current_stream(self.device)
+        self.ev_in.record(cur)
         for d in self.model_dirs:
             net = self.nets[d]
-            P.preprocess(frames_dev, self.sizes[d], out=net.x_nhwc)
-            out = net.run()                                              # (batch, C, S, S) uint8 {0,1}
+            st = self.streams[d]
+            st.wait_event(self.ev_in)
+            with torch.cuda.stream(st):
+                P.preprocess(frames_dev, self.sizes[d], out=net.x_nhwc)
+                out = net.run()                                          # (batch, C, S, S) uint8 {0,1}
+                self.ev_done[d].record(st)
             for name in self.classes:
                 meta = MODELS_META[name]
                 if meta['model_dir'] == d:
                     class_planes[CLASS_IDS[name] - 1] = out[:, meta['index']]
+        for d in self.model_dirs:
+            cur.wait_event(self.ev_done[d])
         P.postprocess(class_planes, self.order, self.Ho, self.Wo, self.batch, self.device,
                       mask=self.mask, label=self.label, counts=self.counts)
         radii = P.radial_thickness(self.mask) if self.thickness else None
