@@ -379,7 +379,11 @@ __global__ void __launch_bounds__(256) se_scale_weights_kernel(const float* __re
   }
   __nv_bfloat16* o = out + static_cast<size_t>(n) * rows * Ktot + k;
   const float* wk = w + k;
-  for (int row = 0; row < rows; ++row) o[static_cast<size_t>(row) * Ktot] = __float2bfloat16_rn(__ldg(wk + static_cast<size_t>(row) * Ktot) * g);
+  const int per = (rows + gridDim.z - 1) / gridDim.z;  // rows are split over blockIdx.z for parallelism
+  const int r0 = blockIdx.z * per, r1 = min(rows, r0 + per);
+#pragma unroll 4
+  for (int row = r0; row < r1; ++row)
+    o[static_cast<size_t>(row) * Ktot] = __float2bfloat16_rn(__ldg(wk + static_cast<size_t>(row) * Ktot) * g);
 }
 
 static int grid_for(size_t total, int block) {
@@ -488,7 +492,9 @@ extern "C" int octseg_se_hidden(const float* pool_sum, float inv_hw, const float
 extern "C" int octseg_se_scale_weights(const float* hidden, const float* w2t, const float* b2, const float* w, void* out,
                                        int32_t N, int32_t rows, int32_t Ktot, int32_t C, int32_t Cr, void* stream) {
   if (Cr > 4096) return fail(OCTSEG_EINVAL, "se_scale_weights: Cr too large");
-  dim3 grid(cdiv(Ktot, 256), N);
+  int zc = 1;  // enough blocks to fill the machine (the gate is recomputed per row chunk, it is tiny)
+  while (zc < 16 && cdiv(Ktot, 256) * N * zc < 148 * 4 && rows / (zc * 2) >= 8) zc *= 2;
+  dim3 grid(cdiv(Ktot, 256), N, zc);
   se_scale_weights_kernel<<<grid, 256, static_cast<size_t>(Cr) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       hidden, w2t, b2, w, static_cast<__nv_bfloat16*>(out), rows, Ktot, C, Cr);
   return check_launch("se_scale_weights_kernel");
