@@ -39,20 +39,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 
-// packed fp32x2 math (sm_100 FFMA2): two FMAs per issue slot
-__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-  unsigned long long d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-  return d;
-}
-__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
+// packed fp32x2 math (sm_100 FFMA2, __ffma2_rn): two FMAs per issue slot; float2 lets the compiler
+// keep the operands in aligned register pairs without extra moves
 // ------------------------------------------------------------------------------------ stem
 // One block = 16x16 output pixels; the input patch and the whole filter bank sit in shared
 // memory; each thread owns one pixel and CO output channels in registers.
@@ -98,9 +86,9 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const int oy = oy0 + ty, ox = ox0 + tx;
-  unsigned long long acc2[CO / 2];
+  float2 acc2[CO / 2];
 #pragma unroll
-  for (int c = 0; c < CO / 2; ++c) acc2[c] = 0ull;
+  for (int c = 0; c < CO / 2; ++c) acc2[c] = make_float2(0.f, 0.f);
   for (int ky = 0; ky < p.k; ++ky) {
     for (int kx = 0; kx < p.k; ++kx) {
       const float* pp = patch + ((ty * p.stride + ky) * pdim + tx * p.stride + kx) * 3;
@@ -108,20 +96,23 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float v = pp[c];
-        const unsigned long long vv = pack_f32x2(v, v);
-        const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(ww + c * CO);
+        const float2 vv = make_float2(v, v);
+        const float4* w4 = reinterpret_cast<const float4*>(ww + c * CO);
 #pragma unroll
         for (int g = 0; g < CO / 4; ++g) {
-          const ulonglong2 w = w2[g];
-          acc2[2 * g] = f32x2_fma(vv, w.x, acc2[2 * g]);
-          acc2[2 * g + 1] = f32x2_fma(vv, w.y, acc2[2 * g + 1]);
+          const float4 w = w4[g];
+          acc2[2 * g] = __ffma2_rn(vv, make_float2(w.x, w.y), acc2[2 * g]);
+          acc2[2 * g + 1] = __ffma2_rn(vv, make_float2(w.z, w.w), acc2[2 * g + 1]);
         }
       }
     }
   }
   float acc[CO];
 #pragma unroll
-  for (int c = 0; c < CO / 2; ++c) unpack_f32x2(acc2[c], acc[2 * c], acc[2 * c + 1]);
+  for (int c = 0; c < CO / 2; ++c) {
+    acc[2 * c] = acc2[c].x;
+    acc[2 * c + 1] = acc2[c].y;
+  }
   if (oy < p.Ho && ox < p.Wo) {
     __nv_bfloat16* o = p.out + ((static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox) * p.out_ldc;
 #pragma unroll
@@ -188,15 +179,14 @@ constexpr int kDwP = 4;          // output pixels per item
 constexpr int kDwCgChunk = 32;   // channel groups per block column (256 channels)
 
 // 8 bf16 (uint4) -> four fp32x2 pairs
-__device__ __forceinline__ void bf16x8_to_f32x2(const uint4& v, unsigned long long (&f)[4]) {
+__device__ __forceinline__ void bf16x8_to_f32x2(const uint4& v, float2 (&f)[4]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    f[i] = pack_f32x2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+  for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
 }
 
 template <int K, int S, bool CHECK>
-__device__ __forceinline__ void dw_rows(unsigned long long (&acc)[kDwP][4], const uint4* __restrict__ in4,
+__device__ __forceinline__ void dw_rows(float2 (&acc)[kDwP][4], const uint4* __restrict__ in4,
                                         const float* __restrict__ wsm_cg, int C8, int W, int H, int ix0, int iy0) {
   constexpr int WIN = (kDwP - 1) * S + K;
 #pragma unroll(K == 3 ? 3 : 1)
@@ -210,23 +200,26 @@ __device__ __forceinline__ void dw_rows(unsigned long long (&acc)[kDwP][4], cons
       const int ix = ix0 + dx;
       v[dx] = (!CHECK || (ix >= 0 && ix < W)) ? __ldg(row + static_cast<size_t>(ix) * C8) : make_uint4(0, 0, 0, 0);
     }
-    unsigned long long wr[K][4];
+    float2 wr[K][4];
 #pragma unroll
     for (int kx = 0; kx < K; ++kx) {
-      const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wsm_cg + (ky * K + kx) * (kDwCgChunk * 8));
-      const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(wsm_cg + (ky * K + kx) * (kDwCgChunk * 8) + 4);
-      wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w1.x; wr[kx][3] = w1.y;
+      const float4 w0 = *reinterpret_cast<const float4*>(wsm_cg + (ky * K + kx) * (kDwCgChunk * 8));
+      const float4 w1 = *reinterpret_cast<const float4*>(wsm_cg + (ky * K + kx) * (kDwCgChunk * 8) + 4);
+      wr[kx][0] = make_float2(w0.x, w0.y);
+      wr[kx][1] = make_float2(w0.z, w0.w);
+      wr[kx][2] = make_float2(w1.x, w1.y);
+      wr[kx][3] = make_float2(w1.z, w1.w);
     }
 #pragma unroll
     for (int dx = 0; dx < WIN; ++dx) {
-      unsigned long long f[4];
+      float2 f[4];
       bf16x8_to_f32x2(v[dx], f);
 #pragma unroll
       for (int p = 0; p < kDwP; ++p) {
         const int kx = dx - p * S;  // compile-time after unrolling
         if (kx >= 0 && kx < K) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[p][e] = f32x2_fma(f[e], wr[kx][e], acc[p][e]);
+          for (int e = 0; e < 4; ++e) acc[p][e] = __ffma2_rn(f[e], wr[kx][e], acc[p][e]);
         }
       }
     }
@@ -268,11 +261,11 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
   uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * Ho * Wo * C8 + cg;
   const float* wsm_cg = &wsm[0][0] + cgl * 8;
   constexpr int WIN = (kDwP - 1) * S + K;
-  unsigned long long bs[4];
+  float2 bs[4];
   float ps[8];
 #pragma unroll
   for (int e = 0; e < 4; ++e)
-    bs[e] = active ? pack_f32x2(__ldg(bias + cg * 8 + 2 * e), __ldg(bias + cg * 8 + 2 * e + 1)) : 0ull;
+    bs[e] = active ? make_float2(__ldg(bias + cg * 8 + 2 * e), __ldg(bias + cg * 8 + 2 * e + 1)) : make_float2(0.f, 0.f);
 #pragma unroll
   for (int e = 0; e < 8; ++e) ps[e] = 0.f;
   if (active) {
@@ -280,7 +273,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
       const int pg = pg0 + pgl;
       const int oy = pg / wg;
       const int ox0 = (pg - oy * wg) * kDwP;
-      unsigned long long acc[kDwP][4];
+      float2 acc[kDwP][4];
 #pragma unroll
       for (int p = 0; p < kDwP; ++p)
 #pragma unroll
@@ -297,7 +290,10 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __r
         if (ox0 + p < Wo) {
           float y[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) unpack_f32x2(acc[p][e], y[2 * e], y[2 * e + 1]);
+          for (int e = 0; e < 4; ++e) {
+            y[2 * e] = acc[p][e].x;
+            y[2 * e + 1] = acc[p][e].y;
+          }
           if (act == OCTSEG_ACT_SWISH) {  // uniform branch: only one activation's code runs
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
