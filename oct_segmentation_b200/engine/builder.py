@@ -102,6 +102,18 @@ class Builder:
             self._add(name, plan.run, tc_macs=geom.macs)
             return out_act
 
+        # narrow decoder conv over cat([up(x), skips...]): the half-resolution tile grid of the fused form
+        # reads the full-resolution skips through stride-2 boxes, 9 per tile and phase, and is bound by
+        # that activation feed.  Split it: depth-to-space conv of the upsampled part (no bias/act), then a
+        # plain 3x3 conv of the skips (wide boxes: 3x less feed) that adds the first part before the
+        # activation.  Costs one extra bf16 round trip of the (narrow) output.
+        if (bf16_out and not transposed and len(srcs) > 1 and srcs[0][1] and not any(up for _, up in srcs[1:])
+                and groups == 1 and res is None and cout <= 64 and srcs[1][0].W >= 112):
+            cup = srcs[0][0].C
+            part = self.conv([srcs[0]], w[:, :cup], None, name=name + '.up', pad=(1, 1), act='none')
+            return self.conv(list(srcs[1:]), w[:, cup:], b, name=name, pad=(1, 1), act=act, res=part,
+                             res_mode='before_act')
+
         # single-source upsample+conv / ConvTranspose with few output channels: one depth-to-space conv
         # on the half-resolution grid (N = 4*Cout) instead of four N = Cout phase problems
         if (bf16_out and len(srcs) == 1 and (transposed or srcs[0][1]) and res is None and 4 * pad8(cout) <= 256

@@ -72,8 +72,9 @@ class CheckedBuilder(Builder):
     @torch.no_grad()
     def run_checked(self):
         """Runs the op list one launch at a time; returns [(name, rel_l2)]."""
-        checks = {name.replace('[mask]', ''): (name, r, g) for name, r, g in self.checks}
-        assert len(checks) == len(self.checks)
+        checks = {}
+        for name, r, g in self.checks:          # a split conv registers its inner launch, then the whole op: keep the latter
+            checks[name.replace('[mask]', '')] = (name, r, g)
         errs = []
         for op_name, op in zip(self.op_names, self.ops):
             op()
