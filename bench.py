@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -238,8 +238,15 @@ def ours_arm(args):
                     else:
                         other_ms += s.elapsed_time(e)
         achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'launches_r1_traffic.json')
+        if os.path.exists(tpath):                       # dram__bytes_read+write per conv_tc_kernel launch (ncu pass)
+            tj = json.load(open(tpath))
+            if tj.get('batch', 16) == B:
+                traffic, traffic_src = tj['dram_bytes_per_launch'], 'profiles/launches_r1_traffic.json'
         roof = {'bound': 'tensor', 'kernel': 'conv_tc_kernel', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+                'algorithmic_flops_per_launch': tc_flops / max(n_tc, 1),
                 'launches_measured': n_tc, 'avg_launch_ms': tc_ms / max(n_tc, 1),
                 'share_of_network_time': tc_ms / (tc_ms + other_ms),
                 'how': 'algorithmic FLOPs (2 x dense MACs of the smp graph, DESIGN.md) of every conv_tc_kernel launch in one '
