@@ -119,18 +119,19 @@ def phantom_targets(start: int, count: int, size: int, n_classes: int) -> np.nda
 
 
 def fit_model(model: 'model_ref.OCTSegmentationModelRef', device, steps: int = 120, size: int = 128, batch: int = 8,
-              lr: float = 2e-3, seed: int = 0) -> float:
+              lr: float = 2e-3, seed: int = 0, target_loss: float = 0.0, max_steps: int = 0) -> float:
     """Short seeded fit of the WHOLE oracle network on phantom targets (Adam, BCE-with-logits), so
     that masks are structured and |logit| is large away from object boundaries -- the regime a
-    trained checkpoint is in, and the one in which Dice between two implementations is meaningful
+    trained checkpoint is in (after `steps` steps it keeps going until the smoothed loss drops below
+    `target_loss` or `max_steps` is reached), and the one in which Dice between two implementations is meaningful
     (SURVEY.md S7 'hard parts').  Returns the final loss.  Leaves the model in eval mode."""
     torch.manual_seed(seed)
     net = model.model.to(device)
     net.train()
     opt = torch.optim.Adam(net.parameters(), lr=lr)
     n_classes = len(model.classes)
-    loss_v = float('nan')
-    for step in range(steps):
+    loss_v, ema = float('nan'), None
+    for step in range(max(steps, max_steps)):
         idx = 1000 + step * batch
         frames = synthetic_frames(idx, batch, size)[..., ::-1].copy()
         x = torch.from_numpy(frames).to(device).permute(0, 3, 1, 2).float()
@@ -140,6 +141,9 @@ def fit_model(model: 'model_ref.OCTSegmentationModelRef', device, steps: int = 1
         loss.backward()
         opt.step()
         loss_v = loss.item()
+        ema = loss_v if ema is None else 0.9 * ema + 0.1 * loss_v
+        if step + 1 >= steps and (target_loss <= 0.0 or ema < target_loss):
+            break
     net.eval()
     model.eval()
     return loss_v
