@@ -21,7 +21,7 @@ def dice(a, b):
     return 2.0 * inter / max(a.sum().item() + b.sum().item(), 1)
 
 
-@pytest.mark.parametrize('key,size,steps', [('VV', 256, 150), ('LM', 256, 200), ('FC_LC', 256, 300)])
+@pytest.mark.parametrize('key,size,steps', [('VV', 512, 150), ('LM', 512, 200), ('FC_LC', 512, 300)])
 def test_fitted_checkpoint_dice(key, size, steps):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
