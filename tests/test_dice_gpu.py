@@ -21,18 +21,18 @@ def dice(a, b):
     return 2.0 * inter / max(a.sum().item() + b.sum().item(), 1)
 
 
-@pytest.mark.parametrize('key,size,steps', [('VV', 512, 150), ('LM', 512, 200), ('FC_LC', 512, 300)])
+@pytest.mark.parametrize('key,size,steps', [('VV', 256, 150), ('LM', 256, 200), ('FC_LC', 256, 400)])
 def test_fitted_checkpoint_dice(key, size, steps):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     ref = synth.make_model(key, calib_size=128, calib_frames=2)
-    loss = synth.fit_model(ref, 'cuda', steps=steps, size=128, batch=8, target_loss=0.008, max_steps=1200)
+    loss = synth.fit_model(ref, 'cuda', steps=steps, size=128, batch=8, target_loss=0.005, max_steps=1500)
     cfg = synth.MODEL_CONFIGS[key]
     ours = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
                                 in_channels=3, classes=cfg['classes'], encoder_weights=None)
     ours.load_state_dict(ref.state_dict(), strict=True)
     ours = ours.cuda().eval()
-    frames = synth.synthetic_frames(5000, 4, size)[..., ::-1].copy()
+    frames = synth.synthetic_frames(5000, 8, size)[..., ::-1].copy()
     x = torch.from_numpy(frames).cuda().permute(0, 3, 1, 2).float()
     with torch.no_grad():
         want = ref.model(x)
