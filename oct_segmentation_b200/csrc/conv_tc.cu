@@ -210,7 +210,7 @@ __device__ __forceinline__ void group_bar_sync(int group) {
 // ReLU / identity are one fmaxf against `lo` (0 or -inf); swish is a separate instantiation, so
 // the per-element code has no branches.
 template <bool SWISH>
-__device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8, const uint4 rv, float lo,
+__device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8, const __nv_bfloat16* r8, float lo,
                                            int res_mode) {
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias8));
   const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias8 + 4));
@@ -223,8 +223,9 @@ __device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8
   x[5] = __uint_as_float(v[5]) + b1.y;
   x[6] = __uint_as_float(v[6]) + b1.z;
   x[7] = __uint_as_float(v[7]) + b1.w;
-  float rr[8];  // residual values (zero bits when the layer has none)
-  {
+  float rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r8) {
+    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r8));
     const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -531,22 +532,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const float* bias = p.bias + tc.n_tile * p.BN;
       const __nv_bfloat16* rrow = (p.res && valid) ? p.res + pix * p.res_ldc + ch0 : nullptr;
 
-      // 64-channel chunks go registers -> swizzled shared tile -> TMA store (n_tma of them, see below)
-      const int n_tma =
-          p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0;
-      // residual of this group's first chunk: issued before waiting for the accumulator, so the (scattered,
-      // 16 B per pixel) loads overlap the MMAs; later chunks are prefetched one chunk ahead
-      uint4 rcur[4], rnext[4];
-      auto load_res = [&](int ck, uint4(&dst)[4]) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cc = ck * 64 + half * 32 + 8 * g;
-          dst[g] = (rrow && cc < nvalid) ? __ldg(reinterpret_cast<const uint4*>(rrow + cc)) : make_uint4(0, 0, 0, 0);
-        }
-      };
-      const int ck_first = ((chunk_ctr & 1) == static_cast<uint32_t>(group)) ? 0 : 1;
-      if (ck_first < n_tma) load_res(ck_first, rcur);
-
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
@@ -555,11 +540,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       // chunk also goes this way when the tile ends at the tensor's channel extent (TMA clips it).
       // The 16 warps form two independent groups (own staging buffer, own named barrier) that take
       // alternate chunks, so one group's barrier / TMEM / store latency overlaps the other's math.
+      const int n_tma =
+          p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0;
       for (int ck = 0; ck < n_tma; ++ck) {
         if (((chunk_ctr + ck) & 1) != static_cast<uint32_t>(group)) continue;  // warp-uniform
         const int cp = ck * 64 + half * 32;
         const uint32_t sbuf = smemOut + group * kOutBytes;
-        if (ck + 2 < n_tma) load_res(ck + 2, rnext);
         if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store left the buffer
         group_bar_sync(group);
         uint32_t v[32];
@@ -568,8 +554,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int cc = cp + 8 * g;
-          const uint4 ov = swish ? epi_pack8<true>(v + 8 * g, bias + cc, rcur[g], lo, p.res_mode)
-                                 : epi_pack8<false>(v + 8 * g, bias + cc, rcur[g], lo, p.res_mode);
+          const __nv_bfloat16* r8 = (rrow && cc < nvalid) ? rrow + cc : nullptr;
+          const uint4 ov = swish ? epi_pack8<true>(v + 8 * g, bias + cc, r8, lo, p.res_mode)
+                                 : epi_pack8<false>(v + 8 * g, bias + cc, r8, lo, p.res_mode);
           const uint32_t dst = sbuf + row * 128 + (((half * 4 + g) ^ (row & 7)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z),
                        "r"(ov.w)
@@ -585,8 +572,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_store_4d(&p.tmOut, sbuf, cch, tc.tw * p.TW, tc.th * p.TH, tc.n);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
       }
       chunk_ctr += n_tma;
 
@@ -605,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int g = 0; g < kEpiPart / 8; ++g) {
             if (cp + g * 8 < nvalid) {
-              const uint4 r8 = rrow ? __ldg(reinterpret_cast<const uint4*>(rrow + cp + 8 * g)) : make_uint4(0, 0, 0, 0);
+              const __nv_bfloat16* r8 = rrow ? rrow + cp + 8 * g : nullptr;
               __nv_bfloat16* og = o + g * 8;
               if (p.d2s) {  // depth-to-space: column -> (2x2 sub-pixel, channel) of a tensor twice the tile grid
                 const int col = ch0 + cp + g * 8, sub = col / p.d2s, co = col - sub * p.d2s;
