@@ -48,6 +48,18 @@ struct SegK {
   int wide;  // 1: one (TW + kw - 1)-pixel box per tap ROW; the kw taps are shifted views of it
 };
 
+// n / d for n * d < 2^32 (tile counters): one IMAD.HI instead of the ~25-instruction software division
+struct FastDiv {
+  uint32_t d, m;  // m = floor(2^32 / d) + 1; unused for d == 1
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.m = d > 1 ? static_cast<uint32_t>((1ull << 32) / d + 1ull) : 0u;
+  return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : __umulhi(n, f.m); }
+
 struct __align__(64) ConvKParams {
   CUtensorMap tmA[OCTSEG_MAX_SEG];
   CUtensorMap tmB[3];  // weight boxes (kc x BN) for kc = 16, 32, 64
@@ -65,6 +77,7 @@ struct __align__(64) ConvKParams {
   int res_ldc;
   void* out;
   int out_H, out_W, out_ldc, out_c_off, out_pack, d2s;
+  FastDiv fd_ntn, fd_phases, fd_tw, fd_th, fd_TW;
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -207,51 +220,66 @@ __device__ __forceinline__ void group_bar_sync(int group) {
 }
 
 // bias + residual + activation of 8 consecutive channels of one pixel -> 8 packed bf16.
-// ReLU / identity are one fmaxf against `lo` (0 or -inf); swish is a separate instantiation, so
-// the per-element code has no branches.
-template <bool SWISH>
-__device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float* bias8, const __nv_bfloat16* r8, float lo,
-                                           int res_mode) {
+// The epilogue of the output-bound layers is issue-bound, so the per-element code is specialised at
+// compile time on (activation, residual mode) and uses packed fp32x2 math (add/mul/fma.f32x2):
+//   relu            : FADD2 + cvt.rn.relu.bf16x2            (1 issue slot per element)
+//   swish           : FADD2, FMUL2, 2 MUFU.TANH, FFMA2, cvt  (3 per element)
+//   residual (bf16) : + 2 unpack + FADD2 per pair
+__device__ __forceinline__ uint32_t cvt_bf16x2(float2 x) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x.y), "f"(x.x));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2_relu(float2 x) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x.y), "f"(x.x));
+  return d;
+}
+__device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
+template <int ACT, int RES>
+__device__ __forceinline__ uint4 epi8(const uint32_t* v, const float* bias8, const __nv_bfloat16* r8) {
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias8));
   const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias8 + 4));
-  float x[8];
-  x[0] = __uint_as_float(v[0]) + b0.x;
-  x[1] = __uint_as_float(v[1]) + b0.y;
-  x[2] = __uint_as_float(v[2]) + b0.z;
-  x[3] = __uint_as_float(v[3]) + b0.w;
-  x[4] = __uint_as_float(v[4]) + b1.x;
-  x[5] = __uint_as_float(v[5]) + b1.y;
-  x[6] = __uint_as_float(v[6]) + b1.z;
-  x[7] = __uint_as_float(v[7]) + b1.w;
-  float rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (r8) {
-    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r8));
-    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+  float2 x[4];
+  x[0] = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
+  x[1] = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
+  x[2] = __fadd2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(b1.x, b1.y));
+  x[3] = __fadd2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(b1.z, b1.w));
+  float2 r[4];
+  if (RES != OCTSEG_RES_NONE) {
+    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+    if (r8) rv = __ldg(reinterpret_cast<const uint4*>(r8));
+    r[0] = bf16x2_to_f32x2(rv.x);
+    r[1] = bf16x2_to_f32x2(rv.y);
+    r[2] = bf16x2_to_f32x2(rv.z);
+    r[3] = bf16x2_to_f32x2(rv.w);
+  }
+  if (RES == OCTSEG_RES_BEFORE_ACT) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = __fadd2_rn(x[e], r[e]);
+  }
+  if (ACT == OCTSEG_ACT_SWISH) {  // x*sigmoid(x) = h*tanh(h) + h, h = x/2
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 f = __bfloat1622float2(r2[e]);
-      rr[2 * e] = f.x;
-      rr[2 * e + 1] = f.y;
+      const float2 h = __fmul2_rn(x[e], make_float2(0.5f, 0.5f));
+      x[e] = __ffma2_rn(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
     }
   }
-  const float pre = res_mode == OCTSEG_RES_BEFORE_ACT ? 1.f : 0.f;
-  const float post = res_mode == OCTSEG_RES_AFTER_ACT ? 1.f : 0.f;
   uint4 ov;
-  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+  if (RES == OCTSEG_RES_AFTER_ACT) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float y0 = fmaf(pre, rr[2 * e], x[2 * e]), y1 = fmaf(pre, rr[2 * e + 1], x[2 * e + 1]);
-    if (SWISH) {
-      const float h0 = 0.5f * y0, h1 = 0.5f * y1;
-      y0 = fmaf(h0, fast_tanh(h0), h0);
-      y1 = fmaf(h1, fast_tanh(h1), h1);
-    } else {
-      y0 = fmaxf(y0, lo);
-      y1 = fmaxf(y1, lo);
+    for (int e = 0; e < 4; ++e) {
+      if (ACT == OCTSEG_ACT_RELU) x[e] = make_float2(fmaxf(x[e].x, 0.f), fmaxf(x[e].y, 0.f));
+      x[e] = __fadd2_rn(x[e], r[e]);
     }
-    y0 = fmaf(post, rr[2 * e], y0);
-    y1 = fmaf(post, rr[2 * e + 1], y1);
-    o2[e] = __floats2bfloat162_rn(y0, y1);
+    ov = make_uint4(cvt_bf16x2(x[0]), cvt_bf16x2(x[1]), cvt_bf16x2(x[2]), cvt_bf16x2(x[3]));
+  } else if (ACT == OCTSEG_ACT_RELU) {
+    ov = make_uint4(cvt_bf16x2_relu(x[0]), cvt_bf16x2_relu(x[1]), cvt_bf16x2_relu(x[2]), cvt_bf16x2_relu(x[3]));
+  } else {
+    ov = make_uint4(cvt_bf16x2(x[0]), cvt_bf16x2(x[1]), cvt_bf16x2(x[2]), cvt_bf16x2(x[3]));
   }
   return ov;
 }
@@ -261,21 +289,27 @@ struct TileCoord {
 };
 // Tile order: channel tile fastest (CTAs running together share the A tile in L2), then the four
 // output phases of one spatial tile (they read the same input pixels), then space, then image.
-__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int t) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
   TileCoord c;
-  c.n_tile = t % p.n_tiles_n;
-  t /= p.n_tiles_n;
-  c.phase = t % p.phases;
-  t /= p.phases;
-  c.tw = t % p.tiles_w;
-  t /= p.tiles_w;
-  c.th = t % p.tiles_h;
-  c.n = t / p.tiles_h;
+  uint32_t t = static_cast<uint32_t>(tile), q;
+  q = fd_div(t, p.fd_ntn);
+  c.n_tile = static_cast<int>(t - q * p.fd_ntn.d);
+  t = q;
+  q = fd_div(t, p.fd_phases);
+  c.phase = static_cast<int>(t - q * p.fd_phases.d);
+  t = q;
+  q = fd_div(t, p.fd_tw);
+  c.tw = static_cast<int>(t - q * p.fd_tw.d);
+  t = q;
+  q = fd_div(t, p.fd_th);
+  c.th = static_cast<int>(t - q * p.fd_th.d);
+  c.n = static_cast<int>(q);
   c.ph = c.phase >> 1;
   c.pw = c.phase & 1;
   return c;
 }
 
+template <int ACT, int RES>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -515,9 +549,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int half = part & 1;          //                 32-column half of the group's chunk
     const int gtid = (static_cast<int>(threadIdx.x) - 64) & 255;
     const int row = q * 32 + lane;
-    const int th_l = row / p.TW, tw_l = row - th_l * p.TW;
-    const bool swish = p.act == OCTSEG_ACT_SWISH;
-    const float lo = p.act == OCTSEG_ACT_RELU ? 0.f : -INFINITY;
+    const int th_l = static_cast<int>(fd_div(static_cast<uint32_t>(row), p.fd_TW)), tw_l = row - th_l * p.TW;
+    const uint32_t sbuf = smemOut + group * kOutBytes;
+    // this thread's four 16-byte slots of its staging row (128B swizzle: 16-byte chunk index ^ (row & 7))
+    uint32_t sts_addr[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) sts_addr[g] = sbuf + row * 128 + (((half * 4 + g) ^ (row & 7)) << 4);
     int acc = 0;
     uint32_t acc_phase = 0, chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -530,7 +567,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int nvalid = min(p.cout_per_tile, p.Cout - ch0);
       const size_t pix = (static_cast<size_t>(tc.n) * p.out_H + oh) * p.out_W + ow;
       const float* bias = p.bias + tc.n_tile * p.BN;
-      const __nv_bfloat16* rrow = (p.res && valid) ? p.res + pix * p.res_ldc + ch0 : nullptr;
+      const __nv_bfloat16* rrow = nullptr;
+      if (RES != OCTSEG_RES_NONE && valid) rrow = p.res + pix * p.res_ldc + ch0;
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
@@ -540,28 +578,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       // chunk also goes this way when the tile ends at the tensor's channel extent (TMA clips it).
       // The 16 warps form two independent groups (own staging buffer, own named barrier) that take
       // alternate chunks, so one group's barrier / TMEM / store latency overlaps the other's math.
+      // The math runs BEFORE the wait for the staging buffer, so the previous TMA store drains under it.
       const int n_tma =
           p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0;
       for (int ck = 0; ck < n_tma; ++ck) {
         if (((chunk_ctr + ck) & 1) != static_cast<uint32_t>(group)) continue;  // warp-uniform
         const int cp = ck * 64 + half * 32;
-        const uint32_t sbuf = smemOut + group * kOutBytes;
-        if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store left the buffer
-        group_bar_sync(group);
         uint32_t v[32];
         tmem_ld32(taddr + cp, v);
         tmem_ld_wait();
+        uint4 ov[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int cc = cp + 8 * g;
-          const __nv_bfloat16* r8 = (rrow && cc < nvalid) ? rrow + cc : nullptr;
-          const uint4 ov = swish ? epi_pack8<true>(v + 8 * g, bias + cc, r8, lo, p.res_mode)
-                                 : epi_pack8<false>(v + 8 * g, bias + cc, r8, lo, p.res_mode);
-          const uint32_t dst = sbuf + row * 128 + (((half * 4 + g) ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ov.x), "r"(ov.y), "r"(ov.z),
-                       "r"(ov.w)
-                       : "memory");
+          const __nv_bfloat16* r8 = (RES != OCTSEG_RES_NONE && rrow && cc < nvalid) ? rrow + cc : nullptr;
+          ov[g] = epi8<ACT, RES>(v + 8 * g, bias + cc, r8);
         }
+        if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store left the buffer
+        group_bar_sync(group);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sts_addr[g]), "r"(ov[g].x), "r"(ov[g].y),
+                       "r"(ov[g].z), "r"(ov[g].w)
+                       : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         group_bar_sync(group);
         if (gtid == 0) {
@@ -590,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int g = 0; g < kEpiPart / 8; ++g) {
             if (cp + g * 8 < nvalid) {
-              const __nv_bfloat16* r8 = rrow ? rrow + cp + 8 * g : nullptr;
+              const __nv_bfloat16* r8 = (RES != OCTSEG_RES_NONE && rrow) ? rrow + cp + 8 * g : nullptr;
               __nv_bfloat16* og = o + g * 8;
               if (p.d2s) {  // depth-to-space: column -> (2x2 sub-pixel, channel) of a tensor twice the tile grid
                 const int col = ch0 + cp + g * 8, sub = col / p.d2s, co = col - sub * p.d2s;
@@ -598,9 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                     2 * ow + (sub & 1);
                 og = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_ldc + p.out_c_off + co;
               }
-              *reinterpret_cast<uint4*>(og) =
-                  swish ? epi_pack8<true>(v + 8 * g, bias + cp + 8 * g, r8, lo, p.res_mode)
-                        : epi_pack8<false>(v + 8 * g, bias + cp + 8 * g, r8, lo, p.res_mode);
+              *reinterpret_cast<uint4*>(og) = epi8<ACT, RES>(v + 8 * g, bias + cp + 8 * g, r8);
             }
           }
         } else {
@@ -686,6 +723,16 @@ struct octseg_conv_plan {
 };
 
 using namespace octseg;
+
+// epilogue specialisations: [activation none|relu|swish][residual none|before|after]
+typedef void (*ConvKernelFn)(const ConvKParams);
+static const ConvKernelFn kConvKernels[3][3] = {
+    {conv_tc_kernel<OCTSEG_ACT_NONE, OCTSEG_RES_NONE>, conv_tc_kernel<OCTSEG_ACT_NONE, OCTSEG_RES_BEFORE_ACT>,
+     conv_tc_kernel<OCTSEG_ACT_NONE, OCTSEG_RES_AFTER_ACT>},
+    {conv_tc_kernel<OCTSEG_ACT_RELU, OCTSEG_RES_NONE>, conv_tc_kernel<OCTSEG_ACT_RELU, OCTSEG_RES_BEFORE_ACT>,
+     conv_tc_kernel<OCTSEG_ACT_RELU, OCTSEG_RES_AFTER_ACT>},
+    {conv_tc_kernel<OCTSEG_ACT_SWISH, OCTSEG_RES_NONE>, conv_tc_kernel<OCTSEG_ACT_SWISH, OCTSEG_RES_BEFORE_ACT>,
+     conv_tc_kernel<OCTSEG_ACT_SWISH, OCTSEG_RES_AFTER_ACT>}};
 
 extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_plan** out_plan) {
   if (!d || !out_plan) return fail(OCTSEG_EINVAL, "null argument");
@@ -818,6 +865,23 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     return fail(OCTSEG_EINVAL, "d2s output needs bf16 NHWC, one phase, no residual and d2s %% 8 == 0");
   }
   kp.total_tiles = d->phases * d->N * kp.tiles_h * kp.tiles_w * d->n_tiles_n;
+  kp.fd_ntn = make_fastdiv(static_cast<uint32_t>(d->n_tiles_n));
+  kp.fd_phases = make_fastdiv(static_cast<uint32_t>(d->phases));
+  kp.fd_tw = make_fastdiv(static_cast<uint32_t>(kp.tiles_w));
+  kp.fd_th = make_fastdiv(static_cast<uint32_t>(kp.tiles_h));
+  kp.fd_TW = make_fastdiv(static_cast<uint32_t>(d->TW));
+  {
+    const long long lim = 1ll << 32;
+    const long long t = kp.total_tiles;
+    if (t * d->n_tiles_n >= lim || t * kp.tiles_w >= lim || t * kp.tiles_h >= lim) {
+      delete pl;
+      return fail(OCTSEG_EINVAL, "too many tiles (%lld) for the 32-bit tile decoder", t);
+    }
+  }
+  if (d->act == OCTSEG_ACT_SIGMOID && d->out_mode == OCTSEG_OUT_BF16_NHWC) {
+    delete pl;
+    return fail(OCTSEG_EINVAL, "sigmoid is only available with the NCHW head outputs");
+  }
 
   kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC && d->cout_per_tile >= 64 && d->d2s == 0 &&
                       (d->phases == 1 || (d->Hq % d->TH == 0 && d->out_H == 2 * d->Hq && d->out_W == 2 * d->Wq)))
@@ -869,11 +933,14 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      delete pl;
-      return fail(OCTSEG_ECUDA, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
-    }
+    for (int a = 0; a < 3; ++a)
+      for (int r = 0; r < 3; ++r) {
+        cudaError_t e = cudaFuncSetAttribute(kConvKernels[a][r], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+          delete pl;
+          return fail(OCTSEG_ECUDA, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
+        }
+      }
     attr_set = true;
   }
   *out_plan = pl;
@@ -888,6 +955,8 @@ extern "C" int octseg_conv_plan_destroy(octseg_conv_plan* plan) {
 extern "C" int octseg_conv_run(const octseg_conv_plan* plan, void* stream) {
   if (!plan) return fail(OCTSEG_EINVAL, "null plan");
   if (plan->kp.total_tiles <= 0) return OCTSEG_OK;
-  conv_tc_kernel<<<plan->grid, kThreads, plan->smem, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  // sigmoid exists only on the NCHW head paths, which read p.act at run time
+  const int a = plan->kp.act == OCTSEG_ACT_RELU ? 1 : (plan->kp.act == OCTSEG_ACT_SWISH ? 2 : 0);
+  kConvKernels[a][plan->kp.res_mode]<<<plan->grid, kThreads, plan->smem, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   return check_launch("conv_tc_kernel");
 }
