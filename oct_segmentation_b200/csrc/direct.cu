@@ -1,6 +1,6 @@
 // CUDA-core kernels for the layers that are HBM-bound or have a tiny contraction:
-// network stems (Cin = 3), max-pool, depthwise conv (+ squeeze-excite pooling), SE gate,
-// per-image SE-scaled projection weights.  Activations are NHWC bf16, 8 channels (16 bytes)
+// network stems (Cin = 3), max-pool, SE gate, per-image SE-scaled projection weights
+// (the depthwise conv lives in dwconv.cu).  Activations are NHWC bf16, 8 channels (16 bytes)
 // per thread access.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -166,172 +166,6 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
   }
 }
 
-// ------------------------------------------------------------------------------------ depthwise
-// HBM-bound by nature, instruction-bound in practice, so the inner loop is kept lean:
-//   * work item = 8 channels (16 B) x 4 consecutive output pixels of one row; a thread keeps ONE
-//     channel group for its whole life (bias, SE sums in registers) and strides over pixel groups,
-//     consecutive threads take consecutive 16-byte chunks (coalesced whatever C is);
-//   * the fp32 filter bank of the block's <= 32 channel groups sits in shared memory;
-//   * all input vectors of a filter row are loaded before any is used (one exposed latency per row);
-//   * math is packed fp32x2 (fma.rn.f32x2, sm_100): half the FMA issue slots.
-// Squeeze-excite sums leave the block as one global atomic per channel.
-constexpr int kDwP = 4;          // output pixels per item
-constexpr int kDwCgChunk = 32;   // channel groups per block column (256 channels)
-
-// 8 bf16 (uint4) -> four fp32x2 pairs
-__device__ __forceinline__ void bf16x8_to_f32x2(const uint4& v, float2 (&f)[4]) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
-}
-
-template <int K, int S, bool CHECK>
-__device__ __forceinline__ void dw_rows(float2 (&acc)[kDwP][4], const uint4* __restrict__ in4,
-                                        const float* __restrict__ wsm_cg, int C8, int W, int H, int ix0, int iy0) {
-  constexpr int WIN = (kDwP - 1) * S + K;
-#pragma unroll(K == 3 ? 3 : 1)
-  for (int ky = 0; ky < K; ++ky) {
-    const int iy = iy0 + ky;
-    if (CHECK && (iy < 0 || iy >= H)) continue;
-    const uint4* row = in4 + static_cast<size_t>(iy) * W * C8;
-    uint4 v[WIN];
-#pragma unroll
-    for (int dx = 0; dx < WIN; ++dx) {
-      const int ix = ix0 + dx;
-      v[dx] = (!CHECK || (ix >= 0 && ix < W)) ? __ldg(row + static_cast<size_t>(ix) * C8) : make_uint4(0, 0, 0, 0);
-    }
-    float2 wr[K][4];
-#pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      const float4 w0 = *reinterpret_cast<const float4*>(wsm_cg + (ky * K + kx) * (kDwCgChunk * 8));
-      const float4 w1 = *reinterpret_cast<const float4*>(wsm_cg + (ky * K + kx) * (kDwCgChunk * 8) + 4);
-      wr[kx][0] = make_float2(w0.x, w0.y);
-      wr[kx][1] = make_float2(w0.z, w0.w);
-      wr[kx][2] = make_float2(w1.x, w1.y);
-      wr[kx][3] = make_float2(w1.z, w1.w);
-    }
-#pragma unroll
-    for (int dx = 0; dx < WIN; ++dx) {
-      float2 f[4];
-      bf16x8_to_f32x2(v[dx], f);
-#pragma unroll
-      for (int p = 0; p < kDwP; ++p) {
-        const int kx = dx - p * S;  // compile-time after unrolling
-        if (kx >= 0 && kx < K) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[p][e] = __ffma2_rn(f[e], wr[kx][e], acc[p][e]);
-        }
-      }
-    }
-  }
-}
-
-template <int K, int S>
-__global__ void __launch_bounds__(256, 2) dwconv_kernel(const __nv_bfloat16* __restrict__ in,
-                                                        const __nv_bfloat16* __restrict__ weight,  // [K*K][C] bf16
-                                                        const float* __restrict__ bias,
-                                                        __nv_bfloat16* __restrict__ out, int H, int W, int C, int pad_t,
-                                                        int pad_l, int Ho, int Wo, int pg_per_block, int act,
-                                                        float* __restrict__ pool_sum) {
-  __shared__ __align__(16) float wsm[K * K][kDwCgChunk * 8];
-  __shared__ float sums[8][kDwCgChunk];  // [e][channel group]: conflict-free for consecutive groups
-  const int C8 = C >> 3;
-  const int cg0 = blockIdx.x * kDwCgChunk;
-  const int cgc = min(kDwCgChunk, C8 - cg0);
-  const int n = blockIdx.z;
-  const int wg = (Wo + kDwP - 1) / kDwP;  // pixel groups per output row
-  const int npg = Ho * wg;
-  const int pg0 = blockIdx.y * pg_per_block;
-  const int pgc = min(pg_per_block, npg - pg0);
-  for (int i = threadIdx.x; i < K * K * kDwCgChunk * 8; i += 256) {
-    const int tap = i / (kDwCgChunk * 8), cl = i - tap * (kDwCgChunk * 8);
-    const int c = cg0 * 8 + cl;
-    (&wsm[0][0])[i] = c < C ? __bfloat162float(weight[static_cast<size_t>(tap) * C + c]) : 0.f;
-  }
-  if (pool_sum)
-    for (int i = threadIdx.x; i < 8 * kDwCgChunk; i += 256) (&sums[0][0])[i] = 0.f;
-  __syncthreads();
-  // thread -> fixed channel group, strided over pixel groups
-  const int lanes_pg = 256 / cgc;
-  const int cgl = threadIdx.x % cgc;
-  const int pgl0 = threadIdx.x / cgc;
-  const bool active = pgl0 < lanes_pg;
-  const int cg = cg0 + cgl;
-  const uint4* in4 = reinterpret_cast<const uint4*>(in) + static_cast<size_t>(n) * H * W * C8 + cg;
-  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(n) * Ho * Wo * C8 + cg;
-  const float* wsm_cg = &wsm[0][0] + cgl * 8;
-  constexpr int WIN = (kDwP - 1) * S + K;
-  float2 bs[4];
-  float ps[8];
-#pragma unroll
-  for (int e = 0; e < 4; ++e)
-    bs[e] = active ? make_float2(__ldg(bias + cg * 8 + 2 * e), __ldg(bias + cg * 8 + 2 * e + 1)) : make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) ps[e] = 0.f;
-  if (active) {
-    for (int pgl = pgl0; pgl < pgc; pgl += lanes_pg) {
-      const int pg = pg0 + pgl;
-      const int oy = pg / wg;
-      const int ox0 = (pg - oy * wg) * kDwP;
-      float2 acc[kDwP][4];
-#pragma unroll
-      for (int p = 0; p < kDwP; ++p)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[p][e] = bs[e];
-      const int ix0 = ox0 * S - pad_l;
-      const int iy0 = oy * S - pad_t;
-      const bool interior = ix0 >= 0 && ix0 + WIN <= W && iy0 >= 0 && iy0 + K <= H;
-      if (interior)
-        dw_rows<K, S, false>(acc, in4, wsm_cg, C8, W, H, ix0, iy0);
-      else
-        dw_rows<K, S, true>(acc, in4, wsm_cg, C8, W, H, ix0, iy0);
-#pragma unroll
-      for (int p = 0; p < kDwP; ++p) {
-        if (ox0 + p < Wo) {
-          float y[8];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            y[2 * e] = acc[p][e].x;
-            y[2 * e + 1] = acc[p][e].y;
-          }
-          if (act == OCTSEG_ACT_SWISH) {  // uniform branch: only one activation's code runs
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float h = 0.5f * y[e];
-              float t;
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-              y[e] = fmaf(h, t, h);
-            }
-          } else if (act == OCTSEG_ACT_RELU) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
-          } else if (act != OCTSEG_ACT_NONE) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = act_f(y[e], act);
-          }
-          const uint4 o = pack8(y);
-          out4[(static_cast<size_t>(oy) * Wo + ox0 + p) * C8] = o;
-          if (pool_sum) {  // pool what the next layer actually reads (the bf16-rounded activation)
-            float r[8];
-            unpack8(o, r);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ps[e] += r[e];
-          }
-        }
-      }
-    }
-    if (pool_sum) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&sums[e][cgl], ps[e]);
-    }
-  }
-  if (pool_sum) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < cgc * 8; i += 256)
-      atomicAdd(pool_sum + static_cast<size_t>(n) * C + cg0 * 8 + i, sums[i & 7][i >> 3]);
-  }
-}
-
 // ------------------------------------------------------------------------------------ SE gate
 // hidden[n][r] = swish(W1[r,:] . mean[n,:] + b1[r]); one warp per (image, hidden unit)
 __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict__ pool_sum, float inv_hw,
@@ -450,32 +284,6 @@ extern "C" int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t
   maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), N, H, W, C / 8, Ho, Wo);
   return check_launch("maxpool3x3s2_kernel");
-}
-
-extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bias, void* out, int32_t N, int32_t H,
-                             int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l,
-                             int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, void* stream) {
-  if (C % 8) return fail(OCTSEG_EINVAL, "dwconv: C must be a multiple of 8 (C=%d)", C);
-  const int C8 = C / 8;
-  const int npg = Ho * cdiv(Wo, kDwP);
-  const int cols = cdiv(C8, kDwCgChunk);
-  // enough blocks for >= 8 per SM on small feature maps, long strips on large ones
-  int pgb = 64;
-  while (pgb > 8 && static_cast<long long>(cols) * cdiv(npg, pgb) * N < 148 * 8) pgb >>= 1;
-  dim3 grid(cols, cdiv(npg, pgb), N);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const __nv_bfloat16* i = static_cast<const __nv_bfloat16*>(in);
-  const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(weight);
-  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-#define OCTSEG_DW(KK, SS) \
-  dwconv_kernel<KK, SS><<<grid, 256, 0, st>>>(i, w, bias, o, H, W, C, pad_t, pad_l, Ho, Wo, pgb, act, pool_sum)
-  if (k == 3 && stride == 1) OCTSEG_DW(3, 1);
-  else if (k == 3 && stride == 2) OCTSEG_DW(3, 2);
-  else if (k == 5 && stride == 1) OCTSEG_DW(5, 1);
-  else if (k == 5 && stride == 2) OCTSEG_DW(5, 2);
-  else return fail(OCTSEG_EINVAL, "dwconv: unsupported kernel %d / stride %d", k, stride);
-#undef OCTSEG_DW
-  return check_launch("dwconv_kernel");
 }
 
 extern "C" int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1, const float* b1, float* hidden,
