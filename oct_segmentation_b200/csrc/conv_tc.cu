@@ -58,6 +58,7 @@ struct __align__(64) ConvKParams {
   int per_image_weights, act, res_mode, out_mode;
   int k_iters, nstages, total_tiles;
   int use_tma_store;
+  int bias_floats;    // n_tiles_n * BN + 64 bias values staged in shared memory (rounded up to 4)
   int b_stage_bytes;  // bytes of one B stage (kw weight tiles for wide segments)
   int a_stage_bytes;  // kABytes or kABytesWide
   const float* bias;
@@ -170,8 +171,8 @@ __device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t w) {
 
 template <int ACT, int RES>
 __device__ __forceinline__ uint4 epi8(const uint32_t* v, const float* bias8, const __nv_bfloat16* r8) {
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias8));
-  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias8 + 4));
+  const float4 b0 = *reinterpret_cast<const float4*>(bias8);  // shared memory (staged once per CTA)
+  const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
   float2 x[4];
   x[0] = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
   x[1] = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
@@ -248,7 +249,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t a_bytes = static_cast<uint32_t>(p.a_stage_bytes);
   const uint32_t smemB = smem0 + nst * a_bytes;
   const uint32_t smemOut = smemB + nst * b_bytes;        // 2 x 16 KB epilogue staging (TMA store source)
-  const uint32_t bars = smemOut + 2 * kOutBytes;         // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
+  const uint32_t smemBias = smemOut + 2 * kOutBytes;     // fp32 bias of every channel tile
+  const uint32_t bars = smemBias + p.bias_floats * 4;    // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
   const uint32_t bar_tfull = bars + 16 * kMaxStages, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
@@ -266,6 +268,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    float* bs = reinterpret_cast<float*>(smem_gen + (smemBias - smem0));
+    for (int i = threadIdx.x; i < p.bias_floats; i += kThreads) bs[i] = __ldg(p.bias + i);
   }
   if (p.TH * p.TW < 128) {
     // rows the TMA box never writes must still hold finite values for the MMA
@@ -480,10 +486,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int row = q * 32 + lane;
     const int th_l = static_cast<int>(fd_div(static_cast<uint32_t>(row), p.fd_TW)), tw_l = row - th_l * p.TW;
     const uint32_t sbuf = smemOut + group * kOutBytes;
-    // this thread's four 16-byte slots of its staging row (128B swizzle: 16-byte chunk index ^ (row & 7))
-    uint32_t sts_addr[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) sts_addr[g] = sbuf + row * 128 + (((half * 4 + g) ^ (row & 7)) << 4);
+    // this thread's staging row; its four 16-byte slots are chunk (half*4 + g) ^ (row & 7) (128B swizzle)
+    const uint32_t sts_row = sbuf + row * 128;
+    const uint32_t sts_x = static_cast<uint32_t>(((half * 4) ^ (row & 7)) << 4);
     int acc = 0;
     uint32_t acc_phase = 0, chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int ch0 = tc.n_tile * p.cout_per_tile;  // first real channel of this tile
       const int nvalid = min(p.cout_per_tile, p.Cout - ch0);
       const size_t pix = (static_cast<size_t>(tc.n) * p.out_H + oh) * p.out_W + ow;
-      const float* bias = p.bias + tc.n_tile * p.BN;
+      const float* bias = reinterpret_cast<const float*>(smem_gen + (smemBias - smem0)) + tc.n_tile * p.BN;
       const __nv_bfloat16* rrow = nullptr;
       if (RES != OCTSEG_RES_NONE && valid) rrow = p.res + pix * p.res_ldc + ch0;
 
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         group_bar_sync(group);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sts_addr[g]), "r"(ov[g].x), "r"(ov[g].y),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sts_row + (sts_x ^ (g << 4))), "r"(ov[g].x), "r"(ov[g].y),
                        "r"(ov[g].z), "r"(ov[g].w)
                        : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -579,7 +584,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int e = 0; e < kEpiPart; ++e) {
             if (cp + e < nvalid) {
-              const float y = apply_act(__uint_as_float(v[e]) + __ldg(bias + cp + e), p.act);
+              const float y = apply_act(__uint_as_float(v[e]) + bias[cp + e], p.act);
               const int c = p.out_c_off + ch0 + cp + e;
               const size_t idx = base + static_cast<size_t>(c % p.out_ldc) * plane + c / p.out_ldc;
               if (p.out_mode == OCTSEG_OUT_F32_NCHW)
@@ -816,7 +821,8 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   kp.b_stage_bytes = b_tiles * d->BN * 128;
   kp.a_stage_bytes = any_wide ? kABytesWide : kABytes;
   const int stage_bytes = kp.a_stage_bytes + kp.b_stage_bytes;
-  const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes;
+  kp.bias_floats = (d->n_tiles_n * d->BN + 64 + 3) & ~3;
+  const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes - kp.bias_floats * 4;
   int nst = budget / stage_bytes;
   if (nst > kMaxStages) nst = kMaxStages;
   if (nst < 2) {
@@ -824,7 +830,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     return fail(OCTSEG_EINVAL, "tile does not fit shared memory");
   }
   kp.nstages = nst;
-  pl->smem = static_cast<size_t>(nst) * stage_bytes + 2 * kOutBytes + 1024 + 512;
+  pl->smem = static_cast<size_t>(nst) * stage_bytes + 2 * kOutBytes + kp.bias_floats * 4 + 1024 + 512;
   int sms = octseg_sm_count();
   if (sms <= 0) {
     delete pl;

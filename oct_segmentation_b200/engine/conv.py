@@ -108,9 +108,18 @@ def choose_tile(Hq: int, Wq: int) -> Tuple[int, int]:
     return best
 
 
-def choose_bn(cout_p: int) -> Tuple[int, int]:
-    """(n_tiles_n, BN): BN multiple of 16, <= 256, tiles cover cout_p channels."""
+def choose_bn(cout_p: int, k_total: int = 1 << 30) -> Tuple[int, int]:
+    """(n_tiles_n, BN): BN multiple of 16, <= 256, tiles cover cout_p channels.
+
+    Output-bound layers (short K) get BN in whole 64-channel chunks: every chunk then leaves through the
+    TMA-store epilogue (a partial chunk is only allowed at the very end of the tensor, where TMA clips
+    it); the extra zero columns cost MMA time that such layers have to spare.  Long-K layers keep the
+    tightest BN."""
     n_tiles = -(-cout_p // 256)
+    if k_total <= 512 and cout_p > 64:
+        chunks = -(-cout_p // 64)
+        n_tiles = -(-chunks // 4)
+        return n_tiles, 64 * -(-chunks // n_tiles)
     bn = -(-cout_p // n_tiles)
     bn = (bn + 15) // 16 * 16
     return n_tiles, bn
@@ -178,7 +187,9 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
         assert cout_g % 8 == 0, 'grouped conv needs cout/groups % 8 == 0'
         n_tiles_n, BN, cout_per_tile = groups, (cout_g + 15) // 16 * 16, cout_g
     else:
-        n_tiles_n, BN = choose_bn(max(cout_w, 16))
+        k_est = sum((2 * 2 if (transposed or up) else (3 * 3 if phases == 4 else w.shape[2] * w.shape[3])) * sC
+                    for (_, _, _, sC, _), up in srcs)
+        n_tiles_n, BN = choose_bn(max(cout_w, 16), k_est)
         cout_per_tile = BN
     rows = n_tiles_n * BN
 
