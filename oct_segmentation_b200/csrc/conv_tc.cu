@@ -789,7 +789,9 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     return fail(OCTSEG_EINVAL, "sigmoid is only available with the NCHW head outputs");
   }
 
-  kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC && d->cout_per_tile >= 64 && d->d2s == 0 &&
+  // narrow single-tile outputs (Cout < 64) also leave through one TMA chunk: the box is 64 channels wide
+  // and TMA clips it at the tensor map's channel extent
+  kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC && (d->cout_per_tile >= 64 || d->n_tiles_n == 1) && d->d2s == 0 &&
                       (d->phases == 1 || (d->Hq % d->TH == 0 && d->out_H == 2 * d->Hq && d->out_W == 2 * d->Wq)))
                          ? 1
                          : 0;
