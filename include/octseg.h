@@ -120,19 +120,17 @@ int octseg_conv_run(const octseg_conv_plan* plan, void* stream);
  * CUDA-core kernels for the HBM-bound / tiny-K layers.
  * ------------------------------------------------------------------------------------------ */
 
-/* Network stem: dense kxk conv from the 3-channel network input (torch conv2d on
-   `images_tensor`, model.py:189-192) + folded BN + act -> bf16 NHWC.
+/* Network stem input (torch conv2d on `images_tensor`, model.py:189-192): space-to-depth packing of
+   the 3-channel network input for the tensor-core stem conv.  The stride-2 k x k stem conv becomes a
+   stride-1 conv (octseg_conv_*) over  out[n][y][x][(dy*2+dx)*3 + c] = norm(in[n][c][2y+dy][2x+dx]),
+   bf16 NHWC [N][H/2][W/2][16] (channels 12..15 zero).
    Input is addressed by element strides so the NHWC-strided float tensor produced by
    `torch.Tensor(images.transpose(0,3,1,2))` (model.py:189) and uint8 NHWC frames are read in
    place.  in_dtype: 0 = f32, 1 = u8.  `mean`/`inv_std` (3 floats each, HOST pointers, may be
    NULL) apply OCTSegmentationModel.forward's normalisation (model.py:69) on the fly. */
-int octseg_stem_conv(const void* in, int32_t in_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
-                     int32_t N, int32_t H, int32_t W,
-                     const float* weight /* fp32 [kh][kw][3][Cout] */, const float* bias,
-                     int32_t Cout, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l,
-                     int32_t Ho, int32_t Wo, int32_t act,
-                     const float* h_mean, const float* h_inv_std,
-                     void* out /* bf16 NHWC [N][Ho][Wo][out_ldc] */, int32_t out_ldc, void* stream);
+int octseg_stem_pack(const void* in, int32_t in_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                     int32_t N, int32_t H, int32_t W, const float* h_mean, const float* h_inv_std,
+                     void* out /* bf16 NHWC [N][H/2][W/2][16] */, void* stream);
 
 /* torch max_pool2d(kernel 3, stride 2, padding 1) of torchvision ResNet (bf16 NHWC). */
 int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C,

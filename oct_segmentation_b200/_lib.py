@@ -21,7 +21,7 @@ OUT = {'bf16_nhwc': 0, 'f32_nchw': 1, 'u8_nchw': 2}
 EXPORTS = [
     'octseg_last_error', 'octseg_abi_version', 'octseg_sm_count',
     'octseg_conv_plan_create', 'octseg_conv_plan_destroy', 'octseg_conv_run',
-    'octseg_stem_conv', 'octseg_maxpool3x3s2', 'octseg_dwconv', 'octseg_se_hidden',
+    'octseg_stem_pack', 'octseg_maxpool3x3s2', 'octseg_dwconv', 'octseg_se_hidden',
     'octseg_se_scale_weights', 'octseg_preprocess_resize_bgr', 'octseg_postprocess',
     'octseg_radial_thickness',
 ]
@@ -72,10 +72,9 @@ def load() -> C.CDLL:
     lib.octseg_conv_plan_create.argtypes = [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]
     lib.octseg_conv_plan_destroy.argtypes = [C.c_void_p]
     lib.octseg_conv_run.argtypes = [C.c_void_p, C.c_void_p]
-    lib.octseg_stem_conv.argtypes = [
+    lib.octseg_stem_pack.argtypes = [
         C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-        C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-        C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_int32, C.c_void_p]
+        C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
     lib.octseg_maxpool3x3s2.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]
     lib.octseg_dwconv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 11 + [
         C.c_void_p, C.c_void_p]

@@ -1,5 +1,5 @@
 // CUDA-core kernels for the layers that are HBM-bound or have a tiny contraction:
-// network stems (Cin = 3), max-pool, SE gate, per-image SE-scaled projection weights
+// network-stem input packing, max-pool, SE gate, per-image SE-scaled projection weights
 // (the depthwise conv lives in dwconv.cu).  Activations are NHWC bf16, 8 channels (16 bytes)
 // per thread access.
 #include <cuda_bf16.h>
@@ -39,96 +39,52 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 
-// packed fp32x2 math (sm_100 FFMA2, __ffma2_rn): two FMAs per issue slot; float2 lets the compiler
-// keep the operands in aligned register pairs without extra moves
-// ------------------------------------------------------------------------------------ stem
-// One block = 16x16 output pixels; the input patch and the whole filter bank sit in shared
-// memory; each thread owns one pixel and CO output channels in registers.
-struct StemParams {
+// ------------------------------------------------------------------------------------ stem input
+// Network stems are stride-2 convs on the 3-channel input.  They run on the tensor cores as a
+// stride-1 conv over the space-to-depth form of the input: one launch of this kernel reads the frame
+// in place (uint8 NHWC or the NHWC-strided fp32 tensor of the reference's predict()), applies
+// OCTSegmentationModel.forward's normalisation, and writes bf16 [N][H/2][W/2][16] with channel
+// (dy*2 + dx)*3 + c = input pixel (2y+dy, 2x+dx), channel c; channels 12..15 are zero.  A 2x2 block of
+// pixels is 32 bytes = one TMA row of the kc=16 K-segment of conv_tc_kernel.
+struct StemPackParams {
   const void* in;
   int in_dtype;
   long long sn, sc, sh, sw;
-  int N, H, W;
-  const float* weight;
-  const float* bias;
-  int k, stride, pad_t, pad_l, Ho, Wo, act;
+  int N, H2, W2;
   float mean[3], inv_std[3];
-  int normalize;
-  __nv_bfloat16* out;
-  int out_ldc;
+  uint4* out;
 };
 
-template <int CO>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
-  extern __shared__ float smem[];
-  const int taps = p.k * p.k * 3;
-  float* wsm = smem;               // [taps][CO]
-  float* patch = smem + taps * CO; // [ph][pw][3]
-  const int pdim = 15 * p.stride + p.k;
-  const int n = blockIdx.z;
-  const int oy0 = blockIdx.y * 16, ox0 = blockIdx.x * 16;
-  const int iy0 = oy0 * p.stride - p.pad_t, ix0 = ox0 * p.stride - p.pad_l;
-
-  for (int i = threadIdx.x; i < taps * CO; i += 256) wsm[i] = p.weight[i];
-  for (int i = threadIdx.x; i < pdim * pdim * 3; i += 256) {
-    const int c = i % 3, x = (i / 3) % pdim, y = i / (3 * pdim);
-    const int iy = iy0 + y, ix = ix0 + x;
-    float v = 0.f;
-    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-      const long long off = n * p.sn + c * p.sc + iy * p.sh + ix * p.sw;
-      v = p.in_dtype == 0 ? reinterpret_cast<const float*>(p.in)[off]
-                          : static_cast<float>(reinterpret_cast<const uint8_t*>(p.in)[off]);
-      if (p.normalize) v = (v - p.mean[c]) * p.inv_std[c];
-    }
-    patch[i] = v;
-  }
-  __syncthreads();
-
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  float2 acc2[CO / 2];
+__global__ void __launch_bounds__(256) stem_pack_s2d_kernel(const StemPackParams p) {
+  const size_t total = static_cast<size_t>(p.N) * p.H2 * p.W2;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % p.W2);
+    size_t t = idx / p.W2;
+    const int y = static_cast<int>(t % p.H2);
+    const int n = static_cast<int>(t / p.H2);
+    float v[16];
 #pragma unroll
-  for (int c = 0; c < CO / 2; ++c) acc2[c] = make_float2(0.f, 0.f);
-  for (int ky = 0; ky < p.k; ++ky) {
-    for (int kx = 0; kx < p.k; ++kx) {
-      const float* pp = patch + ((ty * p.stride + ky) * pdim + tx * p.stride + kx) * 3;
-      const float* ww = wsm + (ky * p.k + kx) * 3 * CO;
+    for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v = pp[c];
-        const float2 vv = make_float2(v, v);
-        const float4* w4 = reinterpret_cast<const float4*>(ww + c * CO);
+      for (int dx = 0; dx < 2; ++dx)
 #pragma unroll
-        for (int g = 0; g < CO / 4; ++g) {
-          const float4 w = w4[g];
-          acc2[2 * g] = __ffma2_rn(vv, make_float2(w.x, w.y), acc2[2 * g]);
-          acc2[2 * g + 1] = __ffma2_rn(vv, make_float2(w.z, w.w), acc2[2 * g + 1]);
+        for (int c = 0; c < 3; ++c) {
+          const long long off = n * p.sn + c * p.sc + (2 * y + dy) * p.sh + (2 * x + dx) * p.sw;
+          const float raw = p.in_dtype == 0 ? reinterpret_cast<const float*>(p.in)[off]
+                                            : static_cast<float>(reinterpret_cast<const uint8_t*>(p.in)[off]);
+          v[(dy * 2 + dx) * 3 + c] = (raw - p.mean[c]) * p.inv_std[c];
         }
-      }
+#pragma unroll
+    for (int e = 12; e < 16; ++e) v[e] = 0.f;
+    float lo[8], hi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      lo[e] = v[e];
+      hi[e] = v[8 + e];
     }
-  }
-  float acc[CO];
-#pragma unroll
-  for (int c = 0; c < CO / 2; ++c) {
-    acc[2 * c] = acc2[c].x;
-    acc[2 * c + 1] = acc2[c].y;
-  }
-  if (oy < p.Ho && ox < p.Wo) {
-    __nv_bfloat16* o = p.out + ((static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox) * p.out_ldc;
-#pragma unroll
-    for (int g = 0; g < CO / 8; ++g) {
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = acc[g * 8 + e] + __ldg(p.bias + g * 8 + e);
-      if (p.act == OCTSEG_ACT_RELU) {  // uniform branch: only one activation's code runs
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-      } else if (p.act != OCTSEG_ACT_NONE) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = act_f(f[e], p.act);
-      }
-      *reinterpret_cast<uint4*>(o + g * 8) = pack8(f);
-    }
+    p.out[2 * idx] = pack8(lo);
+    p.out[2 * idx + 1] = pack8(hi);
   }
 }
 
@@ -226,15 +182,13 @@ static int grid_for(size_t total, int block) {
 
 using namespace octseg;
 
-extern "C" int octseg_stem_conv(const void* in, int32_t in_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
-                                int32_t N, int32_t H, int32_t W, const float* weight, const float* bias,
-                                int32_t Cout, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t Ho,
-                                int32_t Wo, int32_t act, const float* h_mean, const float* h_inv_std, void* out,
-                                int32_t out_ldc, void* stream) {
-  if (Cout != 32 && Cout != 64) return fail(OCTSEG_EINVAL, "stem conv supports Cout 32 or 64, got %d", Cout);
-  if (k > 7 || stride > 2 || out_ldc % 8) return fail(OCTSEG_EINVAL, "stem conv: k<=7, stride<=2, out_ldc%%8==0");
-  if (in_dtype != 0 && in_dtype != 1) return fail(OCTSEG_EINVAL, "stem conv: in_dtype must be 0 (f32) or 1 (u8)");
-  StemParams p;
+extern "C" int octseg_stem_pack(const void* in, int32_t in_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                                int32_t N, int32_t H, int32_t W, const float* h_mean, const float* h_inv_std, void* out,
+                                void* stream) {
+  if (in_dtype != 0 && in_dtype != 1) return fail(OCTSEG_EINVAL, "stem pack: in_dtype must be 0 (f32) or 1 (u8)");
+  if (H % 2 || W % 2 || H < 2 || W < 2) return fail(OCTSEG_EINVAL, "stem pack: H and W must be even (got %dx%d)", H, W);
+  if (reinterpret_cast<uintptr_t>(out) & 15) return fail(OCTSEG_EINVAL, "stem pack: out must be 16-byte aligned");
+  StemPackParams p;
   p.in = in;
   p.in_dtype = in_dtype;
   p.sn = sn;
@@ -242,39 +196,17 @@ extern "C" int octseg_stem_conv(const void* in, int32_t in_dtype, int64_t sn, in
   p.sh = sh;
   p.sw = sw;
   p.N = N;
-  p.H = H;
-  p.W = W;
-  p.weight = weight;
-  p.bias = bias;
-  p.k = k;
-  p.stride = stride;
-  p.pad_t = pad_t;
-  p.pad_l = pad_l;
-  p.Ho = Ho;
-  p.Wo = Wo;
-  p.act = act;
-  p.normalize = (h_mean && h_inv_std) ? 1 : 0;
+  p.H2 = H / 2;
+  p.W2 = W / 2;
+  const bool norm = h_mean && h_inv_std;
   for (int c = 0; c < 3; ++c) {
-    p.mean[c] = p.normalize ? h_mean[c] : 0.f;
-    p.inv_std[c] = p.normalize ? h_inv_std[c] : 1.f;
+    p.mean[c] = norm ? h_mean[c] : 0.f;
+    p.inv_std[c] = norm ? h_inv_std[c] : 1.f;
   }
-  p.out = static_cast<__nv_bfloat16*>(out);
-  p.out_ldc = out_ldc;
-  const int pdim = 15 * stride + k;
-  const size_t smem = (static_cast<size_t>(k) * k * 3 * Cout + static_cast<size_t>(pdim) * pdim * 3) * sizeof(float);
-  dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), N);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;  // once per process; not a stream operation, keep it out of graph capture
-  if (!attr_set) {
-    OCTSEG_CUDA(cudaFuncSetAttribute(stem_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    OCTSEG_CUDA(cudaFuncSetAttribute(stem_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
-  if (Cout == 64)
-    stem_conv_kernel<64><<<grid, 256, smem, st>>>(p);
-  else
-    stem_conv_kernel<32><<<grid, 256, smem, st>>>(p);
-  return check_launch("stem_conv_kernel");
+  p.out = static_cast<uint4*>(out);
+  const size_t total = static_cast<size_t>(N) * p.H2 * p.W2;
+  stem_pack_s2d_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("stem_pack_s2d_kernel");
 }
 
 extern "C" int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t Ho,

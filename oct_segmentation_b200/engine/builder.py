@@ -32,6 +32,23 @@ def fold_bn(w: torch.Tensor, bn: Optional[torch.nn.BatchNorm2d], conv_bias: Opti
     return w * scale.view(shape), (b - bn.running_mean.detach().float().cpu()) * scale + bn.bias.detach().float().cpu()
 
 
+def stem_s2d_weights(w: torch.Tensor, k: int, pad: Tuple[int, int]) -> Tuple[torch.Tensor, Tuple[int, int]]:
+    """Weights of the stride-1 conv on the 2x2 space-to-depth input that equals a stride-2 k x k conv with
+    top/left padding ``pad``: returns (w2 [Cout, 12, kq_h, kq_w], (q0_h, q0_w)) where q0 <= 0 is the first
+    tap offset (so the new conv pads -q0 at the top/left).  Input row 2*oy + ky - pad = 2*(oy + q) + d."""
+    w = w.detach().float().cpu()
+    cout = w.shape[0]
+    qs = [[((t - p) // 2, (t - p) % 2) for t in range(k)] for p in pad]          # per axis: tap -> (q, d)
+    q0 = tuple(min(q for q, _ in axis) for axis in qs)
+    kq = tuple(max(q for q, _ in axis) - q0[i] + 1 for i, axis in enumerate(qs))
+    w2 = torch.zeros(cout, 12, kq[0], kq[1])
+    for ky, (qy, dy) in enumerate(qs[0]):
+        for kx, (qx, dx) in enumerate(qs[1]):
+            c0 = (dy * 2 + dx) * 3
+            w2[:, c0:c0 + 3, qy - q0[0], qx - q0[1]] = w[:, :, ky, kx]
+    return w2, q0
+
+
 class Builder:
     def __init__(self, device: torch.device, N: int):
         self.lib = _lib.load()
@@ -156,25 +173,31 @@ class Builder:
     def stem(self, x: torch.Tensor, in_dtype: str, w: torch.Tensor, b: torch.Tensor, *, name: str, k: int,
              stride: int, pad: Tuple[int, int], out_hw: Tuple[int, int], act: str,
              mean: Optional[Sequence[float]] = None, std: Optional[Sequence[float]] = None) -> Act:
-        """x: logical (N,3,H,W) view of the static input buffer (any strides)."""
+        """Stride-2 k x k stem conv on the 3-channel input, as a tensor-core conv over the input's
+        space-to-depth form.  x: logical (N,3,H,W) view of the static input buffer (any strides).
+
+        in[2(oy+qy)+dy] with ky = 2qy + dy + pad: the k taps of a row fold into ceil-ish k/2 taps qy of the
+        2x2-packed tensor (12 channels, padded to 16); weights move to w2[co][(dy*2+dx)*3+c][qy-q0][qx-q0]."""
+        assert stride == 2 and x.shape[1] == 3
         N, _, H, W = x.shape
         cout = w.shape[0]
-        out = self.new_act(out_hw[0], out_hw[1], cout)
-        wk = w.detach().float().permute(2, 3, 1, 0).contiguous().to(self.device)   # [kh][kw][3][Cout]
-        bk = b.detach().float().contiguous().to(self.device)
+        x2 = self.new_act(H // 2, W // 2, 12)
         sn, sc, sh, sw = x.stride()
         mean_a = (C.c_float * 3)(*mean) if mean is not None else None
         istd_a = (C.c_float * 3)(*[1.0 / s for s in std]) if std is not None else None
-        self._keep += [wk, bk, x]
+        self._keep += [x]
         lib, dt = self.lib, {'f32': 0, 'u8': 1}[in_dtype]
-        a = _lib.ACT[act]
 
-        def op():
-            _lib.check(lib.octseg_stem_conv(x.data_ptr(), dt, sn, sc, sh, sw, N, H, W, wk.data_ptr(), bk.data_ptr(),
-                                            cout, k, stride, pad[0], pad[1], out_hw[0], out_hw[1], a, mean_a, istd_a,
-                                            out.t.data_ptr(), out.Cp, _lib.stream_ptr()), name)
-        self.macs += N * out_hw[0] * out_hw[1] * cout * 3 * k * k
-        self._add(name, op)
+        def pack_op():
+            _lib.check(lib.octseg_stem_pack(x.data_ptr(), dt, sn, sc, sh, sw, N, H, W, mean_a, istd_a,
+                                            x2.t.data_ptr(), _lib.stream_ptr()), name + '.pack')
+        self._add(name + '.pack', pack_op)
+        w2, q0 = stem_s2d_weights(w, k, pad)
+        assert q0[0] <= 0 and q0[1] <= 0
+        out = self.conv([(x2, False)], w2, b, name=name, pad=(-q0[0], -q0[1]), out_hw=out_hw, act=act)
+        real = N * out_hw[0] * out_hw[1] * cout * 3 * k * k        # algorithmic MACs: the dense count of the real op
+        self.macs += real - self.op_macs[-1]
+        self.op_macs[-1] = real
         return out
 
     def maxpool(self, x: Act, *, name: str) -> Act:

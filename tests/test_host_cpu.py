@@ -132,3 +132,25 @@ def test_gather_table_world_size_2_gloo(n_total):
         assert p.exitcode == 0
     want = np.arange(n_total, dtype=np.int32)[:, None] * np.array([[1, 10, 100, 1000]], dtype=np.int32)
     assert np.array_equal(table, want)           # frame order preserved across ranks == single-rank result
+
+
+@pytest.mark.parametrize('k,pad,H,W', [(7, (3, 3), 32, 64), (3, (1, 1), 32, 32), (3, (0, 0), 64, 32)])
+def test_stem_space_to_depth_weights_equal_the_stride2_conv(k, pad, H, W):
+    """engine.builder.stem_s2d_weights: the stride-1 conv on the 2x2 space-to-depth input (what the
+    tensor-core stem runs) equals the stride-2 k x k stem conv, incl. efficientnet's bottom/right-only padding."""
+    import torch.nn.functional as F
+    from oct_segmentation_b200.engine.builder import stem_s2d_weights
+    g = torch.Generator().manual_seed(k)
+    x = torch.randn(2, 3, H, W, generator=g)
+    w = torch.randn(8, 3, k, k, generator=g)
+    Ho, Wo = H // 2, W // 2
+    pb, pr = (Ho - 1) * 2 + k - H - pad[0], (Wo - 1) * 2 + k - W - pad[1]
+    want = F.conv2d(F.pad(x, (pad[1], max(pr, 0), pad[0], max(pb, 0))), w, stride=2)[:, :, :Ho, :Wo]
+    w2, q0 = stem_s2d_weights(w, k, pad)
+    # channel (dy*2+dx)*3 + c of the packed tensor = pixel (2y+dy, 2x+dx), channel c
+    x2 = x.view(2, 3, Ho, 2, Wo, 2).permute(0, 3, 5, 1, 2, 4).reshape(2, 12, Ho, Wo)
+    kq = w2.shape[2:]
+    xp = F.pad(x2, (-q0[1], kq[1] - 1 + q0[1], -q0[0], kq[0] - 1 + q0[0]))
+    got = F.conv2d(xp, w2)
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, atol=1e-4, rtol=1e-4)
