@@ -150,11 +150,15 @@ int octseg_dwconv(const void* in, const void* weight /* bf16 [kh][kw][C] */, con
 int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1 /* [Cr][C] */, const float* b1,
                      float* hidden, int32_t N, int32_t C, int32_t Cr, void* stream);
 
-/* gate[n][k] = sigmoid(w2[k,:] . hidden[n,:] + b2[k]);  out[n][row][k] = bf16(w[row][k] * gate[n][k])
-   for k < C and 0 for the K padding: per-image weights of the projection conv (B tensor map z = n). */
-int octseg_se_scale_weights(const float* hidden, const float* w2t /* fp32 [Cr][C] */, const float* b2,
-                            const float* w /* fp32 [rows][Ktot] */, void* out /* bf16 [N][rows][Ktot] */,
-                            int32_t N, int32_t rows, int32_t Ktot, int32_t C, int32_t Cr, void* stream);
+/* gate[n][k] = sigmoid(w2[k,:] . hidden[n,:] + b2[k])                               fp32 [N][C]      */
+int octseg_se_gate(const float* hidden, const float* w2t /* fp32 [Cr][C] */, const float* b2, float* gate,
+                   int32_t N, int32_t C, int32_t Cr, void* stream);
+
+/* out[n][row][k] = bf16(w[row][k] * gate[n][k]) for k < C and 0 for the K padding: per-image weights of the
+   projection conv (B tensor map z = n), i.e. `gate * x` folded into `_project_conv`. */
+int octseg_se_scale_weights(const float* gate, const float* w /* fp32 [rows][Ktot] */,
+                            void* out /* bf16 [N][rows][Ktot] */, int32_t N, int32_t rows, int32_t Ktot,
+                            int32_t C, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pre-processing: preprocessing_img (src/data/utils.py:159-166): RGB->BGR + cv2.resize

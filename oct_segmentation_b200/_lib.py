@@ -22,7 +22,7 @@ EXPORTS = [
     'octseg_last_error', 'octseg_abi_version', 'octseg_sm_count',
     'octseg_conv_plan_create', 'octseg_conv_plan_destroy', 'octseg_conv_run',
     'octseg_stem_pack', 'octseg_maxpool3x3s2', 'octseg_dwconv', 'octseg_se_hidden',
-    'octseg_se_scale_weights', 'octseg_preprocess_resize_bgr', 'octseg_postprocess',
+    'octseg_se_gate', 'octseg_se_scale_weights', 'octseg_preprocess_resize_bgr', 'octseg_postprocess',
     'octseg_radial_thickness',
 ]
 
@@ -80,8 +80,10 @@ def load() -> C.CDLL:
         C.c_void_p, C.c_void_p]
     lib.octseg_se_hidden.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_void_p]
-    lib.octseg_se_scale_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                            C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.octseg_se_gate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p]
+    lib.octseg_se_scale_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_void_p]
     lib.octseg_preprocess_resize_bgr.argtypes = [
         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]

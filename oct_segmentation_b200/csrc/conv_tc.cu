@@ -214,6 +214,16 @@ __device__ __forceinline__ uint4 epi8(const uint32_t* v, const float* bias8, con
   return ov;
 }
 
+#ifdef OCTSEG_TRACE
+// Debug build only (tools/trace_conv.py): per-tile clock64 stamps of CTA 0's pipeline roles.
+constexpr int kTraceTiles = 256, kTraceEvents = 16;
+__device__ unsigned long long g_trace[kTraceEvents][kTraceTiles];
+#define OCTSEG_STAMP(ev, it) \
+  do { if (blockIdx.x == 0 && (it) < kTraceTiles) g_trace[ev][it] = clock64(); } while (0)
+#else
+#define OCTSEG_STAMP(ev, it) do { } while (0)
+#endif
+
 struct TileCoord {
   int n_tile, tw, th, n, ph, pw, phase;
 };
@@ -302,7 +312,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      [[maybe_unused]] int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        OCTSEG_STAMP(0, it);  // producer starts issuing this tile
         const TileCoord tc = decode_tile(p, tile);
         const int brow = tc.n_tile * p.BN;
         const int bz = tc.phase + p.phases * (p.per_image_weights ? tc.n : 0);
@@ -344,10 +356,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int ty = 0; ty < sg.kh; ++ty) {
               for (int tx = 0; tx < sg.kw; ++tx) {
                 for (int cc = 0; cc < sg.cchunks; ++cc) {
+                  OCTSEG_STAMP(10, it);  // decode + segment setup done
                   mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                  OCTSEG_STAMP(11, it);  // stage free
                   mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub);
                   tma_load_4d(smemA + stage * a_bytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0 + tx, h0 + ty, tc.n);
                   tma_load_3d(smemB + stage * b_bytes, mb, bar_full + 8 * stage, kofs, brow, bz);
+                  OCTSEG_STAMP(12, it);  // loads issued
                   kofs += 64;
                   if (++stage == nst) {
                     stage = 0;
@@ -396,9 +411,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      [[maybe_unused]] int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        OCTSEG_STAMP(1, it);  // MMA warp ready for this tile
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
+        OCTSEG_STAMP(2, it);  // accumulator free
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.BN);
         uint32_t accum = 0;  // 0 only for the very first MMA of the tile
         for (int s = 0; s < p.nseg; ++s) {
@@ -432,8 +450,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           } else if (kc == 64) {
             // hot path: one 64-channel sub-block per stage, four back-to-back MMAs
             for (; nsub > 0; --nsub) {
+              OCTSEG_STAMP(13, it);
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
+              OCTSEG_STAMP(14, it);  // operands landed
               const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes) >> 4);
               const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes) >> 4);
               tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
@@ -442,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
               accum = 1;
               tc_commit(bar_empty + 8 * stage);
+              OCTSEG_STAMP(15, it);  // MMAs issued, stage committed
               if (++stage == nst) {
                 stage = 0;
                 phase ^= 1;
@@ -472,6 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
         tc_commit(bar_tfull + 8 * acc);
+        OCTSEG_STAMP(3, it);  // all MMAs of the tile issued + committed
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -491,7 +513,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t sts_x = static_cast<uint32_t>(((half * 4) ^ (row & 7)) << 4);
     int acc = 0;
     uint32_t acc_phase = 0, chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    [[maybe_unused]] int it = 0;
+    [[maybe_unused]] const bool tracer = (threadIdx.x == 64) || (threadIdx.x == 64 + 256);  // first thread of each group
+    [[maybe_unused]] const int tev = 4 + 3 * group;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if (tracer) OCTSEG_STAMP(tev, it);  // epilogue group ready for this tile
       const TileCoord tc = decode_tile(p, tile);
       const int i = tc.th * p.TH + th_l, j = tc.tw * p.TW + tw_l;
       const bool valid = (row < p.TH * p.TW) && (i < p.Hq) && (j < p.Wq);
@@ -506,6 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
+      if (tracer) OCTSEG_STAMP(tev + 1, it);  // accumulator full seen
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
 
       // 64-channel chunks: registers -> swizzled shared tile -> one TMA store per chunk.  A partial last
@@ -598,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __syncwarp();
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
+      if (tracer) OCTSEG_STAMP(tev + 2, it);  // accumulator released
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -860,6 +888,13 @@ extern "C" int octseg_conv_plan_destroy(octseg_conv_plan* plan) {
   delete plan;
   return OCTSEG_OK;
 }
+
+#ifdef OCTSEG_TRACE
+extern "C" int octseg_debug_trace(unsigned long long* h_out) {
+  OCTSEG_CUDA(cudaMemcpyFromSymbol(h_out, octseg::g_trace, sizeof(unsigned long long) * kTraceEvents * kTraceTiles));
+  return OCTSEG_OK;
+}
+#endif
 
 extern "C" int octseg_conv_run(const octseg_conv_plan* plan, void* stream) {
   if (!plan) return fail(OCTSEG_EINVAL, "null plan");

@@ -123,53 +123,110 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 }
 
 // ------------------------------------------------------------------------------------ SE gate
-// hidden[n][r] = swish(W1[r,:] . mean[n,:] + b1[r]); one warp per (image, hidden unit)
+// Squeeze-excite of one MBConv block = two tiny dense layers on the pooled activation + a per-image
+// rescale of the projection weights.  All three steps are latency-bound, so each kernel is laid out for
+// many independent loads in flight rather than for FLOPs.
+//
+// hidden[n][r] = swish(W1[r,:] . mean[n,:] + b1[r]): one block per hidden unit r computes it for ALL images,
+// so W1's row is read once and every thread has up to 1 + N independent loads per step.
+constexpr int kSeMaxN = 16;  // images per pass of se_hidden_kernel
 __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict__ pool_sum, float inv_hw,
                                                         const float* __restrict__ w1, const float* __restrict__ b1,
-                                                        float* __restrict__ hidden, int C, int Cr) {
-  const int n = blockIdx.y;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= Cr) return;
-  const float* m = pool_sum + static_cast<size_t>(n) * C;
+                                                        float* __restrict__ hidden, int n0, int nn, int C, int Cr) {
+  __shared__ float part[8][kSeMaxN];
+  const int r = blockIdx.x;
   const float* w = w1 + static_cast<size_t>(r) * C;
-  float s = 0.f;
-  for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w + c), __ldg(m + c), s);
+  const float* m = pool_sum + static_cast<size_t>(n0) * C;
+  float s[kSeMaxN];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int n = 0; n < kSeMaxN; ++n) s[n] = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float wv = __ldg(w + c);
+#pragma unroll
+    for (int n = 0; n < kSeMaxN; ++n)
+      if (n < nn) s[n] = fmaf(wv, __ldg(m + static_cast<size_t>(n) * C + c), s[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < kSeMaxN; ++n) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[n] += __shfl_xor_sync(0xffffffffu, s[n], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) {
-    s = s * inv_hw + b1[r];
-    hidden[static_cast<size_t>(n) * Cr + r] = s / (1.f + __expf(-s));
+#pragma unroll
+    for (int n = 0; n < kSeMaxN; ++n) part[warp][n] = s[n];
+  }
+  __syncthreads();
+  if (threadIdx.x < nn) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += part[w8][threadIdx.x];
+    t = t * inv_hw + b1[r];
+    hidden[static_cast<size_t>(n0 + threadIdx.x) * Cr + r] = t / (1.f + __expf(-t));
   }
 }
 
-// gate[n][k] = sigmoid(W2[k,:] . hidden[n,:] + b2[k]) for this block's 256 input channels k, then
-// out[n][row][k] = bf16(w[row][k] * gate[n][k]) for every weight row (0 for the K padding).
-__global__ void __launch_bounds__(256) se_scale_weights_kernel(const float* __restrict__ hidden,
-                                                               const float* __restrict__ w2t,  // [Cr][C]
-                                                               const float* __restrict__ b2,
-                                                               const float* __restrict__ w,    // [rows][Ktot]
-                                                               __nv_bfloat16* __restrict__ out, int rows, int Ktot,
-                                                               int C, int Cr) {
-  extern __shared__ float hid[];
+// gate[n][k] = sigmoid(W2[k,:] . hidden[n,:] + b2[k]): 64 channels x 4 slices of the hidden units per block
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ hidden,
+                                                      const float* __restrict__ w2t,  // [Cr][C]
+                                                      const float* __restrict__ b2, float* __restrict__ gate, int C,
+                                                      int Cr) {
+  extern __shared__ float se_smem[];  // hid[Cr], then part[4][64]
+  float* hid = se_smem;
+  float* part = se_smem + Cr;
   const int n = blockIdx.y;
-  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int kl = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int k = blockIdx.x * 64 + kl;
   for (int r = threadIdx.x; r < Cr; r += 256) hid[r] = hidden[static_cast<size_t>(n) * Cr + r];
   __syncthreads();
-  if (k >= Ktot) return;
-  float g = 0.f;
+  float s = 0.f;
   if (k < C) {
-    float s = b2[k];
-    for (int r = 0; r < Cr; ++r) s = fmaf(__ldg(w2t + static_cast<size_t>(r) * C + k), hid[r], s);
-    g = 1.f / (1.f + __expf(-s));
+#pragma unroll 8
+    for (int r = slice; r < Cr; r += 4) s = fmaf(__ldg(w2t + static_cast<size_t>(r) * C + k), hid[r], s);
   }
-  __nv_bfloat16* o = out + static_cast<size_t>(n) * rows * Ktot + k;
-  const float* wk = w + k;
-  const int per = (rows + gridDim.z - 1) / gridDim.z;  // rows are split over blockIdx.z for parallelism
-  const int r0 = blockIdx.z * per, r1 = min(rows, r0 + per);
-#pragma unroll 4
-  for (int row = r0; row < r1; ++row)
-    o[static_cast<size_t>(row) * Ktot] = __float2bfloat16_rn(__ldg(wk + static_cast<size_t>(row) * Ktot) * g);
+  part[slice * 64 + kl] = s;
+  __syncthreads();
+  if (slice == 0 && k < C) {
+    const float t = part[kl] + part[64 + kl] + part[128 + kl] + part[192 + kl] + b2[k];
+    gate[static_cast<size_t>(n) * C + k] = 1.f / (1.f + __expf(-t));
+  }
+}
+
+// out[n][row][k..k+7] = bf16(w[row][k..k+7] * gate[n][k..k+7]) (0 for the K padding k >= C): the per-image
+// weights of the projection conv.  Work item = 8 channels of one weight row of one image (32-byte fp32
+// read, 16-byte bf16 write), items flattened so consecutive threads write consecutive 16-byte pieces.
+__global__ void __launch_bounds__(256) se_scale_weights_kernel(const float* __restrict__ gate,
+                                                               const float* __restrict__ w,  // [rows][Ktot]
+                                                               __nv_bfloat16* __restrict__ out, int N, int rows,
+                                                               int Ktot, int C) {
+  const int k8n = Ktot >> 3;
+  const size_t per_image = static_cast<size_t>(rows) * k8n;
+  const size_t total = per_image * N;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx / per_image);
+    const size_t rem = idx - static_cast<size_t>(n) * per_image;  // row * k8n + k8
+    const int k = static_cast<int>(rem % k8n) * 8;
+    float f[8];
+    if (k < C) {  // C and Ktot are multiples of 8: a group is entirely real or entirely padding
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(w + rem * 8));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(w + rem * 8 + 4));
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * C + k));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * C + k + 4));
+      f[0] = a0.x * g0.x;
+      f[1] = a0.y * g0.y;
+      f[2] = a0.z * g0.z;
+      f[3] = a0.w * g0.w;
+      f[4] = a1.x * g1.x;
+      f[5] = a1.y * g1.y;
+      f[6] = a1.z * g1.z;
+      f[7] = a1.w * g1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = 0.f;
+    }
+    reinterpret_cast<uint4*>(out)[idx] = pack8(f);
+  }
 }
 
 static int grid_for(size_t total, int block) {
@@ -220,18 +277,30 @@ extern "C" int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t
 
 extern "C" int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1, const float* b1, float* hidden,
                                 int32_t N, int32_t C, int32_t Cr, void* stream) {
-  dim3 grid(cdiv(Cr, 8), N);
-  se_hidden_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pool_sum, inv_hw, w1, b1, hidden, C, Cr);
+  for (int n0 = 0; n0 < N; n0 += kSeMaxN) {
+    const int nn = N - n0 < kSeMaxN ? N - n0 : kSeMaxN;
+    se_hidden_kernel<<<Cr, 256, 0, static_cast<cudaStream_t>(stream)>>>(pool_sum, inv_hw, w1, b1, hidden, n0, nn, C, Cr);
+  }
   return check_launch("se_hidden_kernel");
 }
 
-extern "C" int octseg_se_scale_weights(const float* hidden, const float* w2t, const float* b2, const float* w, void* out,
-                                       int32_t N, int32_t rows, int32_t Ktot, int32_t C, int32_t Cr, void* stream) {
-  if (Cr > 4096) return fail(OCTSEG_EINVAL, "se_scale_weights: Cr too large");
-  int zc = 1;  // enough blocks to fill the machine (the gate is recomputed per row chunk, it is tiny)
-  while (zc < 16 && cdiv(Ktot, 256) * N * zc < 148 * 4 && rows / (zc * 2) >= 8) zc *= 2;
-  dim3 grid(cdiv(Ktot, 256), N, zc);
-  se_scale_weights_kernel<<<grid, 256, static_cast<size_t>(Cr) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      hidden, w2t, b2, w, static_cast<__nv_bfloat16*>(out), rows, Ktot, C, Cr);
+extern "C" int octseg_se_gate(const float* hidden, const float* w2t, const float* b2, float* gate, int32_t N, int32_t C,
+                              int32_t Cr, void* stream) {
+  if (Cr > 8192) return fail(OCTSEG_EINVAL, "se_gate: Cr too large");
+  dim3 grid(cdiv(C, 64), N);
+  se_gate_kernel<<<grid, 256, (static_cast<size_t>(Cr) + 256) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      hidden, w2t, b2, gate, C, Cr);
+  return check_launch("se_gate_kernel");
+}
+
+extern "C" int octseg_se_scale_weights(const float* gate, const float* w, void* out, int32_t N, int32_t rows,
+                                       int32_t Ktot, int32_t C, void* stream) {
+  if (Ktot % 8 || C % 8 || C > Ktot) return fail(OCTSEG_EINVAL, "se_scale_weights: C and Ktot must be multiples of 8, C <= Ktot");
+  if ((reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(gate) & 15))
+    return fail(OCTSEG_EINVAL, "se_scale_weights: pointers must be 16-byte aligned");
+  const size_t total = static_cast<size_t>(N) * rows * (Ktot / 8);
+  se_scale_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      gate, w, static_cast<__nv_bfloat16*>(out), N, rows, Ktot, C);
   return check_launch("se_scale_weights_kernel");
 }

@@ -241,6 +241,7 @@ class Builder:
         w2d = w2.detach().float().reshape(C_mid, cr).t().contiguous().to(dev)      # [Cr][C]
         b2d = b2.detach().float().contiguous().to(dev)
         hidden = torch.empty(N, cr, dtype=torch.float32, device=dev)
+        gate = torch.empty(N, C_mid, dtype=torch.float32, device=dev)
         spec = [((N, x.H, x.W, x.C, x.Cp), False)]
         geom, packed32 = plan_conv(spec, wp, out_hw=(x.H, x.W), packed_dtype=torch.float32)
         rows, Ktot = packed32.shape[1], packed32.shape[2]
@@ -251,18 +252,20 @@ class Builder:
         plan = ConvPlan(geom, wn, pad_bias(bp, geom, cout), [x.t], out.t, act='none',
                         res=res.t if res is not None else None, res_mode='before_act' if res is not None else 'none',
                         per_image_weights=True, name=name)
-        self._keep += [plan, w1d, b1d, w2d, b2d, hidden, base, wn]
+        self._keep += [plan, w1d, b1d, w2d, b2d, hidden, gate, base, wn]
         lib, inv_hw = self.lib, 1.0 / float(x.H * x.W)
 
         def gate_op():
             st = _lib.stream_ptr()
             _lib.check(lib.octseg_se_hidden(pool.data_ptr(), inv_hw, w1d.data_ptr(), b1d.data_ptr(), hidden.data_ptr(),
                                             N, C_mid, cr, st), name + '.se_hidden')
-            _lib.check(lib.octseg_se_scale_weights(hidden.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), base.data_ptr(),
-                                                   wn.data_ptr(), N, rows, Ktot, C_mid, cr, st), name + '.se_scale_weights')
+            _lib.check(lib.octseg_se_gate(hidden.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gate.data_ptr(), N, C_mid,
+                                          cr, st), name + '.se_gate')
+            _lib.check(lib.octseg_se_scale_weights(gate.data_ptr(), base.data_ptr(), wn.data_ptr(), N, rows, Ktot,
+                                                   C_mid, st), name + '.se_scale_weights')
         self.macs += geom.macs + N * 2 * C_mid * cr
         self.tc_launches += 1
         self._add(name + '.se', gate_op)
-        self.launches += 1                      # gate_op is two launches
+        self.launches += 2                      # gate_op is three launches
         self._add(name, plan.run, tc_macs=geom.macs)
         return out

@@ -1,0 +1,66 @@
+"""Per-tile pipeline timeline of conv_tc_kernel (CTA 0), from a -DOCTSEG_TRACE build of the library:
+  nvcc ... -DOCTSEG_TRACE -o tools/ab/liboctseg_trace.so   (see build_trace() below)
+Events per tile: 0 producer start | 1 MMA ready, 2 accumulator free, 3 MMAs committed |
+4/7 epilogue group 0/1 ready, 5/8 accumulator-full seen, 6/9 accumulator released."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+TRACE_LIB = os.path.join(ROOT, 'tools', 'ab', 'liboctseg_trace.so')
+
+
+def build_trace():
+    import __graft_entry__ as g
+    srcs = [os.path.join(g.CSRC, s) for s in g.SOURCES]
+    subprocess.run([os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')] + g.NVCC_FLAGS + ['-DOCTSEG_TRACE', '-o', TRACE_LIB] + srcs,
+                   check=True)
+
+
+if __name__ == '__main__':
+    if sys.argv[1:] == ['build']:
+        build_trace()
+        sys.exit(0)
+    import numpy as np
+    import torch
+    from oct_segmentation_b200 import _lib
+    _lib.LIB_PATH = TRACE_LIB
+    from oct_segmentation_b200.engine import conv as CV
+    lib = _lib.load()
+    lib.octseg_debug_trace.argtypes = [C.c_void_p]
+    # (name, [(C,H,W)], cout, k, N, act, out_mode)
+    LAYERS = {
+        'head': ('linknet head 32->2 @896 (packed f=2)', [(64, 896, 448)], 4, 1, 16, 'none'),
+        'vvstem': ('regnet stem s2d 16->32 @448 2x2', [(16, 448, 448)], 32, 2, 16, 'relu'),
+        'expand': ('effnet expand 48->288 @224', [(48, 224, 224)], 288, 1, 16, 'swish'),
+        'proj': ('effnet project 32->32 @448', [(32, 448, 448)], 32, 1, 16, 'none'),
+        'c3': ('3x3 64->64 @256', [(64, 256, 256)], 64, 3, 32, 'relu'),
+    }
+    name, srcs, cout, k, n, act = LAYERS[sys.argv[1]]
+    spec = [((n, s[1], s[2], s[0], CV.pad8(s[0])), False) for s in srcs]
+    w = torch.randn(cout, sum(s[0] for s in srcs), k, k) * 0.05
+    geom, packed = CV.plan_conv(spec, w, pad=(k // 2, k // 2), out_hw=(srcs[0][1], srcs[0][2]))
+    bias = CV.pad_bias(torch.zeros(cout), geom, cout)
+    seg_t = [torch.randn(n, s[1], s[2], CV.pad8(s[0]), device='cuda').to(torch.bfloat16) for s in srcs]
+    out = torch.empty(n, geom.out_H, geom.out_W, geom.Cout, dtype=torch.bfloat16, device='cuda')
+    plan = CV.ConvPlan(geom, packed, bias, seg_t, out, act=act, name=name)
+    for _ in range(3):
+        plan.run()
+    torch.cuda.synchronize()
+    buf = np.zeros((16, 256), dtype=np.uint64)
+    _lib.check(lib.octseg_debug_trace(buf.ctypes.data), 'trace')
+    t = buf.astype(np.int64)
+    t0 = t[0, 0]
+    print(name, 'tile', (geom.TH, geom.TW), 'BN', geom.BN, 'ntn', geom.n_tiles_n, 'kc', [s.kc for s in geom.segs])
+    print('tile  prod  | mma_rdy acc_free commit | g0_rdy g0_full g0_rel | g1_rdy g1_full g1_rel')
+    for i in list(range(0, 12)) + list(range(100, 112)):
+        r = [int(t[e, i] - t0) for e in range(10)]
+        print(f'{i:4d} {r[0]:6d} | {r[1]:6d} {r[2]:6d} {r[3]:6d} | {r[4]:6d} {r[5]:6d} {r[6]:6d} | {r[7]:6d} {r[8]:6d} {r[9]:6d}')
+    print('tile  prod: start setup stage_free issued | mma: rdy acc_free k_wait landed issued commit')
+    for i in range(100, 108):
+        r = [int(t[e, i] - t0) for e in range(16)]
+        print(f'{i:4d} {r[0]:7d} {r[10]-r[0]:5d} {r[11]-r[10]:5d} {r[12]-r[11]:5d} | {r[1]:7d} {r[2]-r[1]:5d} {r[13]-r[2]:5d} {r[14]-r[13]:5d} {r[15]-r[14]:5d} {r[3]-r[15]:5d}')
+    d = np.diff(t[3, 50:200])
+    print('steady-state cycles per tile (MMA commit to commit):', float(d.mean()))
