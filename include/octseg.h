@@ -150,9 +150,11 @@ int octseg_dwconv(const void* in, const void* weight /* bf16 [kh][kw][C] */, con
 int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1 /* [Cr][C] */, const float* b1,
                      float* hidden, int32_t N, int32_t C, int32_t Cr, void* stream);
 
-/* gate[n][k] = sigmoid(w2[k,:] . hidden[n,:] + b2[k])                               fp32 [N][C]      */
+/* gate[n][k] = sigmoid(w2[k,:] . hidden[n,:] + b2[k])                               fp32 [N][C]
+   `pool_clear` (may be NULL): fp32 [N][C] buffer set to zero on the way -- the pool_sum that octseg_se_hidden
+   just consumed, so the next octseg_dwconv call finds it zeroed without a separate memset. */
 int octseg_se_gate(const float* hidden, const float* w2t /* fp32 [Cr][C] */, const float* b2, float* gate,
-                   int32_t N, int32_t C, int32_t Cr, void* stream);
+                   float* pool_clear, int32_t N, int32_t C, int32_t Cr, void* stream);
 
 /* out[n][row][k] = bf16(w[row][k] * gate[n][k]) for k < C and 0 for the K padding: per-image weights of the
    projection conv (B tensor map z = n), i.e. `gate * x` folded into `_project_conv`. */

@@ -129,12 +129,14 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 //
 // hidden[n][r] = swish(W1[r,:] . mean[n,:] + b1[r]): one block per hidden unit r computes it for ALL images,
 // so W1's row is read once and every thread has up to 1 + N independent loads per step.
-constexpr int kSeMaxN = 16;  // images per pass of se_hidden_kernel
+constexpr int kSeMaxN = 8;  // images per block of se_hidden_kernel (blockIdx.y = image group)
 __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict__ pool_sum, float inv_hw,
                                                         const float* __restrict__ w1, const float* __restrict__ b1,
-                                                        float* __restrict__ hidden, int n0, int nn, int C, int Cr) {
+                                                        float* __restrict__ hidden, int N, int C, int Cr) {
   __shared__ float part[8][kSeMaxN];
   const int r = blockIdx.x;
+  const int n0 = blockIdx.y * kSeMaxN;
+  const int nn = min(kSeMaxN, N - n0);
   const float* w = w1 + static_cast<size_t>(r) * C;
   const float* m = pool_sum + static_cast<size_t>(n0) * C;
   float s[kSeMaxN];
@@ -169,8 +171,8 @@ __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict_
 // gate[n][k] = sigmoid(W2[k,:] . hidden[n,:] + b2[k]): 64 channels x 4 slices of the hidden units per block
 __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ hidden,
                                                       const float* __restrict__ w2t,  // [Cr][C]
-                                                      const float* __restrict__ b2, float* __restrict__ gate, int C,
-                                                      int Cr) {
+                                                      const float* __restrict__ b2, float* __restrict__ gate,
+                                                      float* __restrict__ pool_clear, int C, int Cr) {
   extern __shared__ float se_smem[];  // hid[Cr], then part[4][64]
   float* hid = se_smem;
   float* part = se_smem + Cr;
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   if (slice == 0 && k < C) {
     const float t = part[kl] + part[64 + kl] + part[128 + kl] + part[192 + kl] + b2[k];
     gate[static_cast<size_t>(n) * C + k] = 1.f / (1.f + __expf(-t));
+    if (pool_clear) pool_clear[static_cast<size_t>(n) * C + k] = 0.f;  // consumed by se_hidden: ready for the next frame batch
   }
 }
 
@@ -277,19 +280,17 @@ extern "C" int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t
 
 extern "C" int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1, const float* b1, float* hidden,
                                 int32_t N, int32_t C, int32_t Cr, void* stream) {
-  for (int n0 = 0; n0 < N; n0 += kSeMaxN) {
-    const int nn = N - n0 < kSeMaxN ? N - n0 : kSeMaxN;
-    se_hidden_kernel<<<Cr, 256, 0, static_cast<cudaStream_t>(stream)>>>(pool_sum, inv_hw, w1, b1, hidden, n0, nn, C, Cr);
-  }
+  dim3 grid(Cr, cdiv(N, kSeMaxN));
+  se_hidden_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pool_sum, inv_hw, w1, b1, hidden, N, C, Cr);
   return check_launch("se_hidden_kernel");
 }
 
-extern "C" int octseg_se_gate(const float* hidden, const float* w2t, const float* b2, float* gate, int32_t N, int32_t C,
-                              int32_t Cr, void* stream) {
+extern "C" int octseg_se_gate(const float* hidden, const float* w2t, const float* b2, float* gate, float* pool_clear,
+                              int32_t N, int32_t C, int32_t Cr, void* stream) {
   if (Cr > 8192) return fail(OCTSEG_EINVAL, "se_gate: Cr too large");
   dim3 grid(cdiv(C, 64), N);
   se_gate_kernel<<<grid, 256, (static_cast<size_t>(Cr) + 256) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      hidden, w2t, b2, gate, C, Cr);
+      hidden, w2t, b2, gate, pool_clear, C, Cr);
   return check_launch("se_gate_kernel");
 }
 

@@ -220,9 +220,7 @@ class Builder:
         self._keep += [wk, bk]
         lib, a = self.lib, _lib.ACT[act]
 
-        def op():
-            if pool is not None:
-                pool.zero_()
+        def op():   # `pool` starts zeroed (lower.py) and is re-zeroed by octseg_se_gate after each use
             _lib.check(lib.octseg_dwconv(x.t.data_ptr(), wk.data_ptr(), bk.data_ptr(), out.t.data_ptr(), x.N, x.H,
                                          x.W, x.C, k, stride, pad[0], pad[1], out_hw[0], out_hw[1], a,
                                          pool.data_ptr() if pool is not None else None, _lib.stream_ptr()), name)
@@ -259,8 +257,8 @@ class Builder:
             st = _lib.stream_ptr()
             _lib.check(lib.octseg_se_hidden(pool.data_ptr(), inv_hw, w1d.data_ptr(), b1d.data_ptr(), hidden.data_ptr(),
                                             N, C_mid, cr, st), name + '.se_hidden')
-            _lib.check(lib.octseg_se_gate(hidden.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gate.data_ptr(), N, C_mid,
-                                          cr, st), name + '.se_gate')
+            _lib.check(lib.octseg_se_gate(hidden.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gate.data_ptr(),
+                                          pool.data_ptr(), N, C_mid, cr, st), name + '.se_gate')
             _lib.check(lib.octseg_se_scale_weights(gate.data_ptr(), base.data_ptr(), wn.data_ptr(), N, rows, Ktot,
                                                    C_mid, st), name + '.se_scale_weights')
         self.macs += geom.macs + N * 2 * C_mid * cr

@@ -20,6 +20,8 @@ class CheckedBuilder(Builder):
         super().__init__(device, N)
         self.ref = Bf16Builder(N, device)
         self.checks = []
+        self._pools = {}        # '<name>.se' -> live SE pool tensor (the gate kernel zeroes it after use)
+        self._pool_snap = {}    # '<name>' -> its contents just before the SE launches
 
     def stem(self, x, in_dtype, w, b, **k):
         out = super().stem(x, in_dtype, w, b, **k)
@@ -65,7 +67,9 @@ class CheckedBuilder(Builder):
 
     def se_project(self, x, pool, w1, b1, w2, b2, wp, bp, **k):
         out = super().se_project(x, pool, w1, b1, w2, b2, wp, bp, **k)
-        self.checks.append((k['name'], lambda: _nchw(self.ref.se_project(x, pool, w1, b1, w2, b2, wp, bp, **k)),
+        self._pools[k['name'] + '.se'] = pool
+        self.checks.append((k['name'],
+                            lambda: _nchw(self.ref.se_project(x, self._pool_snap[k['name']], w1, b1, w2, b2, wp, bp, **k)),
                             lambda: _nchw(out)))
         return out
 
@@ -77,6 +81,8 @@ class CheckedBuilder(Builder):
             checks[name.replace('[mask]', '')] = (name, r, g)
         errs = []
         for op_name, op in zip(self.op_names, self.ops):
+            if op_name in self._pools:
+                self._pool_snap[op_name[:-3]] = self._pools[op_name].clone()
             op()
             torch.cuda.synchronize()
             if op_name not in checks:               # helper launches (SE gate) are covered by their consumer

@@ -1,6 +1,6 @@
 """Turn ncu outputs under gpurun_out/ into the small text/JSON summaries committed under profiles/.
 
-  python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv profiles/launches_r1_summary.md
+  python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv profiles/launches_r1_summary.md 32   (32 = bench batch)
   python tools/summarize_ncu.py full gpurun_out/prof_x.ncu-rep profiles/prof_x_r1.txt
 """
 import collections
@@ -17,7 +17,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__cycles_elapsed.max', 'smsp__inst_executed.sum', 'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct']
 
 
-def launches(src, dst):
+def launches(src, dst, batch=None):
     rows = list(csv.reader(open(src)))
     hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
     h = rows[hi]
@@ -34,7 +34,7 @@ def launches(src, dst):
         else:
             v = v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
         per[r[ii]][r[mi]] = v
-        names[r[ii]] = r[ki].split('(')[0].replace('void ', '')
+        names[r[ii]] = r[ki].split('(')[0].replace('void ', '').split('<')[0]   # template specialisations aggregate
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
     for i, m in per.items():
         a = agg[names[i]]
@@ -51,7 +51,7 @@ def launches(src, dst):
     tc = agg.get('octseg::conv_tc_kernel')
     if tc:
         json.dump({'kernel': 'conv_tc_kernel', 'launches': tc[0], 'dram_bytes_per_launch': tc[2] / tc[0],
-                   'share_of_kernel_time': tc[1] / tot, 'source': src}, open(dst.replace('_summary.md', '_traffic.json'), 'w'))
+                   'share_of_kernel_time': tc[1] / tot, 'source': src, 'batch': int(batch) if batch else None}, open(dst.replace('_summary.md', '_traffic.json'), 'w'))
     print('\n'.join(out))
 
 
@@ -75,4 +75,4 @@ def full(src, dst):
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full}[sys.argv[1]](*sys.argv[2:])
