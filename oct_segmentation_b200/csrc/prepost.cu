@@ -9,47 +9,105 @@
 
 namespace octseg {
 
+// Stage `bytes` of a global row in shared memory: 16-byte loads when both ends allow it.
+__device__ __forceinline__ void stage_row(uint8_t* dst, const uint8_t* __restrict__ src, int bytes) {
+  if (((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(bytes)) & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < (bytes >> 4); i += blockDim.x) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+}
+
 // cv2's uint8 bilinear: horizontal pass in int32 with 11-bit coefficients, vertical pass
 //   dst = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
-// One thread per destination pixel (3 channels, BGR order written).
-__global__ void preprocess_resize_bgr_kernel(const uint8_t* __restrict__ src, int Hs, int Ws,
-                                             uint8_t* __restrict__ dst, int S, const int* __restrict__ xofs,
-                                             const short* __restrict__ xalpha, const int* __restrict__ yofs,
-                                             const short* __restrict__ ybeta, int area2x, int N) {
-  const size_t total = static_cast<size_t>(N) * S * S;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int dx = idx % S;
-    const int dy = (idx / S) % S;
-    const int n = idx / (static_cast<size_t>(S) * S);
-    const uint8_t* img = src + static_cast<size_t>(n) * Hs * Ws * 3;
-    uint8_t o[3];
-    if (area2x) {
-      // cv2 switches INTER_LINEAR to the fast 2x2 area average when both scales are exactly 2
-      const uint8_t* r0 = img + (static_cast<size_t>(2 * dy) * Ws + 2 * dx) * 3;
-      const uint8_t* r1 = r0 + static_cast<size_t>(Ws) * 3;
+// One block per destination row: its two source rows are staged in shared memory with 16-byte loads,
+// a thread produces 4 destination pixels (12 bytes, written as three 32-bit words, BGR order) from
+// byte reads of the staged rows and one 16-byte read of each coefficient table.
+constexpr int kPreThreads = 256;
+__global__ void __launch_bounds__(kPreThreads) preprocess_resize_bgr_kernel(
+    const uint8_t* __restrict__ src, int Hs, int Ws, uint8_t* __restrict__ dst, int S, const int* __restrict__ xofs,
+    const short* __restrict__ xalpha, const int* __restrict__ yofs, const short* __restrict__ ybeta, int area2x) {
+  extern __shared__ __align__(16) uint8_t rows[];  // [2][row_pitch]
+  const int dy = blockIdx.x, n = blockIdx.y;
+  const int row_bytes = Ws * 3, pitch = (row_bytes + 15) & ~15;
+  const uint8_t* img = src + static_cast<size_t>(n) * Hs * row_bytes;
+  int y0, y1, b0 = 0, b1 = 0;
+  if (area2x) {  // cv2 switches INTER_LINEAR to the fast 2x2 area average when both scales are exactly 2
+    y0 = 2 * dy;
+    y1 = 2 * dy + 1;
+  } else {
+    const int sy = yofs[dy];
+    y0 = min(max(sy, 0), Hs - 1);
+    y1 = min(max(sy + 1, 0), Hs - 1);
+    b0 = ybeta[2 * dy];
+    b1 = ybeta[2 * dy + 1];
+  }
+  stage_row(rows, img + static_cast<size_t>(y0) * row_bytes, row_bytes);
+  stage_row(rows + pitch, img + static_cast<size_t>(y1) * row_bytes, row_bytes);
+  __syncthreads();
+  const uint8_t* r0 = rows;
+  const uint8_t* r1 = rows + pitch;
+  uint8_t* drow = dst + (static_cast<size_t>(n) * S + dy) * S * 3;
+  const bool vec = (S & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(xofs) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(xalpha) & 15) == 0;
+  for (int q = threadIdx.x; q < (S + 3) / 4; q += kPreThreads) {
+    uint8_t o[12];
+    int sx[4] = {0, 0, 0, 0}, al[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!area2x) {
+      if (vec) {
+        const int4 s4 = __ldg(reinterpret_cast<const int4*>(xofs) + q);
+        const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(xalpha) + q);  // 8 shorts
+        sx[0] = s4.x, sx[1] = s4.y, sx[2] = s4.z, sx[3] = s4.w;
+        const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((r0[c] + r0[3 + c] + r1[c] + r1[3 + c] + 2) >> 2);
-    } else {
-      const int sx0 = xofs[dx];
-      const int sx1 = min(sx0 + 1, Ws - 1);
-      const int a0 = xalpha[2 * dx], a1 = xalpha[2 * dx + 1];
-      const int sy = yofs[dy];
-      const int y0 = min(max(sy, 0), Hs - 1), y1 = min(max(sy + 1, 0), Hs - 1);
-      const int b0 = ybeta[2 * dy], b1 = ybeta[2 * dy + 1];
-      const uint8_t* r0 = img + static_cast<size_t>(y0) * Ws * 3;
-      const uint8_t* r1 = img + static_cast<size_t>(y1) * Ws * 3;
+        for (int p = 0; p < 4; ++p) {
+          al[2 * p] = static_cast<short>(aw[p] & 0xffffu);
+          al[2 * p + 1] = static_cast<short>(aw[p] >> 16);
+        }
+      } else {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int h0 = r0[sx0 * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
-        const int h1 = r1[sx0 * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
-        o[c] = static_cast<uint8_t>((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+        for (int p = 0; p < 4; ++p) {
+          const int dx = min(4 * q + p, S - 1);
+          sx[p] = xofs[dx];
+          al[2 * p] = xalpha[2 * dx];
+          al[2 * p + 1] = xalpha[2 * dx + 1];
+        }
       }
     }
-    uint8_t* d = dst + idx * 3;
-    d[0] = o[2];  // RGB -> BGR
-    d[1] = o[1];
-    d[2] = o[0];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int dx = min(4 * q + p, S - 1);
+      uint8_t v[3];
+      if (area2x) {
+        const uint8_t* p0 = r0 + 6 * dx;
+        const uint8_t* p1 = r1 + 6 * dx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = static_cast<uint8_t>((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
+      } else {
+        const int x0 = sx[p] * 3, x1 = min(sx[p] + 1, Ws - 1) * 3;
+        const int a0 = al[2 * p], a1 = al[2 * p + 1];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int h0 = r0[x0 + c] * a0 + r0[x1 + c] * a1;
+          const int h1 = r1[x0 + c] * a0 + r1[x1 + c] * a1;
+          v[c] = static_cast<uint8_t>((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+        }
+      }
+      o[3 * p] = v[2];  // RGB -> BGR
+      o[3 * p + 1] = v[1];
+      o[3 * p + 2] = v[0];
+    }
+    if (vec) {
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(drow) + 3 * q;
+#pragma unroll
+      for (int w = 0; w < 3; ++w)
+        d32[w] = o[4 * w] | (o[4 * w + 1] << 8) | (o[4 * w + 2] << 16) | (static_cast<uint32_t>(o[4 * w + 3]) << 24);
+    } else {
+      for (int p = 0; p < 4 && 4 * q + p < S; ++p)
+        for (int c = 0; c < 3; ++c) drow[(4 * q + p) * 3 + c] = o[3 * p + c];
+    }
   }
 }
 
@@ -67,14 +125,17 @@ struct PostParams {
 };
 
 // One thread = 4 consecutive output pixels: 16-byte mask store, 4-byte label store.
+constexpr int kPostRows = 8;
 __global__ void __launch_bounds__(256) postprocess_kernel(const PostParams p) {
   __shared__ int sm_cnt[4];
   if (threadIdx.x < 4) sm_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int Wq = (p.Wo + 3) >> 2;
   const int n = blockIdx.z;
-  const int y = blockIdx.y;
   int cnt[4] = {0, 0, 0, 0};
+  // a block walks kPostRows output rows: 8x fewer same-address count atomics, more loads in flight per block
+  const int y_end = min(p.Ho, (static_cast<int>(blockIdx.y) + 1) * kPostRows);
+  for (int y = blockIdx.y * kPostRows; y < y_end; ++y)
   for (int xq = blockIdx.x * blockDim.x + threadIdx.x; xq < Wq; xq += gridDim.x * blockDim.x) {
     uint32_t m[4] = {0, 0, 0, 0};  // m[px] = 4 class bytes of pixel px
 #pragma unroll
@@ -83,12 +144,19 @@ __global__ void __launch_bounds__(256) postprocess_kernel(const PostParams p) {
       const int S = p.S[c];
       const int sy = p.lut[c][y];
       const uint8_t* row = p.chan[c] + static_cast<size_t>(n) * p.img_stride[c] + static_cast<size_t>(sy) * S;
-      const int* lx = p.lut[c] + p.Ho;
+      const int* lx = p.lut[c] + p.Ho + xq * 4;
+      int sx[4];
+      if (xq * 4 + 3 < p.Wo && (reinterpret_cast<uintptr_t>(lx) & 15) == 0) {  // one 16-byte read of the column table
+        const int4 t = __ldg(reinterpret_cast<const int4*>(lx));
+        sx[0] = t.x, sx[1] = t.y, sx[2] = t.z, sx[3] = t.w;
+      } else {
+#pragma unroll
+        for (int px = 0; px < 4; ++px) sx[px] = (xq * 4 + px < p.Wo) ? lx[px] : -1;
+      }
 #pragma unroll
       for (int px = 0; px < 4; ++px) {
-        const int x = xq * 4 + px;
-        if (x < p.Wo) {
-          const uint32_t v = row[lx[x]] ? 1u : 0u;
+        if (sx[px] >= 0) {
+          const uint32_t v = row[sx[px]] ? 1u : 0u;
           m[px] |= v << (8 * c);
           cnt[c] += v;
         }
@@ -174,11 +242,13 @@ extern "C" int octseg_preprocess_resize_bgr(const uint8_t* src, int32_t N, int32
                                             void* stream) {
   if (!src || !dst) return fail(OCTSEG_EINVAL, "preprocess: null buffer");
   if (!area_fast_2x && (!xofs || !xalpha || !yofs || !ybeta)) return fail(OCTSEG_EINVAL, "preprocess: null LUT");
-  const size_t total = static_cast<size_t>(N) * S * S;
-  size_t g = (total + 255) / 256;
-  if (g > 148 * 32) g = 148 * 32;
-  preprocess_resize_bgr_kernel<<<static_cast<int>(g ? g : 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x, N);
+  if (N <= 0 || S <= 0) return OCTSEG_OK;
+  if (N > 65535) return fail(OCTSEG_EINVAL, "preprocess: at most 65535 frames per call");
+  const size_t smem = 2 * static_cast<size_t>((Ws * 3 + 15) & ~15);
+  if (smem > 48 * 1024) return fail(OCTSEG_EINVAL, "preprocess: source rows of %d pixels do not fit shared memory", Ws);
+  dim3 grid(S, N);
+  preprocess_resize_bgr_kernel<<<grid, kPreThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      src, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x);
   return check_launch("preprocess_resize_bgr_kernel");
 }
 
@@ -205,8 +275,9 @@ extern "C" int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h
   p.mask = mask;
   p.label = label;
   p.counts = counts;
+  if (N <= 0 || Ho <= 0 || Wo <= 0) return OCTSEG_OK;
   const int Wq = (Wo + 3) / 4;
-  dim3 grid(cdiv(Wq, 256), Ho, N);
+  dim3 grid(cdiv(Wq, 256), cdiv(Ho, kPostRows), N);
   postprocess_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("postprocess_kernel");
 }
