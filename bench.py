@@ -136,7 +136,7 @@ def reference_arm(args):
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def ours_arm(args):
@@ -272,9 +272,30 @@ def ours_arm(args):
             line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
                                     'sample': f'{args.cpu_frames} frames through the oracle restatement of src/predict.py '
                                               f'(batch 1 per call, FC_LC run per class, cv2 pre/post), {sum(times):.1f} s'}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there) must not add
+    to it: everything written to fd 1 from here on goes to stderr; emit() writes the result line to the real one."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -287,6 +308,7 @@ def main():
     ap.add_argument('--cpu-frames', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == 'reference':
         reference_arm(args)
     else:
