@@ -45,7 +45,7 @@ class ConvDesc(C.Structure):
         ('bias', C.c_void_p), ('act', C.c_int32), ('res_mode', C.c_int32), ('res', C.c_void_p),
         ('res_ldc', C.c_int32), ('out', C.c_void_p), ('out_mode', C.c_int32), ('out_H', C.c_int32),
         ('out_W', C.c_int32), ('out_ldc', C.c_int32), ('out_c_off', C.c_int32), ('out_pack', C.c_int32),
-        ('d2s', C.c_int32),
+        ('d2s', C.c_int32), ('halo', C.c_int32),
     ]
 
 

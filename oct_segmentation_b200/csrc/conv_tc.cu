@@ -60,13 +60,15 @@ struct __align__(64) ConvKParams {
   int use_tma_store;
   int bias_floats;    // n_tiles_n * BN + 64 bias values staged in shared memory (rounded up to 4)
   int b_stage_bytes;  // bytes of one B stage (kw weight tiles for wide segments)
-  int a_stage_bytes;  // kABytes or kABytesWide
+  int a_stage_bytes;  // kABytes, kABytesWide, or the halo tile (rounded up to 1 KB) in halo mode
+  int halo;           // halo-tile mode: TH=16, TW=8, one halo box per channel chunk, resident weights
+  int b_res_bytes;    // halo mode: bytes of one channel tile's weights (kh*kw*cchunks tiles of BN x 64)
   const float* bias;
   const __nv_bfloat16* res;
   int res_ldc;
   void* out;
   int out_H, out_W, out_ldc, out_c_off, out_pack, d2s;
-  FastDiv fd_ntn, fd_phases, fd_tw, fd_th, fd_TW;
+  FastDiv fd_ntn, fd_phases, fd_tw, fd_th, fd_TW, fd_n;
 };
 
 // ----------------------------------------------------------------------------- tcgen05 wrappers
@@ -232,6 +234,19 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
   TileCoord c;
   uint32_t t = static_cast<uint32_t>(tile), q;
+  if (p.halo) {  // channel tile slowest: its weights stay resident in shared memory across a CTA's tiles
+    q = fd_div(t, p.fd_tw);
+    c.tw = static_cast<int>(t - q * p.fd_tw.d);
+    t = q;
+    q = fd_div(t, p.fd_th);
+    c.th = static_cast<int>(t - q * p.fd_th.d);
+    t = q;
+    q = fd_div(t, p.fd_n);
+    c.n = static_cast<int>(t - q * p.fd_n.d);
+    c.n_tile = static_cast<int>(q);
+    c.phase = c.ph = c.pw = 0;
+    return c;
+  }
   q = fd_div(t, p.fd_ntn);
   c.n_tile = static_cast<int>(t - q * p.fd_ntn.d);
   t = q;
@@ -258,12 +273,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t smemA = smem0;
   const uint32_t a_bytes = static_cast<uint32_t>(p.a_stage_bytes);
   const uint32_t smemB = smem0 + nst * a_bytes;
-  const uint32_t smemOut = smemB + nst * b_bytes;        // 2 x 16 KB epilogue staging (TMA store source)
+  const uint32_t smemOut = smemB + (p.halo ? static_cast<uint32_t>(p.b_res_bytes) : nst * b_bytes);  // 2 x 16 KB epilogue staging
   const uint32_t smemBias = smemOut + 2 * kOutBytes;     // fp32 bias of every channel tile
   const uint32_t bars = smemBias + p.bias_floats * 4;    // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
   const uint32_t bar_tfull = bars + 16 * kMaxStages, bar_tempty = bar_tfull + 16;
-  const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t bar_bres = bar_tempty + 16;  // halo mode: resident weights landed
+  const uint32_t tmem_slot = bar_bres + 8;
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
+    mbar_init(bar_bres, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -312,6 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int halo_nt = -1;  // halo mode: channel tile whose weights are resident
       [[maybe_unused]] int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         OCTSEG_STAMP(0, it);  // producer starts issuing this tile
@@ -319,6 +337,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int brow = tc.n_tile * p.BN;
         const int bz = tc.phase + p.phases * (p.per_image_weights ? tc.n : 0);
         int kofs = 0;
+        if (p.halo) {
+          const SegK& sg = p.seg[0];
+          if (tc.n_tile != halo_nt) {
+            // new channel tile: drain the ring (every MMA that reads the old weights has completed), then
+            // load its kh*kw*cchunks weight tiles into the resident region
+            if (halo_nt >= 0)
+              for (int i = 0; i < nst; ++i) {
+                const int st = stage + i < nst ? stage + i : stage + i - nst;
+                mbar_wait(bar_empty + 8 * st, (stage + i < nst ? phase : phase ^ 1) ^ 1);
+              }
+            halo_nt = tc.n_tile;
+            const int nb = sg.kh * sg.kw * sg.cchunks;
+            mbar_arrive_expect_tx(bar_bres, static_cast<uint32_t>(p.b_res_bytes));
+            for (int i = 0; i < nb; ++i)
+              tma_load_3d(smemB + static_cast<uint32_t>(i * p.BN * 128), &p.tmB[2], bar_bres, i * 64, brow, 0);
+          }
+          const int h0 = tc.th * p.TH + sg.off_h[0], w0 = tc.tw * p.TW + sg.off_w[0];
+          const int cbase = sg.c_per_tile * tc.n_tile;
+          const uint32_t tx_bytes = static_cast<uint32_t>((p.TH + sg.kh - 1) * (p.TW + sg.kw - 1) * 128);
+          for (int cc = 0; cc < sg.cchunks; ++cc) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
+            tma_load_4d(smemA + stage * a_bytes, &p.tmA[0], bar_full + 8 * stage, cbase + cc * 64, w0, h0, tc.n);
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         for (int s = 0; s < p.nseg; ++s) {
           const SegK& sg = p.seg[s];
           const int h0 = sg.mul * tc.th * p.TH + sg.off_h[tc.ph];
@@ -411,6 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int halo_nt = -1;
+      uint32_t bres_phase = 0;
       [[maybe_unused]] int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         OCTSEG_STAMP(1, it);  // MMA warp ready for this tile
@@ -419,7 +469,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         OCTSEG_STAMP(2, it);  // accumulator free
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.BN);
         uint32_t accum = 0;  // 0 only for the very first MMA of the tile
-        for (int s = 0; s < p.nseg; ++s) {
+        if (p.halo) {
+          const SegK& sg = p.seg[0];
+          const int nt = static_cast<int>(fd_div(fd_div(fd_div(static_cast<uint32_t>(tile), p.fd_tw), p.fd_th), p.fd_n));
+          if (nt != halo_nt) {  // this channel tile's weights: wait for the producer's resident load
+            halo_nt = nt;
+            mbar_wait(bar_bres, bres_phase);
+            bres_phase ^= 1;
+          }
+          const int pw = p.TW + sg.kw - 1;  // halo row pitch in pixels
+          // A: 8-pixel tile rows are the 8-row groups; group stride = one halo row (pw * 128 B)
+          uint64_t desc_a = make_kmajor_desc(0, 64);
+          desc_a = (desc_a & ~(0x3FFFull << 32)) | (static_cast<uint64_t>((pw * 128) >> 4) << 32);
+          const uint64_t desc_b = make_kmajor_desc(0, 64);
+          const uint32_t tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
+          for (int cc = 0; cc < sg.cchunks; ++cc) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t a0 = smemA + stage * a_bytes;
+            for (int ty = 0; ty < sg.kh; ++ty)
+              for (int tx = 0; tx < sg.kw; ++tx) {
+                const uint64_t adesc = desc_a | ((a0 + static_cast<uint32_t>((ty * pw + tx) * 128)) >> 4);
+                const uint64_t bdesc =
+                    desc_b | ((smemB + static_cast<uint32_t>((ty * sg.kw + tx) * sg.cchunks + cc) * tile_bytes) >> 4);
+                tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+                tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                accum = 1;
+              }
+            tc_commit(bar_empty + 8 * stage);
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        for (int s = 0; s < (p.halo ? 0 : p.nseg); ++s) {
           const int kc = p.seg[s].kc;
           int nsub = p.seg[s].kh * p.seg[s].kw * p.seg[s].cchunks;
           const uint64_t desc_hi = make_kmajor_desc(0, kc);
@@ -713,9 +799,14 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
       delete pl;
       return fail(OCTSEG_EINVAL, "segment %d: wide boxes need kc=64, mul=1, TH=1, kw>=2 and TW+kw-1<=136", s);
     }
+    if (d->halo && (d->nseg != 1 || d->phases != 1 || sg.kc != 64 || sg.mul != 1 || sg.wide || d->TH != 16 || d->TW != 8 ||
+                    d->per_image_weights || sg.kh > 8 || sg.kw > 8)) {
+      delete pl;
+      return fail(OCTSEG_EINVAL, "halo mode needs nseg=1, phases=1, kc=64, mul=1, TH=16, TW=8, shared weights");
+    }
     const uint32_t box[4] = {static_cast<uint32_t>(sg.kc),
-                             static_cast<uint32_t>(sg.wide ? d->TW + sg.kw - 1 : d->TW * sg.mul),
-                             static_cast<uint32_t>(d->TH * sg.mul), 1u};
+                             static_cast<uint32_t>(d->halo ? d->TW + sg.kw - 1 : (sg.wide ? d->TW + sg.kw - 1 : d->TW * sg.mul)),
+                             static_cast<uint32_t>(d->halo ? d->TH + sg.kh - 1 : d->TH * sg.mul), 1u};
     const uint32_t estr[4] = {1u, static_cast<uint32_t>(sg.mul), static_cast<uint32_t>(sg.mul), 1u};
     int rc = encode_map(&kp.tmA[s], sg.ptr, 4, dims, strides, box, estr, "A", sg.kc);
     if (rc) {
@@ -738,7 +829,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     if (sg.wide && sg.kw > b_tiles) b_tiles = sg.kw;
     if (sg.wide) any_wide = true;
     const int nsub = sg.kh * sg.kw * sg.cchunks, subs = 64 / sg.kc;
-    k_iters += sg.wide ? sg.kh * sg.cchunks : (nsub + subs - 1) / subs;
+    k_iters += d->halo ? sg.cchunks : (sg.wide ? sg.kh * sg.cchunks : (nsub + subs - 1) / subs);
     k_total += nsub * sg.kc;
     kc_used[sg.kc == 64 ? 2 : (sg.kc == 32 ? 1 : 0)] = true;
   }
@@ -804,10 +895,11 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   kp.fd_tw = make_fastdiv(static_cast<uint32_t>(kp.tiles_w));
   kp.fd_th = make_fastdiv(static_cast<uint32_t>(kp.tiles_h));
   kp.fd_TW = make_fastdiv(static_cast<uint32_t>(d->TW));
+  kp.fd_n = make_fastdiv(static_cast<uint32_t>(d->N));
   {
     const long long lim = 1ll << 32;
     const long long t = kp.total_tiles;
-    if (t * d->n_tiles_n >= lim || t * kp.tiles_w >= lim || t * kp.tiles_h >= lim) {
+    if (t * d->n_tiles_n >= lim || t * kp.tiles_w >= lim || t * kp.tiles_h >= lim || t * d->N >= lim) {
       delete pl;
       return fail(OCTSEG_EINVAL, "too many tiles (%lld) for the 32-bit tile decoder", t);
     }
@@ -848,11 +940,19 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     }
   }
 
+  kp.halo = d->halo ? 1 : 0;
+  kp.b_res_bytes = 0;
   kp.b_stage_bytes = b_tiles * d->BN * 128;
   kp.a_stage_bytes = any_wide ? kABytesWide : kABytes;
+  if (kp.halo) {
+    const octseg_conv_seg& sg = d->seg[0];
+    kp.b_res_bytes = sg.kh * sg.kw * sg.cchunks * d->BN * 128;
+    kp.b_stage_bytes = 0;  // the stages hold halo tiles only
+    kp.a_stage_bytes = ((d->TH + sg.kh - 1) * (d->TW + sg.kw - 1) * 128 + 1023) & ~1023;
+  }
   const int stage_bytes = kp.a_stage_bytes + kp.b_stage_bytes;
   kp.bias_floats = (d->n_tiles_n * d->BN + 64 + 3) & ~3;
-  const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes - kp.bias_floats * 4;
+  const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes - kp.bias_floats * 4 - kp.b_res_bytes;
   int nst = budget / stage_bytes;
   if (nst > kMaxStages) nst = kMaxStages;
   if (nst < 2) {
@@ -860,7 +960,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     return fail(OCTSEG_EINVAL, "tile does not fit shared memory");
   }
   kp.nstages = nst;
-  pl->smem = static_cast<size_t>(nst) * stage_bytes + 2 * kOutBytes + kp.bias_floats * 4 + 1024 + 512;
+  pl->smem = static_cast<size_t>(nst) * stage_bytes + kp.b_res_bytes + 2 * kOutBytes + kp.bias_floats * 4 + 1024 + 512;
   int sms = octseg_sm_count();
   if (sms <= 0) {
     delete pl;

@@ -21,6 +21,8 @@ from .. import _lib
 
 KC = 64  # K elements per pipeline stage (one 128-byte swizzle atom of bf16)
 WIDE_BOXES = True  # allow shifted-view tap reuse (SegSpec.wide)
+HALO_TILES = True  # allow halo-tile mode (ConvGeom.halo)
+HALO_B_BYTES = 80 * 1024   # resident-weight budget of halo mode (shared memory)
 
 
 def choose_kc(c_eff: int) -> int:
@@ -93,6 +95,7 @@ class ConvGeom:
     out_H: int
     out_W: int
     macs: int = 0        # algorithmic MACs of the reference op (dense count, for rooflines)
+    halo: int = 0        # 1: 16x8 tiles, one halo-box A load per channel chunk, weights resident in smem
 
 
 def choose_tile(Hq: int, Wq: int) -> Tuple[int, int]:
@@ -244,14 +247,26 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
         c_lo += sC
     packed = torch.stack([torch.cat(b, dim=1) for b in blocks]).to(packed_dtype).contiguous()
     Ktot = packed.shape[2]
-    if TH == 1 and WIDE_BOXES:
+    # Halo-tile mode for narrow single-source k x k convs (stride 1): the tile is 16 x 8 pixels, its
+    # (16+kh-1) x (8+kw-1) halo is ONE TMA box per channel chunk and the taps are shifted views of it
+    # (8-pixel rows keep the UMMA 8-row groups at a uniform stride); the channel tile's whole weight
+    # slice stays resident in shared memory.  Cuts the L2->smem traffic of such layers ~9x.
+    halo = 0
+    if (HALO_TILES and len(segs) == 1 and phases == 1 and not transposed):
+        sg = segs[0]
+        b_bytes = sg.kh * sg.kw * sg.cchunks * BN * 128
+        cover = (-(-Hq // 16) * 16) * (-(-Wq // 8) * 8)
+        if (sg.kc == 64 and sg.mul == 1 and sg.kh * sg.kw >= 4 and sg.kh <= 7 and sg.kw <= 7 and b_bytes <= HALO_B_BYTES
+                and Hq * Wq >= 0.75 * cover):
+            halo, TH, TW = 1, 16, 8
+    if TH == 1 and WIDE_BOXES and not halo:
         # activation-traffic saver for L2-bound shapes: the B stage then holds kw weight tiles
         for sg in segs:
             if (sg.kc == 64 and sg.mul == 1 and sg.kw >= 2 and TW + sg.kw - 1 <= 136 and BN <= 128
                     and (sg.c_per_tile == 0 or sg.cchunks == 1)):
                 sg.wide = 1
     geom = ConvGeom(segs, phases, N, Hq, Wq, TH, TW, BN, n_tiles_n, cout_per_tile, cout_w, Ktot, out_H, out_W,
-                    macs)
+                    macs, halo)
     return geom, packed
 
 
@@ -375,6 +390,7 @@ class ConvPlan:
         d.out_c_off = out_c_off
         d.out_pack = out_pack
         d.d2s = d2s
+        d.halo = geom.halo
         handle = C.c_void_p()
         _lib.check(lib.octseg_conv_plan_create(C.byref(d), C.byref(handle)), f'conv_plan_create({name})')
         self._lib, self._h = lib, handle

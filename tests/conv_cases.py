@@ -176,4 +176,13 @@ CASES = [
     ConvCase('wide_3x3_128_w160', [(128, 5, 160, False)], 128),
     ConvCase('wide_up2x2', [(64, 4, 128, True), (64, 8, 256, False)], 64),
     ConvCase('wide_grouped', [(128, 6, 128, False)], 128, groups=2),
+    # halo-tile mode (16x8 tiles, one halo box per chunk, resident weights)
+    ConvCase('halo_3x3_64_partial_tiles', [(64, 40, 44, False)], 64),
+    ConvCase('halo_grouped_56_28', [(392, 28, 28, False)], 392, groups=7),
+    ConvCase('halo_head_u8', [(64, 32, 32, False)], 2, out_mode='u8_nchw', act='none'),
+    ConvCase('halo_head_f32', [(64, 32, 48, False)], 1, out_mode='f32_nchw', act='none'),
+    ConvCase('halo_5x5_cout16', [(64, 32, 32, False)], 16, k=5, pad=(2, 2)),
+    ConvCase('halo_res_before', [(64, 32, 32, False)], 64, res_mode='before_act'),
+    ConvCase('halo_two_chunks', [(128, 32, 32, False)], 32, act='swish'),
+    ConvCase('halo_asym_pad', [(64, 32, 32, False)], 48, pad=(0, 0), pad_br=(2, 2), act='none'),
 ]
