@@ -30,6 +30,7 @@
 namespace octseg {
 
 constexpr int kMaxStages = 8;
+constexpr int kMaxAcc = 8;  // TMEM accumulator ring: min(8, 512 / BN) tiles between the MMA warp and the epilogue
 constexpr int kABytes = 128 * 128;      // A stage: 128 rows x 64 bf16 ...
 constexpr int kABytesWide = 136 * 128;  // ... or 136 rows when a segment loads wide boxes (8 halo pixels)
 constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter -> 4 warps per SM sub-partition
@@ -61,6 +62,7 @@ struct __align__(64) ConvKParams {
   int bias_floats;    // n_tiles_n * BN + 64 bias values staged in shared memory (rounded up to 4)
   int b_stage_bytes;  // bytes of one B stage (kw weight tiles for wide segments)
   int a_stage_bytes;  // kABytes, kABytesWide, or the halo tile (rounded up to 1 KB) in halo mode
+  int n_acc;          // accumulators in the TMEM ring (2 for BN = 256 ... 8 for BN <= 64)
   int halo;           // halo-tile mode: TH=16, TW=8, one halo box per channel chunk, resident weights
   int b_res_bytes;    // halo mode: bytes of one channel tile's weights (kh*kw*cchunks tiles of BN x 64)
   const float* bias;
@@ -78,17 +80,21 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
+__device__ __forceinline__ void tc_commit(uint32_t leader, uint32_t bar) {
   asm volatile(
-      "{\n.reg .pred p;\n"
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar),
+      "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t leader, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -221,7 +227,7 @@ __device__ __forceinline__ uint4 epi8(const uint32_t* v, const float* bias8, con
 constexpr int kTraceTiles = 256, kTraceEvents = 16;
 __device__ unsigned long long g_trace[kTraceEvents][kTraceTiles];
 #define OCTSEG_STAMP(ev, it) \
-  do { if (blockIdx.x == 0 && (it) < kTraceTiles) g_trace[ev][it] = clock64(); } while (0)
+  do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it) < kTraceTiles) g_trace[ev][it] = clock64(); } while (0)
 #else
 #define OCTSEG_STAMP(ev, it) do { } while (0)
 #endif
@@ -277,8 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t smemBias = smemOut + 2 * kOutBytes;     // fp32 bias of every channel tile
   const uint32_t bars = smemBias + p.bias_floats * 4;    // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
-  const uint32_t bar_tfull = bars + 16 * kMaxStages, bar_tempty = bar_tfull + 16;
-  const uint32_t bar_bres = bar_tempty + 16;  // halo mode: resident weights landed
+  const uint32_t bar_tfull = bars + 16 * kMaxStages, bar_tempty = bar_tfull + 8 * kMaxAcc;
+  const uint32_t bar_bres = bar_tempty + 8 * kMaxAcc;  // halo mode: resident weights landed
   const uint32_t tmem_slot = bar_bres + 8;
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
 
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < p.n_acc; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
@@ -325,11 +331,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, elected issuer)
+    {
+      const uint32_t leader = elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
       int halo_nt = -1;  // halo mode: channel tile whose weights are resident
+      // fast path for single-source 1x1 convs (the output-bound layers, one stage per tile): their per-tile
+      // cost is this warp's serial setup, so the segment constants live in registers
+      const bool simple = p.nseg == 1 && !p.halo && !p.seg[0].wide && p.seg[0].kh == 1 && p.seg[0].kw == 1 && p.phases == 1;
+      const int s_kc = p.seg[0].kc, s_cch = p.seg[0].cchunks, s_mul = p.seg[0].mul, s_cpt = p.seg[0].c_per_tile;
+      const int s_offh = p.seg[0].off_h[0], s_offw = p.seg[0].off_w[0], s_subs = 64 / s_kc;
+      const uint32_t s_asub = 128u * s_kc * 2u, s_bsub = static_cast<uint32_t>(p.BN) * s_kc * 2u;
+      const uint32_t s_tx = static_cast<uint32_t>(p.TH * p.TW + p.BN) * s_kc * 2u;
+      const CUtensorMap* s_mb = &p.tmB[kc_index(s_kc)];
       [[maybe_unused]] int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         OCTSEG_STAMP(0, it);  // producer starts issuing this tile
@@ -337,6 +352,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int brow = tc.n_tile * p.BN;
         const int bz = tc.phase + p.phases * (p.per_image_weights ? tc.n : 0);
         int kofs = 0;
+        if (simple) {
+          // single-source 1x1 conv: everything but the tile origin was hoisted out of the tile loop
+          const int h0 = s_mul * tc.th * p.TH + s_offh, w0 = s_mul * tc.tw * p.TW + s_offw;
+          const int cbase = s_cpt * tc.n_tile;
+          for (int cc = 0; cc < s_cch; cc += s_subs) {
+            const int n = s_cch - cc < s_subs ? s_cch - cc : s_subs;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx_if(leader, bar_full + 8 * stage, s_tx * n);
+            for (int j = 0; j < n; ++j) {
+              tma_load_4d_if(leader, smemA + stage * a_bytes + j * s_asub, &p.tmA[0], bar_full + 8 * stage,
+                             cbase + (cc + j) * s_kc, w0, h0, tc.n);
+              tma_load_3d_if(leader, smemB + stage * b_bytes + j * s_bsub, s_mb, bar_full + 8 * stage, (cc + j) * s_kc, brow, bz);
+            }
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         if (p.halo) {
           const SegK& sg = p.seg[0];
           if (tc.n_tile != halo_nt) {
@@ -349,17 +384,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               }
             halo_nt = tc.n_tile;
             const int nb = sg.kh * sg.kw * sg.cchunks;
-            mbar_arrive_expect_tx(bar_bres, static_cast<uint32_t>(p.b_res_bytes));
+            mbar_arrive_expect_tx_if(leader, bar_bres, static_cast<uint32_t>(p.b_res_bytes));
             for (int i = 0; i < nb; ++i)
-              tma_load_3d(smemB + static_cast<uint32_t>(i * p.BN * 128), &p.tmB[2], bar_bres, i * 64, brow, 0);
+              tma_load_3d_if(leader, smemB + static_cast<uint32_t>(i * p.BN * 128), &p.tmB[2], bar_bres, i * 64, brow, 0);
           }
           const int h0 = tc.th * p.TH + sg.off_h[0], w0 = tc.tw * p.TW + sg.off_w[0];
           const int cbase = sg.c_per_tile * tc.n_tile;
           const uint32_t tx_bytes = static_cast<uint32_t>((p.TH + sg.kh - 1) * (p.TW + sg.kw - 1) * 128);
           for (int cc = 0; cc < sg.cchunks; ++cc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
-            tma_load_4d(smemA + stage * a_bytes, &p.tmA[0], bar_full + 8 * stage, cbase + cc * 64, w0, h0, tc.n);
+            mbar_arrive_expect_tx_if(leader, bar_full + 8 * stage, tx_bytes);
+            tma_load_4d_if(leader, smemA + stage * a_bytes, &p.tmA[0], bar_full + 8 * stage, cbase + cc * 64, w0, h0, tc.n);
             if (++stage == nst) {
               stage = 0;
               phase ^= 1;
@@ -384,10 +419,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int ty = 0; ty < sg.kh; ++ty) {
               for (int cc = 0; cc < sg.cchunks; ++cc) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
-                tma_load_4d(smemA + stage * a_bytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0, h0 + ty, tc.n);
+                mbar_arrive_expect_tx_if(leader, bar_full + 8 * stage, tx_bytes);
+                tma_load_4d_if(leader, smemA + stage * a_bytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0, h0 + ty, tc.n);
                 for (int tx = 0; tx < sg.kw; ++tx)
-                  tma_load_3d(smemB + stage * b_bytes + tx * tile_bytes, mb, bar_full + 8 * stage,
+                  tma_load_3d_if(leader, smemB + stage * b_bytes + tx * tile_bytes, mb, bar_full + 8 * stage,
                               kofs + ((ty * sg.kw + tx) * sg.cchunks + cc) * 64, brow, bz);
                 if (++stage == nst) {
                   stage = 0;
@@ -407,9 +442,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   OCTSEG_STAMP(10, it);  // decode + segment setup done
                   mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                   OCTSEG_STAMP(11, it);  // stage free
-                  mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub);
-                  tma_load_4d(smemA + stage * a_bytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0 + tx, h0 + ty, tc.n);
-                  tma_load_3d(smemB + stage * b_bytes, mb, bar_full + 8 * stage, kofs, brow, bz);
+                  mbar_arrive_expect_tx_if(leader, bar_full + 8 * stage, tx_sub);
+                  tma_load_4d_if(leader, smemA + stage * a_bytes, ma, bar_full + 8 * stage, cbase + cc * 64, w0 + tx, h0 + ty, tc.n);
+                  tma_load_3d_if(leader, smemB + stage * b_bytes, mb, bar_full + 8 * stage, kofs, brow, bz);
                   OCTSEG_STAMP(12, it);  // loads issued
                   kofs += 64;
                   if (++stage == nst) {
@@ -426,11 +461,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           while (nsub > 0) {
             const int n = nsub < subs ? nsub : subs;
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, tx_sub * n);
+            mbar_arrive_expect_tx_if(leader, bar_full + 8 * stage, tx_sub * n);
             for (int j = 0; j < n; ++j) {
-              tma_load_4d(smemA + stage * a_bytes + j * a_sub, &p.tmA[s], bar_full + 8 * stage, cbase + cc * sg.kc,
+              tma_load_4d_if(leader, smemA + stage * a_bytes + j * a_sub, &p.tmA[s], bar_full + 8 * stage, cbase + cc * sg.kc,
                           w0 + tx, h0 + ty, tc.n);
-              tma_load_3d(smemB + stage * b_bytes + j * b_sub, mb, bar_full + 8 * stage, kofs, brow, bz);
+              tma_load_3d_if(leader, smemB + stage * b_bytes + j * b_sub, mb, bar_full + 8 * stage, kofs, brow, bz);
               kofs += sg.kc;
               if (++cc == sg.cchunks) {
                 cc = 0;
@@ -450,8 +485,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected issuer)
+    {
+      const uint32_t leader = elect_one_sync();
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.BN >> 3) << 17) |
                              (static_cast<uint32_t>(128 >> 4) << 24);
@@ -461,6 +497,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t acc_phase = 0;
       int halo_nt = -1;
       uint32_t bres_phase = 0;
+      const bool simple = p.nseg == 1 && !p.halo && !p.seg[0].wide && p.seg[0].kh == 1 && p.seg[0].kw == 1 && p.phases == 1;
+      const int s_kc = p.seg[0].kc, s_cch = p.seg[0].cchunks, s_subs = 64 / s_kc, s_steps = s_kc / 16;
+      const uint32_t s_asub = 128u * s_kc * 2u, s_bsub = static_cast<uint32_t>(p.BN) * s_kc * 2u;
+      const uint64_t s_desc = make_kmajor_desc(0, s_kc);
       [[maybe_unused]] int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         OCTSEG_STAMP(1, it);  // MMA warp ready for this tile
@@ -469,7 +509,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         OCTSEG_STAMP(2, it);  // accumulator free
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.BN);
         uint32_t accum = 0;  // 0 only for the very first MMA of the tile
-        if (p.halo) {
+        if (simple) {
+          for (int cc = 0; cc < s_cch; cc += s_subs) {
+            const int n = s_cch - cc < s_subs ? s_cch - cc : s_subs;
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            for (int j = 0; j < n; ++j) {
+              const uint64_t adesc = s_desc | ((smemA + stage * a_bytes + j * s_asub) >> 4);
+              const uint64_t bdesc = s_desc | ((smemB + stage * b_bytes + j * s_bsub) >> 4);
+              for (int t = 0; t < s_steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
+                tc_mma_bf16(leader, d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
+                accum = 1;
+              }
+            }
+            tc_commit(leader, bar_empty + 8 * stage);
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else if (p.halo) {
           const SegK& sg = p.seg[0];
           const int nt = static_cast<int>(fd_div(fd_div(fd_div(static_cast<uint32_t>(tile), p.fd_tw), p.fd_th), p.fd_n));
           if (nt != halo_nt) {  // this channel tile's weights: wait for the producer's resident load
@@ -492,20 +551,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint64_t adesc = desc_a | ((a0 + static_cast<uint32_t>((ty * pw + tx) * 128)) >> 4);
                 const uint64_t bdesc =
                     desc_b | ((smemB + static_cast<uint32_t>((ty * sg.kw + tx) * sg.cchunks + cc) * tile_bytes) >> 4);
-                tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-                tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                tc_mma_bf16(leader, d_tmem, adesc, bdesc, idesc, accum);
+                tc_mma_bf16(leader, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                tc_mma_bf16(leader, d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                tc_mma_bf16(leader, d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
                 accum = 1;
               }
-            tc_commit(bar_empty + 8 * stage);
+            tc_commit(leader, bar_empty + 8 * stage);
             if (++stage == nst) {
               stage = 0;
               phase ^= 1;
             }
           }
         }
-        for (int s = 0; s < (p.halo ? 0 : p.nseg); ++s) {
+        for (int s = 0; s < ((p.halo || simple) ? 0 : p.nseg); ++s) {
           const int kc = p.seg[s].kc;
           int nsub = p.seg[s].kh * p.seg[s].kw * p.seg[s].cchunks;
           const uint64_t desc_hi = make_kmajor_desc(0, kc);
@@ -521,13 +580,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               for (int tx = 0; tx < kw; ++tx) {
                 const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes + tx * 128u) >> 4);
                 const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes + tx * tile_bytes) >> 4);
-                tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-                tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                tc_mma_bf16(leader, d_tmem, adesc, bdesc, idesc, accum);
+                tc_mma_bf16(leader, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                tc_mma_bf16(leader, d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                tc_mma_bf16(leader, d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
                 accum = 1;
               }
-              tc_commit(bar_empty + 8 * stage);
+              tc_commit(leader, bar_empty + 8 * stage);
               if (++stage == nst) {
                 stage = 0;
                 phase ^= 1;
@@ -542,12 +601,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               OCTSEG_STAMP(14, it);  // operands landed
               const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes) >> 4);
               const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes) >> 4);
-              tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-              tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-              tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-              tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              tc_mma_bf16(leader, d_tmem, adesc, bdesc, idesc, accum);
+              tc_mma_bf16(leader, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              tc_mma_bf16(leader, d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              tc_mma_bf16(leader, d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
               accum = 1;
-              tc_commit(bar_empty + 8 * stage);
+              tc_commit(leader, bar_empty + 8 * stage);
               OCTSEG_STAMP(15, it);  // MMAs issued, stage committed
               if (++stage == nst) {
                 stage = 0;
@@ -565,11 +624,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes + j * a_sub) >> 4);
                 const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes + j * b_sub) >> 4);
                 for (int t = 0; t < steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
-                  tc_mma_bf16(d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
+                  tc_mma_bf16(leader, d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
                   accum = 1;
                 }
               }
-              tc_commit(bar_empty + 8 * stage);
+              tc_commit(leader, bar_empty + 8 * stage);
               if (++stage == nst) {
                 stage = 0;
                 phase ^= 1;
@@ -578,10 +637,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
           }
         }
-        tc_commit(bar_tfull + 8 * acc);
+        tc_commit(leader, bar_tfull + 8 * acc);
         OCTSEG_STAMP(3, it);  // all MMAs of the tile issued + committed
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == p.n_acc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   } else {
@@ -602,8 +663,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     [[maybe_unused]] int it = 0;
     [[maybe_unused]] const bool tracer = (threadIdx.x == 64) || (threadIdx.x == 64 + 256);  // first thread of each group
     [[maybe_unused]] const int tev = 4 + 3 * group;
+    // With one channel tile the chunk layout is the same for every tile, so a group knows from the chunk
+    // counter alone whether it owns a chunk of the next tile.  If it does not (single-chunk tiles: every
+    // other tile) it only keeps its place in the accumulator ring -- no decode, no per-tile setup.
+    const int nvalid1 = min(p.cout_per_tile, p.Cout);
+    const int n_tma1 = p.use_tma_store ? ((nvalid1 >> 6) + ((nvalid1 & 63) ? 1 : 0)) : 0;
+    const bool can_skip = p.n_tiles_n == 1 && n_tma1 * 64 >= nvalid1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       if (tracer) OCTSEG_STAMP(tev, it);  // epilogue group ready for this tile
+      if (can_skip && static_cast<int>((group ^ chunk_ctr) & 1u) >= n_tma1) {
+        mbar_wait(bar_tfull + 8 * acc, acc_phase);  // stay within the ring: arrivals must land in this tile's phase
+        if (tracer) OCTSEG_STAMP(tev + 1, it);
+        mbar_arrive(bar_tempty + 8 * acc);
+        if (tracer) OCTSEG_STAMP(tev + 2, it);
+        chunk_ctr += n_tma1;
+        if (++acc == p.n_acc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
       const TileCoord tc = decode_tile(p, tile);
       const int i = tc.th * p.TH + th_l, j = tc.tw * p.TW + tw_l;
       const bool valid = (row < p.TH * p.TW) && (i < p.Hq) && (j < p.Wq);
@@ -712,8 +791,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
       if (tracer) OCTSEG_STAMP(tev + 2, it);  // accumulator released
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == p.n_acc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
     }
     if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores landed before exit
   }
@@ -940,6 +1021,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     }
   }
 
+  kp.n_acc = 512 / d->BN < kMaxAcc ? 512 / d->BN : kMaxAcc;
   kp.halo = d->halo ? 1 : 0;
   kp.b_res_bytes = 0;
   kp.b_stage_bytes = b_tiles * d->BN * 128;

@@ -54,6 +54,44 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Predicated single-issuer forms.  The producer / MMA warps run their loops CONVERGED (all 32 lanes) and
+// only the instruction that must be issued once is predicated on the elected lane: the address and
+// descriptor arithmetic then stays warp-uniform (uniform datapath, no per-operand R2UR moves), which is
+// what bounds the per-tile latency of these single-thread roles.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_if(uint32_t leader, uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}" ::"r"(bar),
+      "r"(bytes), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_if(uint32_t leader, uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %7, 0;\n"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];\n}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_if(uint32_t leader, uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1, int c2) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %6, 0;\n"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
