@@ -59,6 +59,7 @@ struct __align__(64) ConvKParams {
   int per_image_weights, act, res_mode, out_mode;
   int k_iters, nstages, total_tiles;
   int use_tma_store;
+  int out_grouped;    // grouped conv with < 64 channels per group: 5-D output map (c in group, group, w, h, n), one chunk per tile
   int bias_floats;    // n_tiles_n * BN + 64 bias values staged in shared memory (rounded up to 4)
   int b_stage_bytes;  // bytes of one B stage (kw weight tiles for wide segments)
   int a_stage_bytes;  // kABytes, kABytesWide, or the halo tile (rounded up to 1 KB) in halo mode
@@ -668,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // other tile) it only keeps its place in the accumulator ring -- no decode, no per-tile setup.
     const int nvalid1 = min(p.cout_per_tile, p.Cout);
     const int n_tma1 = p.use_tma_store ? ((nvalid1 >> 6) + ((nvalid1 & 63) ? 1 : 0)) : 0;
-    const bool can_skip = p.n_tiles_n == 1 && n_tma1 * 64 >= nvalid1;
+    const bool can_skip = (p.n_tiles_n == 1 || p.out_grouped) && n_tma1 * 64 >= nvalid1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       if (tracer) OCTSEG_STAMP(tev, it);  // epilogue group ready for this tile
       if (can_skip && static_cast<int>((group ^ chunk_ctr) & 1u) >= n_tma1) {
@@ -706,7 +707,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       // alternate chunks, so one group's barrier / TMEM / store latency overlaps the other's math.
       // The math runs BEFORE the wait for the staging buffer, so the previous TMA store drains under it.
       const int n_tma =
-          p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0;
+          p.out_grouped ? 1
+                        : (p.use_tma_store ? ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0)) : 0);
       for (int ck = 0; ck < n_tma; ++ck) {
         if (((chunk_ctr + ck) & 1) != static_cast<uint32_t>(group)) continue;  // warp-uniform
         const int cp = ck * 64 + half * 32;
@@ -731,7 +733,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         group_bar_sync(group);
         if (gtid == 0) {
           const int cch = p.out_c_off + ch0 + ck * 64;
-          if (p.phases == 4)
+          if (p.out_grouped)
+            tma_store_5d(&p.tmOut, sbuf, 0, tc.n_tile, tc.tw * p.TW, tc.th * p.TH, tc.n);
+          else if (p.phases == 4)
             tma_store_5d(&p.tmOut, sbuf, cch, tc.pw, tc.tw * p.TW, tc.ph, tc.n * p.Hq + tc.th * p.TH);
           else
             tma_store_4d(&p.tmOut, sbuf, cch, tc.tw * p.TW, tc.th * p.TH, tc.n);
@@ -992,11 +996,31 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
 
   // narrow single-tile outputs (Cout < 64) also leave through one TMA chunk: the box is 64 channels wide
   // and TMA clips it at the tensor map's channel extent
-  kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC && (d->cout_per_tile >= 64 || d->n_tiles_n == 1) && d->d2s == 0 &&
+  // channel tiles narrower than a chunk (grouped convs, e.g. 56 channels per group): the output is viewed
+  // as (channel in group, group, w, h, n); the 64-wide store box is clipped at the group's extent
+  kp.out_grouped = (d->out_mode == OCTSEG_OUT_BF16_NHWC && d->n_tiles_n > 1 && d->cout_per_tile < 64 && d->phases == 1 &&
+                    d->d2s == 0 && d->Cout == d->n_tiles_n * d->cout_per_tile && (d->cout_per_tile * 2) % 16 == 0)
+                       ? 1
+                       : 0;
+  kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC &&
+                      (d->cout_per_tile >= 64 || d->n_tiles_n == 1 || kp.out_grouped) && d->d2s == 0 &&
                       (d->phases == 1 || (d->Hq % d->TH == 0 && d->out_H == 2 * d->Hq && d->out_W == 2 * d->Wq)))
                          ? 1
                          : 0;
-  if (kp.use_tma_store) {
+  if (kp.out_grouped) {
+    const uint64_t ld = static_cast<uint64_t>(d->out_ldc) * 2;
+    const uint64_t dims[5] = {static_cast<uint64_t>(d->cout_per_tile), static_cast<uint64_t>(d->n_tiles_n),
+                              static_cast<uint64_t>(d->out_W), static_cast<uint64_t>(d->out_H), static_cast<uint64_t>(d->N)};
+    const uint64_t strides[4] = {static_cast<uint64_t>(d->cout_per_tile) * 2, ld, ld * d->out_W, ld * d->out_W * d->out_H};
+    const uint32_t box[5] = {64u, 1u, static_cast<uint32_t>(d->TW), static_cast<uint32_t>(d->TH), 1u};
+    const uint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    const int rc = encode_map(&kp.tmOut, static_cast<const __nv_bfloat16*>(d->out) + d->out_c_off, 5, dims, strides, box, estr,
+                              "out(grouped)");
+    if (rc) {
+      delete pl;
+      return rc;
+    }
+  } else if (kp.use_tma_store) {
     const uint64_t ld = static_cast<uint64_t>(d->out_ldc) * 2;
     const uint64_t cext = static_cast<uint64_t>(d->out_c_off + d->Cout);
     int rc;
