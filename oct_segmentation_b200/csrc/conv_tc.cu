@@ -71,7 +71,7 @@ struct __align__(64) ConvKParams {
   int res_ldc;
   void* out;
   int out_H, out_W, out_ldc, out_c_off, out_pack, d2s;
-  FastDiv fd_ntn, fd_phases, fd_tw, fd_th, fd_TW, fd_n;
+  FastDiv fd_ntn, fd_phases, fd_tw, fd_th, fd_TW, fd_n, fd_ldc;
 };
 
 // ----------------------------------------------------------------------------- tcgen05 wrappers
@@ -670,9 +670,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int nvalid1 = min(p.cout_per_tile, p.Cout);
     const int n_tma1 = p.use_tma_store ? ((nvalid1 >> 6) + ((nvalid1 & 63) ? 1 : 0)) : 0;
     const bool can_skip = (p.n_tiles_n == 1 || p.out_grouped) && n_tma1 * 64 >= nvalid1;
+    // Narrow direct-store tiles (the NCHW heads: <= 32 output columns): one or two warps per lane quarter
+    // cover a tile, so the 4 warps of a quarter take tiles in rotation instead of all walking every tile.
+    const bool rot = p.n_tiles_n == 1 && n_tma1 == 0 && nvalid1 <= 2 * kEpiPart;
+    const int rot_np = nvalid1 <= kEpiPart ? 1 : 2, rot_sets = kEpiSplit / rot_np;
+    const int rot_set = part / rot_np, rot_slice = part - rot_set * rot_np;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       if (tracer) OCTSEG_STAMP(tev, it);  // epilogue group ready for this tile
-      if (can_skip && static_cast<int>((group ^ chunk_ctr) & 1u) >= n_tma1) {
+      if ((can_skip && static_cast<int>((group ^ chunk_ctr) & 1u) >= n_tma1) || (rot && (it % rot_sets) != rot_set)) {
         mbar_wait(bar_tfull + 8 * acc, acc_phase);  // stay within the ring: arrivals must land in this tile's phase
         if (tracer) OCTSEG_STAMP(tev + 1, it);
         mbar_arrive(bar_tempty + 8 * acc);
@@ -746,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
       // remaining channels (and every non-bf16 output): direct stores from registers
       for (int c0 = n_tma * 64; c0 < nvalid; c0 += 64) {
-        const int cp = c0 + part * kEpiPart;
+        const int cp = rot ? rot_slice * kEpiPart : c0 + part * kEpiPart;
         if (cp >= nvalid) continue;  // warp-uniform
         uint32_t v[kEpiPart];
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
@@ -782,7 +787,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (cp + e < nvalid) {
               const float y = apply_act(__uint_as_float(v[e]) + bias[cp + e], p.act);
               const int c = p.out_c_off + ch0 + cp + e;
-              const size_t idx = base + static_cast<size_t>(c % p.out_ldc) * plane + c / p.out_ldc;
+              const int sub = static_cast<int>(fd_div(static_cast<uint32_t>(c), p.fd_ldc));  // c / out_ldc
+              const size_t idx = base + static_cast<size_t>(c - sub * p.out_ldc) * plane + sub;
               if (p.out_mode == OCTSEG_OUT_F32_NCHW)
                 reinterpret_cast<float*>(p.out)[idx] = y;
               else
@@ -981,6 +987,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   kp.fd_th = make_fastdiv(static_cast<uint32_t>(kp.tiles_h));
   kp.fd_TW = make_fastdiv(static_cast<uint32_t>(d->TW));
   kp.fd_n = make_fastdiv(static_cast<uint32_t>(d->N));
+  kp.fd_ldc = make_fastdiv(static_cast<uint32_t>(d->out_ldc > 0 ? d->out_ldc : 1));
   {
     const long long lim = 1ll << 32;
     const long long t = kp.total_tiles;
