@@ -130,3 +130,91 @@ class EnsemblePipeline:
         if copy:
             out = [o.copy() if o is not None else None for o in out]
         return tuple(out)
+
+    # ------------------------------------------------------------------ pipelined host-to-host stream
+    def _stream_sets(self):
+        if getattr(self, '_sets', None) is None:
+            Hs, Ws = self.src_hw
+            sets = []
+            with torch.cuda.device(self.device):
+                for _ in range(2):
+                    sets.append({
+                        'pin_frames': torch.empty(self.batch, Hs, Ws, 3, dtype=torch.uint8).pin_memory(),
+                        'pin_mask': torch.empty(self.batch, self.Ho, self.Wo, 4, dtype=torch.uint8).pin_memory(),
+                        'pin_label': torch.empty(self.batch, self.Ho, self.Wo, dtype=torch.uint8).pin_memory(),
+                        'pin_counts': torch.empty(self.batch, 4, dtype=torch.int32).pin_memory(),
+                        'pin_radii': torch.empty(self.batch, 4, 360, dtype=torch.int32).pin_memory(),
+                        'dev_frames': torch.empty(self.batch, Hs, Ws, 3, dtype=torch.uint8, device=self.device),
+                        'dev_mask': torch.empty_like(self.mask), 'dev_label': torch.empty_like(self.label),
+                        'dev_counts': torch.empty_like(self.counts),
+                        'dev_radii': torch.empty(self.batch, 4, 360, dtype=torch.int32, device=self.device),
+                        'ev_h2d': torch.cuda.Event(), 'ev_in_free': torch.cuda.Event(),
+                        'ev_out_ready': torch.cuda.Event(), 'ev_d2h': torch.cuda.Event(), 'used': False,
+                    })
+                self._copy_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            self._sets = sets
+        return self._sets
+
+    def stream_host(self, batches, copy: bool = True):
+        """Pipelined form of ``run_host`` over an iterable of host batches (uint8 (n <= batch, Hs, Ws, 3)):
+        the H2D copy of batch i+1 and the D2H copy of batch i-1 run on their own streams under the compute
+        of batch i (two sets of pinned and device staging buffers).  Yields host (mask, label, counts,
+        radii) per batch, in order.  With copy=False the arrays are views of pinned buffers that stay valid
+        until the generator has been advanced twice more."""
+        sets = self._stream_sets()
+        h2d, d2h = self._copy_streams
+        pending = []
+
+        def collect(k, n, with_radii):
+            S = sets[k]
+            S['ev_d2h'].synchronize()
+            out = [S['pin_mask'][:n].numpy(), S['pin_label'][:n].numpy(), S['pin_counts'][:n].numpy(),
+                   S['pin_radii'][:n].numpy() if with_radii else None]
+            if copy:
+                out = [o.copy() if o is not None else None for o in out]
+            return tuple(out)
+
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            for i, frames in enumerate(batches):
+                k = i % 2
+                S = sets[k]
+                n = frames.shape[0]
+                assert n <= self.batch and tuple(frames.shape[1:3]) == self.src_hw
+                if S['used']:
+                    S['ev_h2d'].synchronize()               # pinned input of batch i-2 has left the host
+                S['pin_frames'][:n].copy_(torch.from_numpy(frames))
+                with torch.cuda.stream(h2d):
+                    if S['used']:
+                        h2d.wait_event(S['ev_in_free'])     # batch i-2 has been moved out of the device staging buffer
+                    S['dev_frames'][:n].copy_(S['pin_frames'][:n], non_blocking=True)
+                    S['ev_h2d'].record(h2d)
+                cur.wait_event(S['ev_h2d'])
+                self.frames_dev[:n].copy_(S['dev_frames'][:n], non_blocking=True)
+                if n < self.batch:
+                    self.frames_dev[n:].zero_()
+                S['ev_in_free'].record(cur)
+                mask, label, counts, radii = self.run_device(self.frames_dev)
+                if S['used']:
+                    cur.wait_event(S['ev_d2h'])             # batch i-2's results have left the device staging buffers
+                S['dev_mask'][:n].copy_(mask[:n], non_blocking=True)
+                S['dev_label'][:n].copy_(label[:n], non_blocking=True)
+                S['dev_counts'][:n].copy_(counts[:n], non_blocking=True)
+                if radii is not None:
+                    S['dev_radii'][:n].copy_(radii[:n], non_blocking=True)
+                S['ev_out_ready'].record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(S['ev_out_ready'])
+                    S['pin_mask'][:n].copy_(S['dev_mask'][:n], non_blocking=True)
+                    S['pin_label'][:n].copy_(S['dev_label'][:n], non_blocking=True)
+                    S['pin_counts'][:n].copy_(S['dev_counts'][:n], non_blocking=True)
+                    if radii is not None:
+                        S['pin_radii'][:n].copy_(S['dev_radii'][:n], non_blocking=True)
+                    S['ev_d2h'].record(d2h)
+                S['used'] = True
+                pending.append((k, n, radii is not None))
+                if len(pending) == 2:
+                    yield collect(*pending.pop(0))
+            while pending:
+                yield collect(*pending.pop(0))
+

@@ -93,9 +93,9 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
     batch = min(batch_size, n)
     pipe = EnsemblePipeline(models, classes, output_size, dev, batch, src_hw=frames.shape[1:3],
                             thickness=quantities is not None)
-    for lo in range(0, n, batch):
-        hi = min(lo + batch, n)
-        mask, label, counts, radii = pipe.run_host(frames[lo:hi])
+    spans = [(lo, min(lo + batch, n)) for lo in range(0, n, batch)]
+    # copies of batch i+1 / i-1 overlap the compute of batch i (EnsemblePipeline.stream_host)
+    for (lo, hi), (mask, label, counts, radii) in zip(spans, pipe.stream_host(frames[lo:hi] for lo, hi in spans)):
         for i in range(lo, hi):
             for class_name in classes:
                 idx = CLASS_IDS[class_name] - 1

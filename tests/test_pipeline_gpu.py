@@ -85,6 +85,21 @@ def test_pipeline_postprocessing_is_exact_given_the_same_planes(model_pairs):
         assert np.array_equal(pipe.nets[d].x_nhwc.cpu().numpy(), want_in)
 
 
+def test_stream_host_equals_run_host(model_pairs):
+    """The pipelined host stream (double-buffered copies under compute) returns, batch by batch, exactly what
+    the synchronous run_host returns -- including a ragged last batch."""
+    _, ours = model_pairs
+    pipe = EnsemblePipeline(ours, CLASSES, [200, 200], 'cuda:0', 2, src_hw=(160, 160), thickness=True)
+    frames = synth.synthetic_frames(330, 7, 160)
+    spans = [(0, 2), (2, 4), (4, 6), (6, 7)]
+    want = [pipe.run_host(frames[lo:hi]) for lo, hi in spans]
+    got = list(pipe.stream_host(frames[lo:hi] for lo, hi in spans))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert np.array_equal(a, b)
+
+
 def test_predict_main_end_to_end(tmp_path, model_pairs):
     """src/predict.py main(): models_dir with config.json + weights.ckpt, PNG inputs, PNG + JSON outputs."""
     refs, _ = model_pairs
