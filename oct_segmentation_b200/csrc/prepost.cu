@@ -116,76 +116,75 @@ struct PostParams {
   const int* lut[4];
   long long img_stride[4];
   int S[4];
-  int order[4];
-  int n_order;
+  unsigned long long label_lut;  // 16 x 4 bits: label of every class-presence combination (bit c = class c present)
   int N, Ho, Wo;
   uint8_t* mask;
   uint8_t* label;
   int* counts;
 };
 
-// One thread = 4 consecutive output pixels: 16-byte mask store, 4-byte label store.
+// One thread = 4 consecutive output pixels of kPostRows rows: 16-byte mask store, 4-byte label store.
+// The kernel is issue-bound (ncu: 76 % issue-active at 125 instructions per pixel in its first form), so the
+// per-pixel work is pared down: per class one 16-byte read of the column table per quad and per pixel
+// LDG.U8 + min + multiply-add into the pixel's 4-class word; the label is a 16-entry table lookup on the
+// class-presence bits ((m * 0x01020408) >> 24); the four per-class counts ride in the four bytes of one
+// register (<= 4 px x kPostRows rows per thread) until the end.
 constexpr int kPostRows = 8;
 __global__ void __launch_bounds__(256) postprocess_kernel(const PostParams p) {
   __shared__ int sm_cnt[4];
+  __shared__ uint8_t sm_lab[16];
   if (threadIdx.x < 4) sm_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < 16) sm_lab[threadIdx.x] = static_cast<uint8_t>((p.label_lut >> (4 * threadIdx.x)) & 0xF);
   __syncthreads();
   const int Wq = (p.Wo + 3) >> 2;
   const int n = blockIdx.z;
-  int cnt[4] = {0, 0, 0, 0};
-  // a block walks kPostRows output rows: 8x fewer same-address count atomics, more loads in flight per block
+  uint32_t cntp = 0;  // byte c = pixels of class c seen by this thread
   const int y_end = min(p.Ho, (static_cast<int>(blockIdx.y) + 1) * kPostRows);
   for (int y = blockIdx.y * kPostRows; y < y_end; ++y)
-  for (int xq = blockIdx.x * blockDim.x + threadIdx.x; xq < Wq; xq += gridDim.x * blockDim.x) {
-    uint32_t m[4] = {0, 0, 0, 0};  // m[px] = 4 class bytes of pixel px
+    for (int xq = blockIdx.x * blockDim.x + threadIdx.x; xq < Wq; xq += gridDim.x * blockDim.x) {
+      uint32_t m[4] = {0, 0, 0, 0};  // m[px] = 4 class bytes of pixel px
+      const bool full = xq * 4 + 3 < p.Wo;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (!p.chan[c]) continue;
-      const int S = p.S[c];
-      const int sy = p.lut[c][y];
-      const uint8_t* row = p.chan[c] + static_cast<size_t>(n) * p.img_stride[c] + static_cast<size_t>(sy) * S;
-      const int* lx = p.lut[c] + p.Ho + xq * 4;
-      int sx[4];
-      if (xq * 4 + 3 < p.Wo && (reinterpret_cast<uintptr_t>(lx) & 15) == 0) {  // one 16-byte read of the column table
-        const int4 t = __ldg(reinterpret_cast<const int4*>(lx));
-        sx[0] = t.x, sx[1] = t.y, sx[2] = t.z, sx[3] = t.w;
-      } else {
+      for (int c = 0; c < 4; ++c) {
+        if (!p.chan[c]) continue;
+        const int S = p.S[c];
+        const int sy = __ldg(p.lut[c] + y);
+        const uint8_t* row = p.chan[c] + static_cast<size_t>(n) * p.img_stride[c] + static_cast<size_t>(sy) * S;
+        const int* lx = p.lut[c] + p.Ho + xq * 4;
+        int sx[4];
+        if (full && (reinterpret_cast<uintptr_t>(lx) & 15) == 0) {  // one 16-byte read of the column table
+          const int4 t = __ldg(reinterpret_cast<const int4*>(lx));
+          sx[0] = t.x, sx[1] = t.y, sx[2] = t.z, sx[3] = t.w;
+        } else {
 #pragma unroll
-        for (int px = 0; px < 4; ++px) sx[px] = (xq * 4 + px < p.Wo) ? lx[px] : -1;
+          for (int px = 0; px < 4; ++px) sx[px] = (xq * 4 + px < p.Wo) ? lx[px] : -1;
+        }
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          if (full || sx[px] >= 0) {
+            const uint32_t v = min(static_cast<uint32_t>(__ldg(row + sx[px])), 1u);
+            m[px] = v * (1u << (8 * c)) + m[px];
+          }
+        }
       }
+      cntp += m[0] + m[1] + m[2] + m[3];
+      uint32_t lab = 0;
 #pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        if (sx[px] >= 0) {
-          const uint32_t v = row[sx[px]] ? 1u : 0u;
-          m[px] |= v << (8 * c);
-          cnt[c] += v;
+      for (int px = 0; px < 4; ++px) lab |= static_cast<uint32_t>(sm_lab[(m[px] * 0x01020408u) >> 24]) << (8 * px);
+      const size_t pix = (static_cast<size_t>(n) * p.Ho + y) * p.Wo + xq * 4;
+      if (full && (p.Wo & 3) == 0) {
+        *reinterpret_cast<uint4*>(p.mask + pix * 4) = make_uint4(m[0], m[1], m[2], m[3]);
+        if (p.label) *reinterpret_cast<uint32_t*>(p.label + pix) = lab;
+      } else {
+        for (int px = 0; px < 4 && xq * 4 + px < p.Wo; ++px) {
+          reinterpret_cast<uint32_t*>(p.mask)[pix + px] = m[px];
+          if (p.label) p.label[pix + px] = (lab >> (8 * px)) & 0xff;
         }
       }
     }
-    uint32_t lab = 0;
-#pragma unroll
-    for (int px = 0; px < 4; ++px) {
-      uint32_t l = 0;
-      for (int k = 0; k < p.n_order; ++k) {  // later classes overwrite earlier ones
-        const int c = p.order[k];
-        if ((m[px] >> (8 * c)) & 1u) l = c + 1;
-      }
-      lab |= l << (8 * px);
-    }
-    const size_t pix = (static_cast<size_t>(n) * p.Ho + y) * p.Wo + xq * 4;
-    if (xq * 4 + 3 < p.Wo && (p.Wo & 3) == 0) {
-      *reinterpret_cast<uint4*>(p.mask + pix * 4) = make_uint4(m[0], m[1], m[2], m[3]);
-      if (p.label) *reinterpret_cast<uint32_t*>(p.label + pix) = lab;
-    } else {
-      for (int px = 0; px < 4 && xq * 4 + px < p.Wo; ++px) {
-        reinterpret_cast<uint32_t*>(p.mask)[pix + px] = m[px];
-        if (p.label) p.label[pix + px] = (lab >> (8 * px)) & 0xff;
-      }
-    }
-  }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    int v = cnt[c];
+    int v = static_cast<int>((cntp >> (8 * c)) & 0xffu);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sm_cnt[c], v);
@@ -265,10 +264,15 @@ extern "C" int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h
     p.img_stride[c] = h_img_stride ? h_img_stride[c] : static_cast<long long>(h_S[c]) * h_S[c];
     if (p.chan[c] && !p.lut[c]) return fail(OCTSEG_EINVAL, "postprocess: class %d has no LUT", c);
   }
-  for (int k = 0; k < 4; ++k) p.order[k] = k < n_order ? h_order[k] : 0;
   for (int k = 0; k < n_order; ++k)
-    if (p.order[k] < 0 || p.order[k] > 3) return fail(OCTSEG_EINVAL, "postprocess: bad class index in order");
-  p.n_order = n_order;
+    if (h_order[k] < 0 || h_order[k] > 3) return fail(OCTSEG_EINVAL, "postprocess: bad class index in order");
+  p.label_lut = 0;  // later classes in `order` overwrite earlier ones (src/data/utils.py:231-233)
+  for (unsigned idx = 0; idx < 16; ++idx) {
+    unsigned long long l = 0;
+    for (int k = 0; k < n_order; ++k)
+      if ((idx >> h_order[k]) & 1u) l = static_cast<unsigned long long>(h_order[k]) + 1;
+    p.label_lut |= l << (4 * idx);
+  }
   p.N = N;
   p.Ho = Ho;
   p.Wo = Wo;
