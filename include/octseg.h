@@ -106,9 +106,9 @@ typedef struct octseg_conv_desc {
   int32_t d2s;         /* depth-to-space bf16 output: > 0 = channels per output pixel; GEMM column c is
                           channel c % d2s of pixel (2y + (c/d2s)/2, 2x + (c/d2s)%2) of a tensor twice as
                           large as the tile grid (fused upsample / ConvTranspose in one pass)        */
-  int32_t halo;        /* 1 = halo-tile mode (needs nseg=1, phases=1, kc=64, mul=1, TH=16, TW=8, no per-image
+  int32_t halo;        /* 1 = halo-tile mode (needs nseg=1, phases=1, mul=1, TH=16, TW=8, no per-image
                           weights): one (TW+kw-1) x (TH+kh-1) halo box of A per channel chunk, the kh*kw taps are
-                          shifted views of it, and the channel tile's weights (kh*kw*cchunks*BN*128 bytes) stay
+                          shifted views of it, and the channel tile's weights (kh*kw*cchunks*BN*kc*2 bytes) stay
                           resident in shared memory; tiles are ordered channel tile slowest                */
 } octseg_conv_desc;
 

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t smemA = smem0;
   const uint32_t a_bytes = static_cast<uint32_t>(p.a_stage_bytes);
   const uint32_t smemB = smem0 + nst * a_bytes;
-  const uint32_t smemOut = smemB + (p.halo ? static_cast<uint32_t>(p.b_res_bytes) : nst * b_bytes);  // 2 x 16 KB epilogue staging
+  // 2 x 16 KB epilogue staging (1 KB aligned: its 128B swizzle is address based)
+  const uint32_t smemOut = smemB + (p.halo ? ((static_cast<uint32_t>(p.b_res_bytes) + 1023u) & ~1023u) : nst * b_bytes);
   const uint32_t smemBias = smemOut + 2 * kOutBytes;     // fp32 bias of every channel tile
   const uint32_t bars = smemBias + p.bias_floats * 4;    // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
@@ -387,15 +388,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int nb = sg.kh * sg.kw * sg.cchunks;
             mbar_arrive_expect_tx_if(leader, bar_bres, static_cast<uint32_t>(p.b_res_bytes));
             for (int i = 0; i < nb; ++i)
-              tma_load_3d_if(leader, smemB + static_cast<uint32_t>(i * p.BN * 128), &p.tmB[2], bar_bres, i * 64, brow, 0);
+              tma_load_3d_if(leader, smemB + static_cast<uint32_t>(i * p.BN * sg.kc * 2), &p.tmB[kc_index(sg.kc)], bar_bres,
+                             i * sg.kc, brow, 0);
           }
           const int h0 = tc.th * p.TH + sg.off_h[0], w0 = tc.tw * p.TW + sg.off_w[0];
           const int cbase = sg.c_per_tile * tc.n_tile;
-          const uint32_t tx_bytes = static_cast<uint32_t>((p.TH + sg.kh - 1) * (p.TW + sg.kw - 1) * 128);
+          const uint32_t tx_bytes = static_cast<uint32_t>((p.TH + sg.kh - 1) * (p.TW + sg.kw - 1) * sg.kc * 2);
           for (int cc = 0; cc < sg.cchunks; ++cc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             mbar_arrive_expect_tx_if(leader, bar_full + 8 * stage, tx_bytes);
-            tma_load_4d_if(leader, smemA + stage * a_bytes, &p.tmA[0], bar_full + 8 * stage, cbase + cc * 64, w0, h0, tc.n);
+            tma_load_4d_if(leader, smemA + stage * a_bytes, &p.tmA[0], bar_full + 8 * stage, cbase + cc * sg.kc, w0, h0, tc.n);
             if (++stage == nst) {
               stage = 0;
               phase ^= 1;
@@ -538,25 +540,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             bres_phase ^= 1;
           }
           const int pw = p.TW + sg.kw - 1;  // halo row pitch in pixels
-          // A: 8-pixel tile rows are the 8-row groups; group stride = one halo row (pw * 128 B)
-          uint64_t desc_a = make_kmajor_desc(0, 64);
-          desc_a = (desc_a & ~(0x3FFFull << 32)) | (static_cast<uint64_t>((pw * 128) >> 4) << 32);
-          const uint64_t desc_b = make_kmajor_desc(0, 64);
-          const uint32_t tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
+          const int rb = sg.kc * 2;         // bytes per pixel of a chunk = the swizzle span (32 / 64 / 128)
+          // A: 8-pixel tile rows are the 8-row groups; group stride = one halo row (pw * rb bytes)
+          uint64_t desc_a = make_kmajor_desc(0, sg.kc);
+          desc_a = (desc_a & ~(0x3FFFull << 32)) | (static_cast<uint64_t>((pw * rb) >> 4) << 32);
+          const uint64_t desc_b = make_kmajor_desc(0, sg.kc);
+          const uint32_t tile_bytes = static_cast<uint32_t>(p.BN * rb);
+          const int steps = sg.kc / 16;
           for (int cc = 0; cc < sg.cchunks; ++cc) {
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             const uint32_t a0 = smemA + stage * a_bytes;
             for (int ty = 0; ty < sg.kh; ++ty)
               for (int tx = 0; tx < sg.kw; ++tx) {
-                const uint64_t adesc = desc_a | ((a0 + static_cast<uint32_t>((ty * pw + tx) * 128)) >> 4);
+                const uint64_t adesc = desc_a | ((a0 + static_cast<uint32_t>((ty * pw + tx) * rb)) >> 4);
                 const uint64_t bdesc =
                     desc_b | ((smemB + static_cast<uint32_t>((ty * sg.kw + tx) * sg.cchunks + cc) * tile_bytes) >> 4);
-                tc_mma_bf16(leader, d_tmem, adesc, bdesc, idesc, accum);
-                tc_mma_bf16(leader, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                tc_mma_bf16(leader, d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                tc_mma_bf16(leader, d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-                accum = 1;
+                for (int t = 0; t < steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
+                  tc_mma_bf16(leader, d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
+                  accum = 1;
+                }
               }
             tc_commit(leader, bar_empty + 8 * stage);
             if (++stage == nst) {
@@ -890,10 +893,10 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
       delete pl;
       return fail(OCTSEG_EINVAL, "segment %d: wide boxes need kc=64, mul=1, TH=1, kw>=2 and TW+kw-1<=136", s);
     }
-    if (d->halo && (d->nseg != 1 || d->phases != 1 || sg.kc != 64 || sg.mul != 1 || sg.wide || d->TH != 16 || d->TW != 8 ||
+    if (d->halo && (d->nseg != 1 || d->phases != 1 || sg.mul != 1 || sg.wide || d->TH != 16 || d->TW != 8 ||
                     d->per_image_weights || sg.kh > 8 || sg.kw > 8)) {
       delete pl;
-      return fail(OCTSEG_EINVAL, "halo mode needs nseg=1, phases=1, kc=64, mul=1, TH=16, TW=8, shared weights");
+      return fail(OCTSEG_EINVAL, "halo mode needs nseg=1, phases=1, mul=1, TH=16, TW=8, shared weights");
     }
     const uint32_t box[4] = {static_cast<uint32_t>(sg.kc),
                              static_cast<uint32_t>(d->halo ? d->TW + sg.kw - 1 : (sg.wide ? d->TW + sg.kw - 1 : d->TW * sg.mul)),
@@ -1059,13 +1062,14 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   kp.a_stage_bytes = any_wide ? kABytesWide : kABytes;
   if (kp.halo) {
     const octseg_conv_seg& sg = d->seg[0];
-    kp.b_res_bytes = sg.kh * sg.kw * sg.cchunks * d->BN * 128;
+    kp.b_res_bytes = sg.kh * sg.kw * sg.cchunks * d->BN * sg.kc * 2;
     kp.b_stage_bytes = 0;  // the stages hold halo tiles only
-    kp.a_stage_bytes = ((d->TH + sg.kh - 1) * (d->TW + sg.kw - 1) * 128 + 1023) & ~1023;
+    kp.a_stage_bytes = ((d->TH + sg.kh - 1) * (d->TW + sg.kw - 1) * sg.kc * 2 + 1023) & ~1023;
   }
   const int stage_bytes = kp.a_stage_bytes + kp.b_stage_bytes;
   kp.bias_floats = (d->n_tiles_n * d->BN + 64 + 3) & ~3;
-  const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes - kp.bias_floats * 4 - kp.b_res_bytes;
+  const int b_res_region = (kp.b_res_bytes + 1023) & ~1023;
+  const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes - kp.bias_floats * 4 - b_res_region;
   int nst = budget / stage_bytes;
   if (nst > kMaxStages) nst = kMaxStages;
   if (nst < 2) {
@@ -1073,7 +1077,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     return fail(OCTSEG_EINVAL, "tile does not fit shared memory");
   }
   kp.nstages = nst;
-  pl->smem = static_cast<size_t>(nst) * stage_bytes + kp.b_res_bytes + 2 * kOutBytes + kp.bias_floats * 4 + 1024 + 512;
+  pl->smem = static_cast<size_t>(nst) * stage_bytes + b_res_region + 2 * kOutBytes + kp.bias_floats * 4 + 1024 + 512;
   int sms = octseg_sm_count();
   if (sms <= 0) {
     delete pl;

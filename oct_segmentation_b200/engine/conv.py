@@ -254,9 +254,9 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
     halo = 0
     if (HALO_TILES and len(segs) == 1 and phases == 1 and not transposed):
         sg = segs[0]
-        b_bytes = sg.kh * sg.kw * sg.cchunks * BN * 128
+        b_bytes = sg.kh * sg.kw * sg.cchunks * BN * sg.kc * 2
         cover = (-(-Hq // 16) * 16) * (-(-Wq // 8) * 8)
-        if (sg.kc == 64 and sg.mul == 1 and sg.kh * sg.kw >= 4 and sg.kh <= 7 and sg.kw <= 7 and b_bytes <= HALO_B_BYTES
+        if (sg.mul == 1 and sg.kh * sg.kw >= 4 and sg.kh <= 7 and sg.kw <= 7 and b_bytes <= HALO_B_BYTES
                 and Hq * Wq >= 0.75 * cover):
             halo, TH, TW = 1, 16, 8
     if TH == 1 and WIDE_BOXES and not halo:

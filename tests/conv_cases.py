@@ -185,4 +185,7 @@ CASES = [
     ConvCase('halo_res_before', [(64, 32, 32, False)], 64, res_mode='before_act'),
     ConvCase('halo_two_chunks', [(128, 32, 32, False)], 32, act='swish'),
     ConvCase('halo_asym_pad', [(64, 32, 32, False)], 48, pad=(0, 0), pad_br=(2, 2), act='none'),
+    ConvCase('halo_kc16_4x4_stem_like', [(12, 32, 40, False)], 64, k=4, pad=(2, 2), pad_br=(1, 1)),
+    ConvCase('halo_kc16_2x2_stem_like', [(12, 48, 32, False)], 32, k=2, pad=(0, 0), pad_br=(1, 1), act='swish'),
+    ConvCase('halo_kc32_two_chunks', [(40, 32, 32, False)], 64),
 ]
