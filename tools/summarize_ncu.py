@@ -48,7 +48,7 @@ def launches(src, dst, batch=None):
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f'| {k} | {a[0]} | {a[1] / 1e3:.3f} | {100 * a[1] / tot:.1f}% | {a[2] / max(a[0], 1) / 1e6:.2f} |')
     open(dst, 'w').write('\n'.join(out) + '\n')
-    tc = agg.get('octseg::conv_tc_kernel')
+    tc = next((v for k, v in agg.items() if k.split('::')[-1] == 'conv_tc_kernel'), None)
     if tc:
         json.dump({'kernel': 'conv_tc_kernel', 'launches': tc[0], 'dram_bytes_per_launch': tc[2] / tc[0],
                    'share_of_kernel_time': tc[1] / tot, 'source': src, 'batch': int(batch) if batch else None}, open(dst.replace('_summary.md', '_traffic.json'), 'w'))
