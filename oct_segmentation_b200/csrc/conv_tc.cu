@@ -13,10 +13,16 @@
 // Nearest-x2 upsample + 3x3 conv and ConvTranspose(k4,s2,p1) are executed as four output-phase
 // sub-problems on the half-resolution grid (weights pre-combined per phase on the host).
 //
-// One persistent CTA per SM, 18 warps: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2-17 = epilogue (4 per TMEM lane quarter, 16 columns of each 64-column chunk each: the
-// epilogue is instruction-latency bound, so it needs several warps per scheduler).  Accumulators are double-buffered in TMEM so
-// the epilogue of tile i overlaps the MMAs of tile i+1.
+// Halo-tile mode (narrow single-source k x k convs): 16 x 8 pixel tiles, ONE halo box of A per channel
+// chunk whose kh*kw taps are shifted views (UMMA group stride = halo row pitch), weights resident in
+// shared memory.  Row tiles (TH = 1) reuse one wide box per tap row the same way.
+//
+// One persistent CTA per SM, 18 warps: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (both run
+// converged and predicate only the issuing instruction on an elected lane, so their address arithmetic
+// stays on the uniform datapath), warps 2-17 = epilogue (4 per TMEM lane quarter, two chunk-alternating
+// groups of 8: the epilogue is instruction-latency bound, so it needs several warps per scheduler).
+// Accumulators form a ring of min(8, 512/BN) tiles in TMEM, so the epilogue of tile i overlaps the MMAs of
+// the following tiles.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
