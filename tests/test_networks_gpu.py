@@ -57,6 +57,20 @@ def test_every_launch_matches_torch_in_situ(key):
     assert not bad, f'{key}: launches off by more than 1e-2: {bad[:8]}'
 
 
+@pytest.mark.parametrize('key,H,W,N', [('LM', 96, 160, 3), ('VV', 224, 160, 3), ('FC_LC', 160, 224, 1)])
+def test_every_launch_matches_torch_in_situ_non_square(key, H, W, N):
+    """Same per-launch check on non-square inputs and odd batch sizes: feature maps such as 7x5, 14x10, 28x20
+    exercise partial tiles of every tiling mode (row tiles, 16x8 halo tiles, depthwise 8x16 / 4x32 tiles)."""
+    ref, ours = build_pair(key)
+    fr = synth.synthetic_frames(101, N, max(H, W))[:, :H, :W, ::-1].copy()
+    x = torch.from_numpy(fr).cuda()
+    net = CompiledNet(ours.model, N, H, W, x.device, 'u8', 'f32_nchw', use_graph=False, builder_cls=CheckedBuilder)
+    net.x_nhwc.copy_(x)
+    errs = net.builder.run_checked()
+    bad = [(n, e) for n, e in errs if not e <= 1e-2]
+    assert not bad, f'{key} {H}x{W}: launches off by more than 1e-2: {bad[:8]}'
+
+
 @pytest.mark.parametrize('key', ['LM', 'VV', 'FC_LC'])
 def test_network_matches_oracle(key):
     ref, ours = build_pair(key)
