@@ -207,6 +207,18 @@ int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h_S, const i
 int octseg_radial_thickness(const uint8_t* mask, int32_t N, int32_t H, int32_t W, const double* cos_sin,
                             int32_t* radii, void* stream);
 
+/* Overlay cosmetics of save_results (src/data/utils.py:209-230 + get_img_mask_union_pil,
+   src/models/smp/utils.py:203-213), one pass, bit-exact vs the reference's cv2 + PIL output:
+   per class in paint order: CLOSE(ellipse 5x5) -> rim = dilate7 & ~erode7 -> 5x5 binomial blur ->
+   two PIL alpha pastes (fill alpha = h_fill_lut[k], k = 256 * blur in 0..256; rim alpha = rim_alpha).
+   img, out: DEVICE uint8 [N][H][W][3] RGB; mask: DEVICE uint8 [N][H][W][4] (non-zero = class present,
+   4-byte aligned - the mask octseg_postprocess writes); h_order: HOST class channels (0..3) in
+   cfg.classes order; h_colors: HOST uint8 [4][3] RGB per class channel; h_fill_lut: HOST uint8 [257].
+   H, W >= 3. */
+int octseg_overlay(const uint8_t* img, const uint8_t* mask, uint8_t* out, int32_t N, int32_t H, int32_t W,
+                   const int32_t* h_order, int32_t n_order, const uint8_t* h_colors,
+                   const uint8_t* h_fill_lut, int32_t rim_alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

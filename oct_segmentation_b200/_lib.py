@@ -23,7 +23,7 @@ EXPORTS = [
     'octseg_conv_plan_create', 'octseg_conv_plan_destroy', 'octseg_conv_run',
     'octseg_stem_pack', 'octseg_maxpool3x3s2', 'octseg_dwconv', 'octseg_se_hidden',
     'octseg_se_gate', 'octseg_se_scale_weights', 'octseg_preprocess_resize_bgr', 'octseg_postprocess',
-    'octseg_radial_thickness',
+    'octseg_radial_thickness', 'octseg_overlay',
 ]
 
 
@@ -93,6 +93,9 @@ def load() -> C.CDLL:
         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.octseg_radial_thickness.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
+    lib.octseg_overlay.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
+                                   C.c_int32, C.c_void_p]
     for name in EXPORTS:
         if name not in ('octseg_last_error',):
             getattr(lib, name).restype = C.c_int

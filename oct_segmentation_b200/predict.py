@@ -133,18 +133,21 @@ def color_mask(mask: np.ndarray, classes: Sequence[str]) -> np.ndarray:
     return out
 
 
-def save_results(images, masks, images_name, classes, save_dir: str) -> None:
-    """Writes <name>_mask.png (colour mask, identical to the reference's) and <name>_overlay.png.
-    The overlay is a plain alpha blend of the colour mask; the reference's morphology/Gaussian
-    overlay cosmetics are a listed follow-up, not part of the hot path."""
-    for img, mask, name in zip(images, masks, images_name):
-        cm = color_mask(mask, classes)
-        Image.fromarray(cm).save(f'{save_dir}/{name}_mask.png')
-        base = np.array(img.convert('RGB')).astype(np.float32)
-        fg = (mask[:, :, [CLASS_IDS[c] - 1 for c in classes]] != 0).any(axis=2)
-        over = base.copy()
-        over[fg] = 0.75 * base[fg] + 0.25 * cm[fg].astype(np.float32)
-        Image.fromarray(over.astype(np.uint8)).save(f'{save_dir}/{name}_overlay.png')
+def save_results(images, masks, images_name, classes, save_dir: str, batch_size: int = 16, device: str = 'cuda') -> None:
+    """src/data/utils.py:195-235: writes <name>_mask.png (priority colour mask) and <name>_overlay.png
+    (closed + blurred fill and dilate/erode rim pasted per class over the frame).  The overlay is computed
+    by ``octseg_overlay`` in batches on the GPU, bit-exact vs the reference's cv2 + PIL arithmetic
+    (tests/golden/overlay_ref.npz); PNG encoding stays on the host (PIL), like the reference's."""
+    order = [CLASS_IDS[c] - 1 for c in classes]
+    dev = torch.device(device)
+    for lo in range(0, len(images), batch_size):
+        hi = min(lo + batch_size, len(images))
+        frames = np.stack([np.asarray(img.convert('RGB')) for img in images[lo:hi]])
+        m8 = np.stack([(np.asarray(m) != 0).astype(np.uint8) for m in masks[lo:hi]])
+        over = P.overlay(torch.from_numpy(frames).to(dev), torch.from_numpy(m8).to(dev), order).cpu().numpy()
+        for k in range(hi - lo):
+            Image.fromarray(over[k]).save(f'{save_dir}/{images_name[lo + k]}_overlay.png')
+            Image.fromarray(color_mask(masks[lo + k], classes)).save(f'{save_dir}/{images_name[lo + k]}_mask.png')
 
 
 def main(cfg) -> None:

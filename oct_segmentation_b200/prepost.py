@@ -140,6 +140,42 @@ def radial_thickness(mask: torch.Tensor) -> torch.Tensor:
     return radii
 
 
+CLASS_COLORS_RGB = {'Lumen': (228, 30, 199), 'Fibrous cap': (123, 171, 226), 'Lipid core': (125, 227, 127),
+                    'Vasa vasorum': (208, 2, 27)}   # src/data/utils.py:15-36 (== model.CLASS_COLORS_RGB, test-checked)
+
+
+@lru_cache(maxsize=1)
+def overlay_alpha_tables() -> Tuple[np.ndarray, int]:
+    """Alpha bytes of save_results' two pastes (src/data/utils.py:223-230, src/models/smp/utils.py:209-211):
+    ``uint8(blur * 64 * 0.85 * 255)`` for blur = k/256, k = 0..256, and ``uint8(1 * 255 * 0.85 * 255)``; the
+    reference's float -> uint8 cast of out-of-range values wraps (truncate, mod 256), kept as is."""
+    k = np.arange(257, dtype=np.float64)
+    fill = np.trunc(((k / 256.0) * 64) * 0.85 * 255).astype(np.int64) & 0xFF
+    rim = int(math.trunc(1.0 * 255 * 0.85 * 255)) & 0xFF
+    return fill.astype(np.uint8), rim
+
+
+def overlay(frames_rgb: torch.Tensor, mask: torch.Tensor, order: Sequence[int],
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """<name>_overlay.png of save_results for a batch.  frames_rgb: uint8 CUDA (N, H, W, 3) at the output size;
+    mask: uint8 CUDA (N, H, W, 4) as written by ``postprocess``; order: class channels in cfg.classes order."""
+    assert frames_rgb.is_cuda and frames_rgb.dtype == torch.uint8 and frames_rgb.is_contiguous()
+    assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+    N, H, W, _ = frames_rgb.shape
+    assert tuple(mask.shape) == (N, H, W, 4)
+    if out is None:
+        out = torch.empty_like(frames_rgb)
+    fill, rim = overlay_alpha_tables()
+    colors = np.array([CLASS_COLORS_RGB[n] for n in CLASS_NAMES], np.uint8)
+    ordr = (C.c_int32 * 4)(*(list(order) + [0] * (4 - len(order))))
+    with torch.cuda.device(frames_rgb.device):
+        _lib.check(_lib.load().octseg_overlay(frames_rgb.data_ptr(), mask.data_ptr(), out.data_ptr(), N, H, W, ordr,
+                                              len(order), colors.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                              fill.ctypes.data_as(C.POINTER(C.c_uint8)), rim, _lib.stream_ptr()),
+                   'overlay')
+    return out
+
+
 def dicom_ratio(h: int) -> int:
     return int(h * 150 // 1000)
 

@@ -7,6 +7,8 @@
                          src/data/convert_int_to_cv.py:96-108 == src/data/utils.py:231-233)
   demo_frame_small.npz : one real OCT frame (data/demo/input/001_1_007.png) downsampled to 250x250
                          by plain decimation, used as a realistic pre-processing input
+  overlay_ref.npz      : <name>_overlay.png / <name>_mask.png written BY THE REFERENCE'S OWN save_results
+                         (src/data/utils.py:195-235) for small frames + masks (shapes touching every border)
 """
 import ast
 import glob
@@ -96,6 +98,40 @@ def main():
             radii_sets.append(rr)
     np.savez_compressed(f'{OUT}/quantities_ref.npz', q=q, ratio=ratio, keep_idx=np.array(keep_idx),
                         radii_hits=np.stack(radii_sets).reshape(len(keep_idx), 4, 360))
+    # overlay cosmetics: run the reference's save_results itself
+    import tempfile
+    (union_fn,) = reference_functions(f'{REF}/src/models/smp/utils.py', ['get_img_mask_union_pil'])
+    consts = {}
+    tree = ast.parse(open(f'{REF}/src/data/utils.py').read())
+    for node in tree.body:
+        if isinstance(node, ast.Assign) and any(getattr(t, 'id', '') in ('CLASS_MAP', 'CLASS_COLORS_RGB', 'CLASS_IDS')
+                                                for t in node.targets):
+            exec(compile(ast.Module([node], []), 'utils.py', 'exec'), consts)
+    consts.update({'get_img_mask_union_pil': union_fn, 'tqdm': lambda it, **k: it})
+    (save_results,) = reference_functions(f'{REF}/src/data/utils.py', ['save_results'], extra=consts)
+    rng = np.random.default_rng(7)
+    cases = []
+    for (H, W), classes in (((96, 128), ['Lumen', 'Fibrous cap', 'Lipid core', 'Vasa vasorum']),
+                            ((50, 37), ['Vasa vasorum', 'Lumen']), ((64, 64), ['Lipid core', 'Fibrous cap', 'Lumen'])):
+        frame = small[:H, :W].copy() if small.shape[0] >= H and small.shape[1] >= W else rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        yy, xx = np.mgrid[:H, :W]
+        mask = np.zeros((H, W, 4))
+        mask[:, :, 0] = (yy - H / 2) ** 2 + (xx - W / 2) ** 2 < (H / 3) ** 2
+        mask[:, :, 1] = (yy - H / 3) ** 2 / 50 + (xx - 2 * W / 3) ** 2 / 300 < 1
+        mask[:, :, 2] = rng.random((H, W)) > 0.9
+        mask[:, :, 3] = (abs(yy - H * 0.7) < 3) & (xx > 5)
+        mask[0:4, 0:9, 0] = 1
+        mask[H - 3:, W - 6:, 1] = 1
+        mask[:, 0, 2] = 1
+        mask[0, :, 3] = 1
+        d = tempfile.mkdtemp()
+        save_results([Image.fromarray(frame)], [mask.copy()], ['x'], classes, d)
+        cases.append((frame, mask.astype(np.uint8), classes, np.array(Image.open(f'{d}/x_overlay.png')),
+                      np.array(Image.open(f'{d}/x_mask.png'))))
+    np.savez_compressed(f'{OUT}/overlay_ref.npz', n=len(cases),
+                        **{f'frame{i}': c[0] for i, c in enumerate(cases)}, **{f'mask{i}': c[1] for i, c in enumerate(cases)},
+                        **{f'classes{i}': np.array(c[2]) for i, c in enumerate(cases)},
+                        **{f'overlay{i}': c[3] for i, c in enumerate(cases)}, **{f'colormask{i}': c[4] for i, c in enumerate(cases)})
     print('wrote', os.listdir(OUT))
 
 

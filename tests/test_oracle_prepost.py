@@ -98,3 +98,34 @@ def test_quantities_from_counts_host_logic():
     assert not r['Lumen']['present'] and not r['Lipid core']['present']       # empty / full channel
     assert r['Fibrous cap']['present'] and r['Fibrous cap']['area'] == 2.0
     assert r['Vasa vasorum']['area'] == pow(12345 // 150, 0.5)
+
+
+def test_overlay_matches_reference_save_results_outputs():
+    """oracle.overlay / color_mask vs the PNGs the reference's own save_results (src/data/utils.py:195-235)
+    wrote for the same frames and masks (tests/golden/make_golden.py), bit for bit."""
+    d = np.load(os.path.join(G, 'overlay_ref.npz'))
+    for i in range(int(d['n'])):
+        classes = [str(c) for c in d[f'classes{i}']]
+        got = R.overlay(d[f'frame{i}'], d[f'mask{i}'], classes)
+        assert np.array_equal(got, d[f'overlay{i}']), f'case {i}: {(got != d[f"overlay{i}"]).any(axis=2).sum()} pixels differ'
+        assert np.array_equal(R.color_mask(d[f'mask{i}'], classes), d[f'colormask{i}'])
+
+
+def test_overlay_building_blocks_match_cv2_and_numpy():
+    assert np.array_equal(cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5)), R.ELLIPSE5)
+    assert np.array_equal(cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (7, 7)), R.ELLIPSE7)
+    assert np.allclose(cv2.getGaussianKernel(5, 0).ravel() * 16, [1, 4, 6, 4, 1])
+    rng = np.random.default_rng(3)
+    m = (rng.random((40, 52)) > 0.6).astype(np.float64)
+    closed = cv2.morphologyEx(m, cv2.MORPH_CLOSE, R.ELLIPSE5)
+    assert np.array_equal(closed != 0, R._morph(R._morph(m != 0, R.ELLIPSE5, True), R.ELLIPSE5, False))
+    assert np.array_equal(cv2.dilate(m, R.ELLIPSE7) != 0, R._morph(m != 0, R.ELLIPSE7, True))
+    assert np.array_equal(cv2.erode(m, R.ELLIPSE7) != 0, R._morph(m != 0, R.ELLIPSE7, False))
+    fill, rim = R.overlay_alpha_tables()
+    k = np.arange(257, dtype=np.float64)
+    with np.errstate(invalid='ignore'):
+        assert np.array_equal(fill, (((k / 256.0) * 64) * 0.85 * 255).astype('uint8'))   # numpy's wrapping cast (x86)
+    assert rim == 231 and fill[256] == 48                                               # SURVEY.md section 8, row R4
+    # the product's host tables are the oracle's
+    pf, pr = P.overlay_alpha_tables()
+    assert np.array_equal(pf, fill) and pr == rim

@@ -125,3 +125,16 @@ def test_predict_main_end_to_end(tmp_path, model_pairs):
         assert (save_dir / f'frame_{i}_overlay.png').exists()
     q = json.load(open(save_dir / 'quantities.json'))
     assert set(q) == {'frame_0', 'frame_1'} and set(q['frame_0']) == set(CLASSES)
+
+
+def test_save_results_writes_the_reference_pngs(tmp_path):
+    """predict.save_results (same arguments as src/data/utils.py:195) on the frames + float64 masks the
+    reference's own save_results was run on (tests/golden/make_golden.py): both PNGs identical."""
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'overlay_ref.npz'))
+    for i in range(int(d['n'])):
+        classes = [str(c) for c in d[f'classes{i}']]
+        pred.save_results([Image.fromarray(d[f'frame{i}'])] * 3, [d[f'mask{i}'].astype(np.float64)] * 3,
+                          ['a', 'b', 'c'], classes, str(tmp_path), batch_size=2)
+        for name in 'abc':
+            assert np.array_equal(np.array(Image.open(tmp_path / f'{name}_overlay.png')), d[f'overlay{i}'])
+            assert np.array_equal(np.array(Image.open(tmp_path / f'{name}_mask.png')), d[f'colormask{i}'])

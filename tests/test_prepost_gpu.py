@@ -117,3 +117,55 @@ def test_postprocess_full_size_properties():
     assert torch.equal(label, want)
     lut = torch.from_numpy(P.nearest_table(512, Ho)).cuda().long()
     assert torch.equal(mask[..., 0], planes[0][:, lut][:, :, lut])
+
+
+def test_overlay_matches_reference_save_results_outputs():
+    """octseg_overlay vs the <name>_overlay.png the reference's own save_results wrote
+    (src/data/utils.py:195-235; tests/golden/make_golden.py), bit for bit."""
+    d = np.load(os.path.join(G, 'overlay_ref.npz'))
+    for i in range(int(d['n'])):
+        order = [R.CLASS_IDS[str(c)] - 1 for c in d[f'classes{i}']]
+        got = P.overlay(torch.from_numpy(d[f'frame{i}'][None].copy()).cuda(),
+                        torch.from_numpy(d[f'mask{i}'][None].copy()).cuda(), order)[0].cpu().numpy()
+        ref = d[f'overlay{i}']
+        assert np.array_equal(got, ref), f'case {i}: {(got != ref).any(axis=2).sum()} pixels differ'
+
+
+@pytest.mark.parametrize('H,W,N', [(3, 3, 1), (8, 5, 2), (33, 70, 3), (257, 130, 2)])
+def test_overlay_bit_exact_vs_oracle_ragged_sizes(H, W, N):
+    """Tile borders, images smaller than one tile, random speckle + blobs, non-{0,1} mask bytes, class subsets."""
+    rng = np.random.default_rng(H * 1000 + W)
+    frames = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    mask = (rng.random((N, H, W, 4)) > 0.8).astype(np.uint8) * rng.integers(1, 256, (N, H, W, 4), dtype=np.uint8)
+    yy, xx = np.mgrid[:H, :W]
+    mask[:, :, :, 0] |= ((yy - H / 2) ** 2 + (xx - W / 2) ** 2 < (min(H, W) / 3) ** 2).astype(np.uint8)
+    for order in ([0, 1, 2, 3], [3, 0], [2], []):
+        got = P.overlay(torch.from_numpy(frames).cuda(), torch.from_numpy(mask).cuda(), order).cpu().numpy()
+        names = [R.CLASS_NAMES[c] for c in order]
+        for n in range(N):
+            assert np.array_equal(got[n], R.overlay(frames[n], mask[n], names)), (order, n)
+
+
+def test_overlay_full_size_properties():
+    """1000 x 1000 (configs/predict.yaml output_size): an empty mask leaves the frame untouched, a full mask
+    gives the closed-form double paste everywhere, and painting is local (pixels > 7 away from any object
+    keep the frame value)."""
+    rng = np.random.default_rng(11)
+    H = W = 1000
+    frames = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    x = torch.from_numpy(frames).cuda()
+    empty = torch.zeros(2, H, W, 4, dtype=torch.uint8, device='cuda')
+    assert torch.equal(P.overlay(x, empty, [0, 1, 2, 3]), x)
+    full = torch.zeros(2, H, W, 4, dtype=torch.uint8, device='cuda')
+    full[..., 0] = 1
+    fill, rim = P.overlay_alpha_tables()
+    want = R.pil_paste(frames, R.CLASS_COLORS_RGB['Lumen'], np.full((2, H, W), fill[256]))   # no rim: erode == 1
+    assert np.array_equal(P.overlay(x, full, [0]).cpu().numpy(), want)
+    m = np.zeros((2, H, W, 4), np.uint8)
+    m[:, 400:600, 300:500, 3] = 1
+    m[:, 0:20, 980:1000, 1] = 1
+    got = P.overlay(x, torch.from_numpy(m).cuda(), [0, 1, 2, 3]).cpu().numpy()
+    far = cv2.dilate(m.any(axis=3)[0].astype(np.uint8), np.ones((15, 15), np.uint8)) == 0
+    assert np.array_equal(got[0][far], frames[0][far]) and (got[0][~far] != frames[0][~far]).any()
+    for n in range(2):
+        assert np.array_equal(got[n], R.overlay(frames[n], m[n], R.CLASS_NAMES))
