@@ -179,6 +179,14 @@ int octseg_preprocess_resize_bgr(const uint8_t* src /* [N][Hs][Ws][3] RGB */, in
                                  const int32_t* xofs, const int16_t* xalpha, const int32_t* yofs,
                                  const int16_t* ybeta, int32_t area_fast_2x, void* stream);
 
+/* Grayscale extension ("grayscale-to-3ch"; the reference replicates channels only in
+   dataset prep, src/data/utils.py:111): src is uint8 [N][Hs][Ws] and the resized plane is written to all three
+   channels of dst -- identical to octseg_preprocess_resize_bgr on the channel-replicated frame. */
+int octseg_preprocess_resize_gray(const uint8_t* src /* [N][Hs][Ws] */, int32_t N, int32_t Hs,
+                                 int32_t Ws, uint8_t* dst /* [N][S][S][3] BGR */, int32_t S,
+                                 const int32_t* xofs, const int16_t* xalpha, const int32_t* yofs,
+                                 const int16_t* ybeta, int32_t area_fast_2x, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Post-processing: threshold (model.py:195) + cv2.resize INTER_NEAREST (predict.py:92-96) +
  * class routing (predict.py:97-100, MODELS_META) + priority label map (data/utils.py:231-233)
@@ -218,6 +226,12 @@ int octseg_radial_thickness(const uint8_t* mask, int32_t N, int32_t H, int32_t W
 int octseg_overlay(const uint8_t* img, const uint8_t* mask, uint8_t* out, int32_t N, int32_t H, int32_t W,
                    const int32_t* h_order, int32_t n_order, const uint8_t* h_colors,
                    const uint8_t* h_fill_lut, int32_t rim_alpha, void* stream);
+
+/* K-way probability averaging (north-star "ensemble averaging"; opt-in generalisation of the reference's
+   per-class routing): out[i] = (1/K * sum_k sigmoid(logits[k][i])) > 0.5 ? 1 : 0 in fp32.
+   K = 1 is `y.sigmoid() > 0.5` (src/models/smp/model.py:195).  h_logits: HOST array of K (1..8) DEVICE
+   pointers to fp32 tensors of n elements each (16-byte aligned); out: DEVICE uint8 [n] (4-byte aligned). */
+int octseg_fold_average_threshold(const float* const* h_logits, int32_t K, int64_t n, uint8_t* out, void* stream);
 
 #ifdef __cplusplus
 }

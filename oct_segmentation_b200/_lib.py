@@ -23,7 +23,8 @@ EXPORTS = [
     'octseg_conv_plan_create', 'octseg_conv_plan_destroy', 'octseg_conv_run',
     'octseg_stem_pack', 'octseg_maxpool3x3s2', 'octseg_dwconv', 'octseg_se_hidden',
     'octseg_se_gate', 'octseg_se_scale_weights', 'octseg_preprocess_resize_bgr', 'octseg_postprocess',
-    'octseg_radial_thickness', 'octseg_overlay',
+    'octseg_radial_thickness', 'octseg_overlay', 'octseg_preprocess_resize_gray',
+    'octseg_fold_average_threshold',
 ]
 
 
@@ -87,6 +88,7 @@ def load() -> C.CDLL:
     lib.octseg_preprocess_resize_bgr.argtypes = [
         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.octseg_preprocess_resize_gray.argtypes = lib.octseg_preprocess_resize_bgr.argtypes
     lib.octseg_postprocess.argtypes = [
         C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
         C.POINTER(C.c_int32), C.c_int32,
@@ -96,6 +98,7 @@ def load() -> C.CDLL:
     lib.octseg_overlay.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
                                    C.c_int32, C.c_void_p]
+    lib.octseg_fold_average_threshold.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         if name not in ('octseg_last_error',):
             getattr(lib, name).restype = C.c_int

@@ -3,6 +3,7 @@
 //   postprocess: predict.py:92-100 + data/utils.py:231-233 + analysis.py:199
 //   thickness  : calculate_object_thickness (src/app/tools/analysis.py:60-130)
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 
 #include "common.h"
@@ -25,13 +26,16 @@ __device__ __forceinline__ void stage_row(uint8_t* dst, const uint8_t* __restric
 // One block per destination row: its two source rows are staged in shared memory with 16-byte loads,
 // a thread produces 4 destination pixels (12 bytes, written as three 32-bit words, BGR order) from
 // byte reads of the staged rows and one 16-byte read of each coefficient table.
+// CS = source channels: 3 (RGB, swapped to BGR) or 1 (grayscale, replicated into the three output channels: the
+// documented extension of SURVEY.md section 8a -- resizing a replicated frame == replicating the resized plane).
 constexpr int kPreThreads = 256;
+template <int CS>
 __global__ void __launch_bounds__(kPreThreads) preprocess_resize_bgr_kernel(
     const uint8_t* __restrict__ src, int Hs, int Ws, uint8_t* __restrict__ dst, int S, const int* __restrict__ xofs,
     const short* __restrict__ xalpha, const int* __restrict__ yofs, const short* __restrict__ ybeta, int area2x) {
   extern __shared__ __align__(16) uint8_t rows[];  // [2][row_pitch]
   const int dy = blockIdx.x, n = blockIdx.y;
-  const int row_bytes = Ws * 3, pitch = (row_bytes + 15) & ~15;
+  const int row_bytes = Ws * CS, pitch = (row_bytes + 15) & ~15;
   const uint8_t* img = src + static_cast<size_t>(n) * Hs * row_bytes;
   int y0, y1, b0 = 0, b1 = 0;
   if (area2x) {  // cv2 switches INTER_LINEAR to the fast 2x2 area average when both scales are exactly 2
@@ -81,22 +85,22 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_resize_bgr_kernel(
       const int dx = min(4 * q + p, S - 1);
       uint8_t v[3];
       if (area2x) {
-        const uint8_t* p0 = r0 + 6 * dx;
-        const uint8_t* p1 = r1 + 6 * dx;
+        const uint8_t* p0 = r0 + 2 * CS * dx;
+        const uint8_t* p1 = r1 + 2 * CS * dx;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = static_cast<uint8_t>((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
+        for (int c = 0; c < CS; ++c) v[c] = static_cast<uint8_t>((p0[c] + p0[CS + c] + p1[c] + p1[CS + c] + 2) >> 2);
       } else {
-        const int x0 = sx[p] * 3, x1 = min(sx[p] + 1, Ws - 1) * 3;
+        const int x0 = sx[p] * CS, x1 = min(sx[p] + 1, Ws - 1) * CS;
         const int a0 = al[2 * p], a1 = al[2 * p + 1];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < CS; ++c) {
           const int h0 = r0[x0 + c] * a0 + r0[x1 + c] * a1;
           const int h1 = r1[x0 + c] * a0 + r1[x1 + c] * a1;
           v[c] = static_cast<uint8_t>((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
         }
       }
-      o[3 * p] = v[2];  // RGB -> BGR
-      o[3 * p + 1] = v[1];
+      o[3 * p] = v[CS - 1];  // RGB -> BGR
+      o[3 * p + 1] = v[CS / 2];
       o[3 * p + 2] = v[0];
     }
     if (vec) {
@@ -231,24 +235,84 @@ __global__ void __launch_bounds__(256) radial_thickness_kernel(const uint8_t* __
   if (lane == 0) radii[(static_cast<size_t>(n) * 4 + cls) * 360 + ray] = found ? current : 0;
 }
 
+// K-way probability averaging (north-star "ensemble averaging"; opt-in generalisation, SURVEY.md section 8a:
+// the reference routes one model per class, src/predict.py:23-28 -- K = 1 is its `sigmoid(y) > 0.5`,
+// src/models/smp/model.py:195):  out = (1/K * sum_k sigmoid(logit_k)) > 0.5  over K same-shaped fp32 logit tensors.
+// HBM-bound: 4K bytes in + 1 byte out per element; one thread = 4 elements (16-byte loads, 4-byte store),
+// the K loads of a thread are independent.
+constexpr int kMaxFolds = 8;
+struct FoldParams {
+  const float* logits[kMaxFolds];
+  uint8_t* out;
+  long long n;
+  int K;
+  float inv_k;
+};
+
+__device__ __forceinline__ float sigmoid_f32(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256) fold_average_threshold_kernel(const FoldParams p) {
+  const long long quads = p.n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < quads; q += stride) {
+    float4 v[kMaxFolds];
+#pragma unroll
+    for (int k = 0; k < kMaxFolds; ++k)
+      if (k < p.K) v[k] = __ldcs(reinterpret_cast<const float4*>(p.logits[k]) + q);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxFolds; ++k)
+      if (k < p.K) {
+        s0 += sigmoid_f32(v[k].x);
+        s1 += sigmoid_f32(v[k].y);
+        s2 += sigmoid_f32(v[k].z);
+        s3 += sigmoid_f32(v[k].w);
+      }
+    const uint32_t w = (s0 * p.inv_k > 0.5f ? 1u : 0u) | (s1 * p.inv_k > 0.5f ? 0x100u : 0u) |
+                       (s2 * p.inv_k > 0.5f ? 0x10000u : 0u) | (s3 * p.inv_k > 0.5f ? 0x1000000u : 0u);
+    reinterpret_cast<uint32_t*>(p.out)[q] = w;
+  }
+  // ragged tail (n % 4 elements)
+  if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
+    const long long i = (quads << 2) + threadIdx.x;
+    float s = 0.f;
+    for (int k = 0; k < p.K; ++k) s += sigmoid_f32(p.logits[k][i]);
+    p.out[i] = s * p.inv_k > 0.5f ? 1 : 0;
+  }
+}
+
 }  // namespace octseg
 
 using namespace octseg;
+
+template <int CS>
+static int launch_preprocess(const uint8_t* src, int32_t N, int32_t Hs, int32_t Ws, uint8_t* dst, int32_t S,
+                             const int32_t* xofs, const int16_t* xalpha, const int32_t* yofs, const int16_t* ybeta,
+                             int32_t area_fast_2x, void* stream) {
+  if (!src || !dst) return fail(OCTSEG_EINVAL, "preprocess: null buffer");
+  if (!area_fast_2x && (!xofs || !xalpha || !yofs || !ybeta)) return fail(OCTSEG_EINVAL, "preprocess: null LUT");
+  if (N <= 0 || S <= 0) return OCTSEG_OK;
+  if (N > 65535) return fail(OCTSEG_EINVAL, "preprocess: at most 65535 frames per call");
+  const size_t smem = 2 * static_cast<size_t>((Ws * CS + 15) & ~15);
+  if (smem > 48 * 1024) return fail(OCTSEG_EINVAL, "preprocess: source rows of %d pixels do not fit shared memory", Ws);
+  dim3 grid(S, N);
+  preprocess_resize_bgr_kernel<CS><<<grid, kPreThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      src, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x);
+  return check_launch("preprocess_resize_bgr_kernel");
+}
 
 extern "C" int octseg_preprocess_resize_bgr(const uint8_t* src, int32_t N, int32_t Hs, int32_t Ws, uint8_t* dst,
                                             int32_t S, const int32_t* xofs, const int16_t* xalpha,
                                             const int32_t* yofs, const int16_t* ybeta, int32_t area_fast_2x,
                                             void* stream) {
-  if (!src || !dst) return fail(OCTSEG_EINVAL, "preprocess: null buffer");
-  if (!area_fast_2x && (!xofs || !xalpha || !yofs || !ybeta)) return fail(OCTSEG_EINVAL, "preprocess: null LUT");
-  if (N <= 0 || S <= 0) return OCTSEG_OK;
-  if (N > 65535) return fail(OCTSEG_EINVAL, "preprocess: at most 65535 frames per call");
-  const size_t smem = 2 * static_cast<size_t>((Ws * 3 + 15) & ~15);
-  if (smem > 48 * 1024) return fail(OCTSEG_EINVAL, "preprocess: source rows of %d pixels do not fit shared memory", Ws);
-  dim3 grid(S, N);
-  preprocess_resize_bgr_kernel<<<grid, kPreThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      src, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x);
-  return check_launch("preprocess_resize_bgr_kernel");
+  return launch_preprocess<3>(src, N, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x, stream);
+}
+
+extern "C" int octseg_preprocess_resize_gray(const uint8_t* src, int32_t N, int32_t Hs, int32_t Ws, uint8_t* dst,
+                                             int32_t S, const int32_t* xofs, const int16_t* xalpha,
+                                             const int32_t* yofs, const int16_t* ybeta, int32_t area_fast_2x,
+                                             void* stream) {
+  return launch_preprocess<1>(src, N, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x, stream);
 }
 
 extern "C" int octseg_postprocess(const uint8_t* const* h_chan, const int32_t* h_S, const int64_t* h_img_stride,
@@ -294,4 +358,26 @@ extern "C" int octseg_radial_thickness(const uint8_t* mask, int32_t N, int32_t H
   dim3 grid(45, 4, N);
   radial_thickness_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, H, W, cos_sin, radii, max_radius);
   return check_launch("radial_thickness_kernel");
+}
+
+extern "C" int octseg_fold_average_threshold(const float* const* h_logits, int32_t K, int64_t n, uint8_t* out,
+                                             void* stream) {
+  if (!h_logits || !out) return fail(OCTSEG_EINVAL, "fold_average: null argument");
+  if (K < 1 || K > kMaxFolds) return fail(OCTSEG_EINVAL, "fold_average: K must be in 1..%d", kMaxFolds);
+  if (n <= 0) return OCTSEG_OK;
+  FoldParams p;
+  for (int k = 0; k < kMaxFolds; ++k) {
+    p.logits[k] = k < K ? h_logits[k] : nullptr;
+    if (k < K && (!h_logits[k] || (reinterpret_cast<uintptr_t>(h_logits[k]) & 15)))
+      return fail(OCTSEG_EINVAL, "fold_average: logits[%d] must be a 16-byte aligned device pointer", k);
+  }
+  if (reinterpret_cast<uintptr_t>(out) & 3) return fail(OCTSEG_EINVAL, "fold_average: out must be 4-byte aligned");
+  p.out = out;
+  p.n = n;
+  p.K = K;
+  p.inv_k = 1.0f / static_cast<float>(K);
+  const long long quads = n >> 2;
+  const int blocks = static_cast<int>(std::min<long long>(std::max<long long>((quads + 255) / 256, 1), 148LL * 8));
+  fold_average_threshold_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("fold_average_threshold_kernel");
 }

@@ -73,18 +73,21 @@ def _cos_sin(device: str) -> torch.Tensor:
 
 def preprocess(frames_rgb: torch.Tensor, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """frames_rgb: uint8 CUDA tensor (N, Hs, Ws, 3) -> uint8 (N, S, S, 3) BGR, bit-exact vs
-    cv2.resize(cv2.cvtColor(img, COLOR_RGB2BGR), (S, S))."""
+    cv2.resize(cv2.cvtColor(img, COLOR_RGB2BGR), (S, S)).  Grayscale frames, (N, Hs, Ws) or (N, Hs, Ws, 1), are
+    replicated into the three channels (== the same call on np.repeat(frame[..., None], 3, -1))."""
     assert frames_rgb.is_cuda and frames_rgb.dtype == torch.uint8 and frames_rgb.is_contiguous()
-    N, Hs, Ws, _ = frames_rgb.shape
+    gray = frames_rgb.dim() == 3 or frames_rgb.shape[3] == 1
+    assert gray or (frames_rgb.dim() == 4 and frames_rgb.shape[3] == 3), 'frames must have 1 or 3 channels'
+    N, Hs, Ws = frames_rgb.shape[:3]
     if out is None:
         out = torch.empty(N, S, S, 3, dtype=torch.uint8, device=frames_rgb.device)
     lib = _lib.load()
     area2x = int(Hs == 2 * S and Ws == 2 * S)
     xo, xa, yo, yb = _resize_luts(Hs, Ws, S, str(frames_rgb.device))
+    fn = lib.octseg_preprocess_resize_gray if gray else lib.octseg_preprocess_resize_bgr
     with torch.cuda.device(frames_rgb.device):
-        _lib.check(lib.octseg_preprocess_resize_bgr(frames_rgb.data_ptr(), N, Hs, Ws, out.data_ptr(), S,
-                                                    xo.data_ptr(), xa.data_ptr(), yo.data_ptr(), yb.data_ptr(),
-                                                    area2x, _lib.stream_ptr()), 'preprocess_resize_bgr')
+        _lib.check(fn(frames_rgb.data_ptr(), N, Hs, Ws, out.data_ptr(), S, xo.data_ptr(), xa.data_ptr(), yo.data_ptr(),
+                      yb.data_ptr(), area2x, _lib.stream_ptr()), 'preprocess_resize')
     return out
 
 
@@ -173,6 +176,23 @@ def overlay(frames_rgb: torch.Tensor, mask: torch.Tensor, order: Sequence[int],
                                               len(order), colors.ctypes.data_as(C.POINTER(C.c_uint8)),
                                               fill.ctypes.data_as(C.POINTER(C.c_uint8)), rim, _lib.stream_ptr()),
                    'overlay')
+    return out
+
+
+def fold_average_threshold(logits: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K-way probability averaging (opt-in; the reference routes one model per class): logits = K same-shaped fp32
+    CUDA tensors -> uint8 {0,1} tensor of that shape, (mean_k sigmoid(logit_k)) > 0.5.  K = 1 is model.py:195."""
+    K = len(logits)
+    x0 = logits[0]
+    for x in logits:
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape == x0.shape
+    if out is None:
+        out = torch.empty(x0.shape, dtype=torch.uint8, device=x0.device)
+    assert out.is_contiguous() and out.dtype == torch.uint8 and out.shape == x0.shape
+    ptrs = (C.c_void_p * K)(*[x.data_ptr() for x in logits])
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.load().octseg_fold_average_threshold(ptrs, K, x0.numel(), out.data_ptr(), _lib.stream_ptr()),
+                   'fold_average_threshold')
     return out
 
 

@@ -129,3 +129,20 @@ def test_overlay_building_blocks_match_cv2_and_numpy():
     # the product's host tables are the oracle's
     pf, pr = P.overlay_alpha_tables()
     assert np.array_equal(pf, fill) and pr == rim
+
+
+def test_fold_average_oracle_reduces_to_the_reference_threshold():
+    """K = 1: mean sigmoid > 0.5 == `y.sigmoid() > 0.5` (src/models/smp/model.py:195) == y > 0; K folds: majority
+    of confident folds wins, symmetric logits tie at exactly 0.5 -> 0."""
+    import torch
+    y = (np.random.default_rng(0).standard_normal((2, 1, 16, 16)) * 4).astype(np.float32)
+    m, _ = R.fold_average_threshold([y])
+    assert np.array_equal(m, (torch.from_numpy(y).sigmoid() > 0.5).numpy().astype(np.uint8))
+    assert np.array_equal(m, (y > 0).astype(np.uint8))
+    a = np.array([10.0, 10.0, -10.0, 2.0], np.float32)
+    b = np.array([10.0, -10.0, -10.0, -2.0], np.float32)
+    c = np.array([-10.0, -10.0, 10.0, 0.5], np.float32)
+    m, margin = R.fold_average_threshold([a, b, c])
+    assert m.tolist() == [1, 0, 0, 1]
+    m2, margin2 = R.fold_average_threshold([a[3:], b[3:]])
+    assert m2.tolist() == [0] and margin2[0] < 1e-12

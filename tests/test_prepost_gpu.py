@@ -169,3 +169,30 @@ def test_overlay_full_size_properties():
     assert np.array_equal(got[0][far], frames[0][far]) and (got[0][~far] != frames[0][~far]).any()
     for n in range(2):
         assert np.array_equal(got[n], R.overlay(frames[n], m[n], R.CLASS_NAMES))
+
+
+@pytest.mark.parametrize('src,dst', [(250, 96), (250, 125), (512, 512), (1000, 896), (1024, 512), (37, 64)])
+def test_preprocess_grayscale_equals_replicated_frame(src, dst):
+    """Grayscale extension: (N, H, W) and (N, H, W, 1) frames == cv2 on the replicated frame."""
+    rng = np.random.default_rng(src * 7 + dst)
+    g = rng.integers(0, 256, (2, src, src + 6), dtype=np.uint8)
+    a = P.preprocess(torch.from_numpy(g).cuda(), dst).cpu().numpy()
+    b = P.preprocess(torch.from_numpy(g[..., None].copy()).cuda(), dst).cpu().numpy()
+    for n in range(2):
+        want = cv2.resize(cv2.cvtColor(np.repeat(g[n][..., None], 3, axis=2), cv2.COLOR_RGB2BGR), (dst, dst))
+        assert np.array_equal(a[n], want) and np.array_equal(b[n], want)
+
+
+@pytest.mark.parametrize('K,shape', [(1, (2, 1, 64, 64)), (3, (2, 2, 96, 96)), (5, (1, 1, 33, 7)), (8, (3, 2, 32, 32))])
+def test_fold_average_threshold_vs_oracle(K, shape):
+    """K-way probability averaging (opt-in): equal to the float64 oracle wherever |mean - 0.5| exceeds the
+    fp32 rounding band (1e-6); K = 1 is exactly `y > 0` (== sigmoid(y) > 0.5, src/models/smp/model.py:195)."""
+    rng = np.random.default_rng(K)
+    logits = [(rng.standard_normal(shape) * 3).astype(np.float32) for _ in range(K)]
+    logits[0].flat[:5] = [0.0, -0.0, 1e-3, -1e-3, 80.0]
+    got = P.fold_average_threshold([torch.from_numpy(x).cuda() for x in logits]).cpu().numpy()
+    want, margin = R.fold_average_threshold(logits)
+    sure = margin > 1e-6
+    assert sure.mean() > 0.999 and np.array_equal(got[sure], want[sure])
+    if K == 1:
+        assert np.array_equal(got, (logits[0] > 0).astype(np.uint8))

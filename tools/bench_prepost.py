@@ -60,6 +60,12 @@ def main():
                           frac_of_hbm=round(b / ms / 1e6 / peak, 3))), flush=True)
     ms = timeit([lambda i=i: prepost.radial_thickness(masks[i]) for i in range(sets)])
     print(json.dumps(dict(kernel='radial_thickness', frames=N, ms=round(ms, 4))), flush=True)
+    big = [torch.randint(0, 255, (N, HO, HO, 3), dtype=torch.uint8, device='cuda') for _ in range(sets)]
+    overs = [torch.empty_like(b_) for b_ in big]
+    ms = timeit([lambda i=i: prepost.overlay(big[i], masks[i], [0, 1, 2, 3], overs[i]) for i in range(sets)])
+    b = N * HO * HO * (3 + 4 + 3)
+    print(json.dumps(dict(kernel='overlay', Ho=HO, frames=N, ms=round(ms, 4), GBps=round(b / ms / 1e6, 1),
+                          frac_of_hbm=round(b / ms / 1e6 / peak, 3))), flush=True)
 
 
 if __name__ == '__main__':
