@@ -31,7 +31,10 @@ class EnsemblePipeline:
     def __init__(self, models: Dict[str, Tuple[object, Dict]], classes: Sequence[str], output_size: Sequence[int],
                  device, batch: int, src_hw: Optional[Tuple[int, int]] = None, thickness: bool = False):
         """models: {model_dir: (OCTSegmentationModel, cfg with 'input_size')} for every model_dir the
-        requested classes need.  output_size: cv2 convention (width, height), as in the reference."""
+        requested classes need.  output_size: cv2 convention (width, height), as in the reference.
+        Opt-in K-way probability averaging (north-star "ensemble averaging"; never the default -- the reference
+        routes exactly one model per class): a LIST of K (model, cfg) folds for a model_dir makes every fold run
+        to fp32 logits and ``octseg_fold_average_threshold`` produce the thresholded planes."""
         self.device = torch.device(device)
         self.classes = list(classes)
         for c in self.classes:
@@ -46,12 +49,20 @@ class EnsemblePipeline:
             d = MODELS_META[c]['model_dir']
             if d not in self.model_dirs:
                 self.model_dirs.append(d)
-        self.nets, self.sizes = {}, {}
+        self.nets, self.fold_nets, self.sizes, self.fold_planes = {}, {}, {}, {}
         for d in self.model_dirs:
-            model, cfg = models[d]
-            S = int(cfg['input_size'])
+            folds = list(models[d]) if isinstance(models[d], list) else [models[d]]
+            S = int(folds[0][1]['input_size'])
             self.sizes[d] = S
-            self.nets[d] = model.model.compiled(batch, S, S, self.device, 'u8', 'u8_nchw')
+            if len(folds) == 1:
+                self.fold_nets[d] = [folds[0][0].model.compiled(batch, S, S, self.device, 'u8', 'u8_nchw')]
+            else:
+                if any(int(cfg['input_size']) != S for _, cfg in folds):
+                    raise ValueError(f'{d}: all folds must share input_size')
+                self.fold_nets[d] = [m.model.compiled(batch, S, S, self.device, 'u8', 'f32_nchw') for m, _ in folds]
+                with torch.cuda.device(self.device):
+                    self.fold_planes[d] = torch.empty(self.fold_nets[d][0].out.shape, dtype=torch.uint8, device=self.device)
+        self.nets = {d: self.fold_nets[d][0] for d in self.model_dirs}
         self.order = [CLASS_IDS[c] - 1 for c in self.classes]
         # the networks are independent: each gets its own stream so small launches of one overlap the others
         with torch.cuda.device(self.device):
@@ -64,8 +75,9 @@ class EnsemblePipeline:
             self.mask = torch.empty(batch, self.Ho, self.Wo, 4, dtype=torch.uint8, device=self.device)
             self.label = torch.empty(batch, self.Ho, self.Wo, dtype=torch.uint8, device=self.device)
             self.counts = torch.zeros(batch, 4, dtype=torch.int32, device=self.device)
-        self.macs_per_frame = sum(self.nets[d].macs for d in self.model_dirs) / batch
-        self.launches_per_batch = sum(self.nets[d].launches for d in self.model_dirs) + len(self.model_dirs) + 1 + int(thickness)
+        all_nets = [net for d in self.model_dirs for net in self.fold_nets[d]]
+        self.macs_per_frame = sum(net.macs for net in all_nets) / batch
+        self.launches_per_batch = (sum(net.launches + 1 for net in all_nets) + len(self.fold_planes) + 1 + int(thickness))
 
     # ------------------------------------------------------------------ device-resident step
     def run_device(self, frames_dev: torch.Tensor):
@@ -74,12 +86,14 @@ class EnsemblePipeline:
         cur = torch.cuda.current_stream(self.device)
         self.ev_in.record(cur)
         for d in self.model_dirs:
-            net = self.nets[d]
             st = self.streams[d]
             st.wait_event(self.ev_in)
             with torch.cuda.stream(st):
-                P.preprocess(frames_dev, self.sizes[d], out=net.x_nhwc)
-                out = net.run()                                          # (batch, C, S, S) uint8 {0,1}
+                outs = []
+                for net in self.fold_nets[d]:
+                    P.preprocess(frames_dev, self.sizes[d], out=net.x_nhwc)
+                    outs.append(net.run())                               # (batch, C, S, S) uint8 {0,1} | fp32 logits
+                out = outs[0] if d not in self.fold_planes else P.fold_average_threshold(outs, out=self.fold_planes[d])
                 self.ev_done[d].record(st)
             for name in self.classes:
                 meta = MODELS_META[name]

@@ -86,8 +86,16 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
             if mdir in models:
                 continue
             start_load = time.time()
-            models[mdir] = load_model(model_dir=os.path.join(models_dir, mdir), device=device)
-            log.info(f"{models[mdir][1]['architecture']} loaded successfully. Time taken: {time.time() - start_load:.1f} s")
+            mpath = os.path.join(models_dir, mdir)
+            fold_dirs = sorted(glob(f'{mpath}/fold_*/config.json'))
+            if fold_dirs and not os.path.exists(f'{mpath}/config.json'):
+                # opt-in extension: K folds -> probability averaging (EnsemblePipeline docstring)
+                models[mdir] = [load_model(model_dir=os.path.dirname(f), device=device) for f in fold_dirs]
+                arch = f"{models[mdir][0][1]['architecture']} x {len(fold_dirs)} folds"
+            else:
+                models[mdir] = load_model(model_dir=mpath, device=device)
+                arch = models[mdir][1]['architecture']
+            log.info(f"{arch} loaded successfully. Time taken: {time.time() - start_load:.1f} s")
     frames = np.stack([np.array(img.convert('RGB') if img.mode != 'RGB' else img) for img in images])
     n = frames.shape[0]
     batch = min(batch_size, n)

@@ -138,3 +138,38 @@ def test_save_results_writes_the_reference_pngs(tmp_path):
         for name in 'abc':
             assert np.array_equal(np.array(Image.open(tmp_path / f'{name}_overlay.png')), d[f'overlay{i}'])
             assert np.array_equal(np.array(Image.open(tmp_path / f'{name}_mask.png')), d[f'colormask{i}'])
+
+
+def test_opt_in_fold_averaging(model_pairs):
+    """K-way probability averaging (opt-in; a list of folds for a model_dir): the VV planes equal the float64 oracle
+    average of the folds' own fp32 logits outside the rounding band, every other class is untouched, and a
+    one-element list is the plain routing path."""
+    _, ours = model_pairs
+    vv_a, cfg = ours['VV']
+    vv_b = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
+                                in_channels=3, classes=cfg['classes'], encoder_weights=None)
+    vv_b.load_state_dict(vv_a.state_dict(), strict=True)
+    with torch.no_grad():                      # a second "fold": same architecture, different head
+        vv_b.model.segmentation_head[0].weight.mul_(-0.7)
+        vv_b.model.segmentation_head[0].bias.add_(0.3)
+    vv_b.model.invalidate()
+    vv_b = vv_b.cuda().eval()
+    Ho = 250
+    frames = synth.synthetic_frames(330, 2, 250)
+    plain = EnsemblePipeline(ours, CLASSES, [Ho, Ho], 'cuda:0', 2, src_hw=(250, 250))
+    want_mask = plain.run_host(frames)[0]
+    one = EnsemblePipeline(dict(ours, VV=[(vv_a, cfg)]), CLASSES, [Ho, Ho], 'cuda:0', 2, src_hw=(250, 250))
+    assert np.array_equal(one.run_host(frames)[0], want_mask)
+    two = EnsemblePipeline(dict(ours, VV=[(vv_a, cfg), (vv_b, cfg)]), CLASSES, [Ho, Ho], 'cuda:0', 2, src_hw=(250, 250))
+    mask, _, counts, _ = two.run_host(frames)
+    assert np.array_equal(mask[..., :3], want_mask[..., :3])
+    logits = [net.out.cpu().numpy() for net in two.fold_nets['VV']]
+    assert logits[0].dtype == np.float32 and not np.array_equal(logits[0], logits[1])
+    want, margin = R.fold_average_threshold(logits)
+    got = two.fold_planes['VV'].cpu().numpy()
+    sure = margin > 1e-6
+    assert sure.mean() > 0.999 and np.array_equal(got[sure], want[sure])
+    S = SMALL['VV']
+    iy, ix = R.nearest_index(S, Ho), R.nearest_index(S, Ho)
+    assert np.array_equal(mask[..., 3], got[:, 0][:, iy][:, :, ix])
+    assert np.array_equal(counts[:, 3], (mask[..., 3] != 0).sum(axis=(1, 2)))
