@@ -7,12 +7,21 @@
 //   img    = paste(img, colour, fill_lut[k]);  img = paste(img, colour, rim ? rim_alpha : 0)
 // with PIL's paste  out = ((t >> 8) + t) >> 8,  t = dst*(255-a) + src*a + 128.
 //
-// The four classes of a pixel are the four bytes of one 32-bit mask word, so the morphology runs on all
-// classes at once (OR / AND of words) and the binomial sums ride in two registers of 16-bit lanes.
-// One block = 32 x 8 output pixels; the mask tile (halo 7), its 5x5 dilation (halo 5) and the closed
-// tile (halo 3) live in shared memory.
+// overlay_kernel (the product path): the morphology runs on BIT PLANES -- one 32-bit word = 32 pixels of one
+// row of one class -- so a dilation / erosion row is a handful of funnel shifts and ORs / ANDs for 32 pixels.
+// One block = 128 x TY output pixels; region = tile + 7 halo rows and one halo word (32 px) per side:
+//   S0  mask words (4 class bytes per pixel, 16-byte loads) -> bit planes M   (nibbles OR-reduced over 8 lanes)
+//   S1  D  = dilate5(M), image exterior forced to 1 (erode's border value)
+//   S2  E  = erode5(D);  Cd = E inside / 0 outside, Ce = E inside / 1 outside, Cr = Cd + reflected columns
+//   S3  RIM = dilate7(Cd) & ~erode7(Ce);  ANY / ALL = OR / AND of the 5x5 (reflected) window of Cr
+//   S4  one warp = 32 pixels of a row: classes whose RIM|ANY word is 0 are skipped warp-uniformly, pixels with a
+//       uniform window take k = 256, only object-boundary pixels compute the binomial sum (5 windows, popcounts).
+// overlay_bytes_kernel is the first, byte-lane version (4 classes = 4 bytes of a word, 32 x 8 tiles), kept as an
+// A/B reference (OCTSEG_OVERLAY_IMPL=bytes).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.h"
 
@@ -46,7 +55,7 @@ __device__ __forceinline__ int reflect101(int v, int n) {  // cv2 BORDER_REFLECT
   return v;
 }
 
-__global__ void __launch_bounds__(kOvX* kOvY) overlay_kernel(const OverlayParams p) {
+__global__ void __launch_bounds__(kOvX* kOvY) overlay_bytes_kernel(const OverlayParams p) {
   __shared__ uint32_t sm_m[kMH * kMW];
   __shared__ uint32_t sm_d[kDH * kDW];
   __shared__ uint32_t sm_c[kCH * kCW];
@@ -154,6 +163,253 @@ __global__ void __launch_bounds__(kOvX* kOvY) overlay_kernel(const OverlayParams
   p.out[pix * 3 + 2] = static_cast<uint8_t>(rgb[2]);
 }
 
+// ---------------------------------------------------------------------------------------------- bit planes
+constexpr int kTileWords = 4;            // 128 output pixels per tile row
+constexpr int kRW = kTileWords + 2;      // region words per row (one halo word per side)
+
+// OR / AND over the horizontal taps dx = -R..R of a bit-plane row (p, c, n = previous, current, next word)
+template <int R>
+__device__ __forceinline__ uint32_t hor_or(uint32_t p, uint32_t c, uint32_t n) {
+  uint32_t v = c;
+#pragma unroll
+  for (int s = 1; s <= R; ++s) v |= __funnelshift_l(p, c, s) | __funnelshift_r(c, n, s);
+  return v;
+}
+template <int R>
+__device__ __forceinline__ uint32_t hor_and(uint32_t p, uint32_t c, uint32_t n) {
+  uint32_t v = c;
+#pragma unroll
+  for (int s = 1; s <= R; ++s) v &= __funnelshift_l(p, c, s) & __funnelshift_r(c, n, s);
+  return v;
+}
+// bits of the 32 pixels starting at column xs of row y that lie inside the image
+__device__ __forceinline__ uint32_t inimg_word(int y, int xs, int H, int W) {
+  if (y < 0 || y >= H) return 0u;
+  const int lo = max(0, -xs), hi = min(32, W - xs);
+  if (hi <= lo) return 0u;
+  return (hi == 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+}
+
+template <int TY>
+__global__ void __launch_bounds__(256) overlay_kernel(const OverlayParams p) {
+  constexpr int RH = TY + 14, PL = RH * kRW, TP = TY * kTileWords;
+  extern __shared__ uint32_t sm[];
+  uint32_t* M = sm;
+  uint32_t* D = M + 4 * PL;
+  uint32_t* Cd = D + 4 * PL;
+  uint32_t* Ce = Cd + 4 * PL;
+  uint32_t* Cr = Ce + 4 * PL;
+  uint32_t* RIM = Cr + 4 * PL;
+  uint32_t* ANY = RIM + 4 * TP;
+  uint32_t* ALL = ANY + 4 * TP;
+  uint8_t* lut = reinterpret_cast<uint8_t*>(ALL + 4 * TP);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.z, H = p.H, W = p.W;
+  const int x0 = blockIdx.x * (32 * kTileWords), y0 = blockIdx.y * TY;
+  const int xr0 = x0 - 32, yr0 = y0 - 7;
+  const uint32_t* mimg = p.mask + static_cast<size_t>(n) * H * W;
+  for (int i = tid; i < 257; i += 256) lut[i] = p.fill_lut[i];
+
+  // S0: pack.  A lane loads 4 pixels (16 bytes); byte c of `t` = the 4 presence bits of class c; the nibbles of
+  // the 8 lanes of a word are OR-reduced with redux.sync over that lane group.
+  const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0;
+  for (int it = warp; it < RH * 2; it += 8) {
+    const int r = it >> 1, u = it & 1;
+    if (u == 1 && lane >= 16) continue;  // second unit of a row = words 4, 5 only (whole lane groups drop out)
+    const int y = yr0 + r, x = xr0 + 128 * u + 4 * lane;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const uint32_t* src = mimg + static_cast<size_t>(y) * W + x;
+      if (vec_ok) {
+        q = __ldg(reinterpret_cast<const uint4*>(src));
+      } else {
+        q.x = __ldg(src);
+        if (x + 1 < W) q.y = __ldg(src + 1);
+        if (x + 2 < W) q.z = __ldg(src + 2);
+        if (x + 3 < W) q.w = __ldg(src + 3);
+      }
+    }
+    const uint32_t t = __vminu4(q.x, kOnes) + 2u * __vminu4(q.y, kOnes) + 4u * __vminu4(q.z, kOnes) + 8u * __vminu4(q.w, kOnes);
+    const int sh = 4 * (lane & 7);
+    const unsigned gm = 0xffu << (lane & 24);
+    uint32_t mine = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t v = __reduce_or_sync(gm, ((t >> (8 * c)) & 0xfu) << sh);
+      if ((lane & 7) == c) mine = v;
+    }
+    if ((lane & 7) < 4) M[(lane & 7) * PL + r * kRW + 4 * u + (lane >> 3)] = mine;
+  }
+  __syncthreads();
+
+  // S1: D = dilate(M, ellipse 5x5) (rows +-2: centre tap; rows -1..1: 5 taps); exterior = 1
+  for (int i = tid; i < (RH - 4) * kRW; i += 256) {
+    const int r = 2 + i / kRW, j = i % kRW;
+    const uint32_t ext = ~inimg_word(yr0 + r, xr0 + 32 * j, H, W);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t* m = M + c * PL + r * kRW + j;
+      uint32_t acc = m[-2 * kRW] | m[2 * kRW];
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const uint32_t* row = m + dy * kRW;
+        acc |= hor_or<2>(j > 0 ? row[-1] : 0u, row[0], j < kRW - 1 ? row[1] : 0u);
+      }
+      D[c * PL + r * kRW + j] = acc | ext;
+    }
+  }
+  __syncthreads();
+
+  // S2: E = erode(D, ellipse 5x5) -> the closed mask in its three border conventions
+  for (int i = tid; i < (RH - 8) * kRW; i += 256) {
+    const int r = 4 + i / kRW, j = i % kRW;
+    const uint32_t in = inimg_word(yr0 + r, xr0 + 32 * j, H, W);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t* d = D + c * PL + r * kRW + j;
+      uint32_t acc = d[-2 * kRW] & d[2 * kRW];
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const uint32_t* row = d + dy * kRW;
+        acc &= hor_and<2>(j > 0 ? row[-1] : 0xffffffffu, row[0], j < kRW - 1 ? row[1] : 0xffffffffu);
+      }
+      const int o = c * PL + r * kRW + j;
+      Cd[o] = acc & in;
+      Ce[o] = acc | ~in;
+      Cr[o] = acc & in;
+    }
+  }
+  __syncthreads();
+  // BORDER_REFLECT_101 columns of Cr: x = -k <- x = k and x = W-1+k <- x = W-1-k (k = 1, 2); one thread per row
+  if (x0 == 0 || xr0 + 32 * kRW > W) {
+    for (int i = tid; i < 4 * (RH - 8); i += 256) {
+      const int c = i / (RH - 8), r = 4 + i % (RH - 8);
+      const int y = yr0 + r;
+      if (y < 0 || y >= H) continue;
+      uint32_t* row = Cr + c * PL + r * kRW;
+#pragma unroll
+      for (int k = 1; k <= 2; ++k) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int bs = (side ? W - 1 - k : k) - xr0, bd = (side ? W - 1 + k : -k) - xr0;
+          if (bd >= 0 && bd < 32 * kRW && bs >= 0 && bs < 32 * kRW) row[bd >> 5] |= ((row[bs >> 5] >> (bs & 31)) & 1u) << (bd & 31);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // S3: rim and the uniform-window planes for the tile's words
+  for (int i = tid; i < TP * 2; i += 256) {
+    const int half = i & 1, j = (i >> 1) & (kTileWords - 1), r = i >> 3;
+    const int y = y0 + r;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = 2 * half + cc;
+      uint32_t rim = 0, any = 0, all = 0;
+      if (y < H) {
+        const int o = c * PL + (r + 7) * kRW + j + 1;
+        const uint32_t* cd = Cd + o;
+        const uint32_t* ce = Ce + o;
+        uint32_t dil = cd[-3 * kRW] | cd[3 * kRW], ero = ce[-3 * kRW] & ce[3 * kRW];
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy) {
+          const uint32_t* a = cd + dy * kRW;
+          const uint32_t* b = ce + dy * kRW;
+          if (dy == -2 || dy == 2) {
+            dil |= hor_or<2>(a[-1], a[0], a[1]);
+            ero &= hor_and<2>(b[-1], b[0], b[1]);
+          } else {
+            dil |= hor_or<3>(a[-1], a[0], a[1]);
+            ero &= hor_and<3>(b[-1], b[0], b[1]);
+          }
+        }
+        rim = dil & ~ero;
+        all = 0xffffffffu;
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy) {
+          const uint32_t* a = Cr + c * PL + (reflect101(y + dy, H) - yr0) * kRW + j + 1;
+          any |= hor_or<2>(a[-1], a[0], a[1]);
+          all &= hor_and<2>(a[-1], a[0], a[1]);
+        }
+      }
+      RIM[c * TP + r * kTileWords + j] = rim;
+      ANY[c * TP + r * kTileWords + j] = any;
+      ALL[c * TP + r * kTileWords + j] = all;
+    }
+  }
+  __syncthreads();
+
+  // S4: paste.  One warp = one word (32 pixels) of a row.
+  const int a_full = lut[256], a_none = lut[0];
+  for (int it = warp; it < TP; it += 8) {
+    const int r = it / kTileWords, j = it % kTileWords;
+    const int y = y0 + r, x = x0 + 32 * j + lane;
+    if (y >= H || x0 + 32 * j >= W) continue;
+    const bool act = x < W;
+    const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
+    int rgb[3] = {0, 0, 0};
+    if (act) {
+      rgb[0] = p.img[pix * 3];
+      rgb[1] = p.img[pix * 3 + 1];
+      rgb[2] = p.img[pix * 3 + 2];
+    }
+    for (int i = 0; i < p.n_order; ++i) {
+      const int c = p.order[i];
+      const int o = c * TP + r * kTileWords + j;
+      const uint32_t rimw = RIM[o], anyw = ANY[o];
+      if ((rimw | anyw) == 0u && a_none == 0) continue;  // warp-uniform: nothing of this class near these 32 pixels
+      const int a2 = ((rimw >> lane) & 1u) ? p.rim_alpha : 0;
+      int a1 = a_none;
+      if ((anyw >> lane) & 1u) {
+        if ((ALL[o] >> lane) & 1u) {
+          a1 = a_full;
+        } else {  // object boundary: k = 5x5 binomial sum of the closed mask
+          int k = 0;
+#pragma unroll
+          for (int dy = -2; dy <= 2; ++dy) {
+            const uint32_t* a = Cr + c * PL + (reflect101(y + dy, H) - yr0) * kRW + j + 1;
+            const uint32_t lo = lane >= 2 ? a[0] : a[-1], hi = lane >= 2 ? a[1] : a[0];
+            const uint32_t win = __funnelshift_r(lo, hi, (lane - 2) & 31) & 31u;  // bit i = column x - 2 + i
+            const int h = __popc(win) + 3 * __popc(win & 14u) + 2 * static_cast<int>((win >> 2) & 1u);
+            k += (dy == 0 ? 6 : (dy == -1 || dy == 1 ? 4 : 1)) * h;
+          }
+          a1 = lut[k];
+        }
+      }
+      if (a1 | a2) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          int t = rgb[ch] * (255 - a1) + p.color[c][ch] * a1 + 128;
+          const int v = ((t >> 8) + t) >> 8;
+          t = v * (255 - a2) + p.color[c][ch] * a2 + 128;
+          rgb[ch] = ((t >> 8) + t) >> 8;
+        }
+      }
+    }
+    if (act) {
+      p.out[pix * 3] = static_cast<uint8_t>(rgb[0]);
+      p.out[pix * 3 + 1] = static_cast<uint8_t>(rgb[1]);
+      p.out[pix * 3 + 2] = static_cast<uint8_t>(rgb[2]);
+    }
+  }
+}
+
+template <int TY>
+static int launch_overlay(const OverlayParams& p, cudaStream_t stream) {
+  constexpr size_t smem = (static_cast<size_t>(5 * 4 * (TY + 14) * kRW + 3 * 4 * TY * kTileWords)) * 4 + 272;
+  static unsigned long long configured = 0;  // bit d = done on device d (the attribute is per device)
+  int dev = 0;
+  OCTSEG_CUDA(cudaGetDevice(&dev));
+  if (!((configured >> (dev & 63)) & 1ull)) {
+    OCTSEG_CUDA(cudaFuncSetAttribute(overlay_kernel<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured |= 1ull << (dev & 63);
+  }
+  dim3 grid(cdiv(p.W, 32 * kTileWords), cdiv(p.H, TY), p.N);
+  overlay_kernel<TY><<<grid, 256, smem, stream>>>(p);
+  return check_launch("overlay_kernel");
+}
+
 }  // namespace octseg
 
 using namespace octseg;
@@ -181,7 +437,12 @@ extern "C" int octseg_overlay(const uint8_t* img, const uint8_t* mask, uint8_t* 
   }
   p.rim_alpha = rim_alpha;
   for (int k = 0; k < 257; ++k) p.fill_lut[k] = h_fill_lut[k];
-  dim3 grid(cdiv(W, kOvX), cdiv(H, kOvY), N);
-  overlay_kernel<<<grid, dim3(kOvX, kOvY), 0, static_cast<cudaStream_t>(stream)>>>(p);
-  return check_launch("overlay_kernel");
+  static const char* impl = getenv("OCTSEG_OVERLAY_IMPL");  // A/B switch for tools/bench_prepost.py, not an API
+  if (impl && !strcmp(impl, "bytes")) {
+    dim3 grid(cdiv(W, kOvX), cdiv(H, kOvY), N);
+    overlay_bytes_kernel<<<grid, dim3(kOvX, kOvY), 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("overlay_bytes_kernel");
+  }
+  if (impl && !strcmp(impl, "ty32")) return launch_overlay<32>(p, static_cast<cudaStream_t>(stream));
+  return launch_overlay<64>(p, static_cast<cudaStream_t>(stream));
 }

@@ -80,22 +80,7 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
         return masks
     dev = torch.device('cuda:0')
     if models is None:
-        models = {}
-        for class_name in classes:
-            mdir = MODELS_META[class_name]['model_dir']
-            if mdir in models:
-                continue
-            start_load = time.time()
-            mpath = os.path.join(models_dir, mdir)
-            fold_dirs = sorted(glob(f'{mpath}/fold_*/config.json'))
-            if fold_dirs and not os.path.exists(f'{mpath}/config.json'):
-                # opt-in extension: K folds -> probability averaging (EnsemblePipeline docstring)
-                models[mdir] = [load_model(model_dir=os.path.dirname(f), device=device) for f in fold_dirs]
-                arch = f"{models[mdir][0][1]['architecture']} x {len(fold_dirs)} folds"
-            else:
-                models[mdir] = load_model(model_dir=mpath, device=device)
-                arch = models[mdir][1]['architecture']
-            log.info(f"{arch} loaded successfully. Time taken: {time.time() - start_load:.1f} s")
+        models = load_models(models_dir, classes, device)
     frames = np.stack([np.array(img.convert('RGB') if img.mode != 'RGB' else img) for img in images])
     n = frames.shape[0]
     batch = min(batch_size, n)
@@ -114,21 +99,29 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
     return masks
 
 
+def list_images(data_path: str) -> List[str]:
+    """The file set of data_processing (src/data/utils.py:175-178), in sorted order."""
+    if os.path.isfile(data_path):
+        return [data_path]
+    return sorted(glob(f'{data_path}/*.[pj][np][ge]*'))
+
+
+def open_images(images_path: Sequence[str], output_size: Sequence[int], pool=None):
+    """Loop body of data_processing (src/data/utils.py:180-191) for the given files; decoding + bicubic resize
+    run on ``pool`` (a concurrent.futures executor) when given."""
+    def one(img_path):
+        return Image.open(img_path).resize(tuple(output_size))
+    images = list(pool.map(one, images_path)) if pool is not None else [one(q) for q in images_path]
+    masks = [np.zeros((output_size[0], output_size[1], 4)) for _ in images_path]
+    image_names = [os.path.basename(img_path).split('.')[0] for img_path in images_path]
+    return images, masks, image_names
+
+
 def data_processing(data_path: str, save_dir: str, output_size: Sequence[int]):
     """src/data/utils.py:169-192: open every image, PIL-resize (bicubic) to output_size, allocate the
     float64 HxWx4 mask.  File order is sorted (the reference's glob order is unspecified)."""
     os.makedirs(save_dir, exist_ok=True)
-    if os.path.isfile(data_path):
-        images_path = [data_path]
-    else:
-        images_path = sorted(glob(f'{data_path}/*.[pj][np][ge]*'))
-    images, masks, image_names = [], [], []
-    for img_path in images_path:
-        img = Image.open(img_path).resize(tuple(output_size))
-        masks.append(np.zeros((output_size[0], output_size[1], 4)))
-        images.append(img)
-        image_names.append(os.path.basename(img_path).split('.')[0])
-    return images, masks, image_names
+    return open_images(list_images(data_path), output_size)
 
 
 def color_mask(mask: np.ndarray, classes: Sequence[str]) -> np.ndarray:
@@ -141,11 +134,12 @@ def color_mask(mask: np.ndarray, classes: Sequence[str]) -> np.ndarray:
     return out
 
 
-def save_results(images, masks, images_name, classes, save_dir: str, batch_size: int = 16, device: str = 'cuda') -> None:
+def save_results(images, masks, images_name, classes, save_dir: str, batch_size: int = 16, device: str = 'cuda',
+                 pool=None) -> None:
     """src/data/utils.py:195-235: writes <name>_mask.png (priority colour mask) and <name>_overlay.png
     (closed + blurred fill and dilate/erode rim pasted per class over the frame).  The overlay is computed
     by ``octseg_overlay`` in batches on the GPU, bit-exact vs the reference's cv2 + PIL arithmetic
-    (tests/golden/overlay_ref.npz); PNG encoding stays on the host (PIL), like the reference's."""
+    (tests/golden/overlay_ref.npz); PNG encoding stays on the host (PIL), like the reference's; ``pool`` spreads it over threads."""
     order = [CLASS_IDS[c] - 1 for c in classes]
     dev = torch.device(device)
     for lo in range(0, len(images), batch_size):
@@ -153,34 +147,101 @@ def save_results(images, masks, images_name, classes, save_dir: str, batch_size:
         frames = np.stack([np.asarray(img.convert('RGB')) for img in images[lo:hi]])
         m8 = np.stack([(np.asarray(m) != 0).astype(np.uint8) for m in masks[lo:hi]])
         over = P.overlay(torch.from_numpy(frames).to(dev), torch.from_numpy(m8).to(dev), order).cpu().numpy()
-        for k in range(hi - lo):
+        def write(k, lo=lo, over=over):
             Image.fromarray(over[k]).save(f'{save_dir}/{images_name[lo + k]}_overlay.png')
             Image.fromarray(color_mask(masks[lo + k], classes)).save(f'{save_dir}/{images_name[lo + k]}_mask.png')
+        if pool is not None:
+            list(pool.map(write, range(hi - lo)))       # PNG encoding (zlib) releases the GIL
+        else:
+            for k in range(hi - lo):
+                write(k)
+
+
+def load_models(models_dir: str, classes: Sequence[str], device: str) -> Dict:
+    """{model_dir: (model, cfg)} for the requested classes (the loading loop of segment, src/predict.py:70-76);
+    a model_dir holding fold_*/ sub-directories instead of config.json loads as a list of folds (opt-in
+    probability averaging, see EnsemblePipeline)."""
+    models = {}
+    for class_name in classes:
+        mdir = MODELS_META[class_name]['model_dir']
+        if mdir in models:
+            continue
+        start_load = time.time()
+        mpath = os.path.join(models_dir, mdir)
+        fold_dirs = sorted(glob(f'{mpath}/fold_*/config.json'))
+        if fold_dirs and not os.path.exists(f'{mpath}/config.json'):
+            models[mdir] = [load_model(model_dir=os.path.dirname(f), device=device) for f in fold_dirs]
+            arch = f"{models[mdir][0][1]['architecture']} x {len(fold_dirs)} folds"
+        else:
+            models[mdir] = load_model(model_dir=mpath, device=device)
+            arch = models[mdir][1]['architecture']
+        log.info(f"{arch} loaded successfully. Time taken: {time.time() - start_load:.1f} s")
+    return models
 
 
 def main(cfg) -> None:
-    """Main function to perform OCT image segmentation prediction."""
+    """Main function to perform OCT image segmentation prediction (src/predict.py:109-149).
+
+    ``stream_chunk: K`` (extension, 0 = the reference's hold-everything flow): the file list is walked in chunks
+    of K frames -- chunk i+1 is decoded and chunk i-1 is PNG-encoded on ``io_workers`` host threads while chunk i
+    is on the GPU, and each chunk's images / float64 masks (35 MB per frame at 1000 x 1000) are released after
+    its results are written, so the frame count is not bounded by host memory.
+    Results are identical to the non-streaming flow."""
     log.info(f'Config:\n\n{cfgmod.to_yaml(cfg)}')
     device = pick_device(option=cfg.device)
     data_dir = str(os.path.join(PROJECT_DIR, cfg.data_dir))
     models_dir = str(os.path.join(PROJECT_DIR, cfg.models_dir))
     save_dir = str(os.path.join(PROJECT_DIR, cfg.save_dir))
+    batch_size = int(cfg.get('batch_size', 16))
+    want_quantities = bool(cfg.get('quantities', False))
+    chunk = int(cfg.get('stream_chunk', 0) or 0)
 
     start = time.time()
-    images, masks, images_name = data_processing(data_path=data_dir, save_dir=save_dir, output_size=cfg.output_size)
-    log.info(f'Number of images: {len(images_name)}')
-
-    start_inference = time.time()
-    quantities = [] if cfg.get('quantities', False) else None
-    masks = segment(images=images, masks=masks, output_size=cfg.output_size, classes=cfg.classes,
-                    models_dir=models_dir, device=device, batch_size=int(cfg.get('batch_size', 16)),
-                    quantities=quantities)
-    log.info(f'Prediction time: {time.time() - start_inference:.1f} s')
-
-    save_results(images=images, masks=masks, images_name=images_name, classes=cfg.classes, save_dir=save_dir)
-    if quantities is not None:
+    if chunk <= 0:
+        images, masks, images_name = data_processing(data_path=data_dir, save_dir=save_dir, output_size=cfg.output_size)
+        log.info(f'Number of images: {len(images_name)}')
+        start_inference = time.time()
+        quantities = [] if want_quantities else None
+        masks = segment(images=images, masks=masks, output_size=cfg.output_size, classes=cfg.classes,
+                        models_dir=models_dir, device=device, batch_size=batch_size, quantities=quantities)
+        log.info(f'Prediction time: {time.time() - start_inference:.1f} s')
+        save_results(images=images, masks=masks, images_name=images_name, classes=cfg.classes, save_dir=save_dir,
+                     batch_size=batch_size)
+        table = dict(zip(images_name, quantities)) if want_quantities else None
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        os.makedirs(save_dir, exist_ok=True)
+        paths = list_images(data_dir)
+        log.info(f'Number of images: {len(paths)} (streamed in chunks of {chunk})')
+        if device != 'cuda':
+            raise RuntimeError('the B200 build of segment() runs on CUDA only (device resolved to %r)' % device)
+        models = load_models(models_dir, cfg.classes, device) if paths else {}
+        table = {} if want_quantities else None
+        spans = [(lo, min(lo + chunk, len(paths))) for lo in range(0, len(paths), chunk)]
+        with ThreadPoolExecutor(max_workers=int(cfg.get('io_workers', 8))) as io, \
+                ThreadPoolExecutor(max_workers=2) as stage:
+            def load(span):
+                return open_images(paths[span[0]:span[1]], cfg.output_size, pool=io)
+            nxt = stage.submit(load, spans[0]) if spans else None
+            saving = None
+            for k, span in enumerate(spans):
+                images, masks, names = nxt.result()
+                nxt = stage.submit(load, spans[k + 1]) if k + 1 < len(spans) else None
+                quantities = [] if want_quantities else None
+                masks = segment(images=images, masks=masks, output_size=cfg.output_size, classes=cfg.classes,
+                                models_dir=models_dir, device=device, batch_size=batch_size, models=models,
+                                quantities=quantities)
+                if want_quantities:
+                    table.update(zip(names, quantities))
+                if saving is not None:
+                    saving.result()
+                saving = stage.submit(save_results, images, masks, names, cfg.classes, save_dir, batch_size, 'cuda', io)
+            if saving is not None:
+                saving.result()
+        log.info(f'Prediction + I/O time: {time.time() - start:.1f} s')
+    if table is not None:
         with open(os.path.join(save_dir, 'quantities.json'), 'w') as f:
-            json.dump(dict(zip(images_name, quantities)), f, indent=1)
+            json.dump(table, f, indent=1)
     log.info(f'Overall computation time: {time.time() - start:.1f} s')
     log.info('Complete')
 

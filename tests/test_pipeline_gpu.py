@@ -173,3 +173,33 @@ def test_opt_in_fold_averaging(model_pairs):
     iy, ix = R.nearest_index(S, Ho), R.nearest_index(S, Ho)
     assert np.array_equal(mask[..., 3], got[:, 0][:, iy][:, :, ix])
     assert np.array_equal(counts[:, 3], (mask[..., 3] != 0).sum(axis=(1, 2)))
+
+
+def test_streaming_main_equals_hold_everything_main(tmp_path, model_pairs):
+    """`stream_chunk` (chunks decoded / segmented / encoded in overlap, bounded host memory) writes exactly the
+    files of the reference-shaped flow: same PNG pixels, same quantities.json; ragged last chunk and last batch."""
+    refs, _ = model_pairs
+    models_dir, data_dir = tmp_path / 'models', tmp_path / 'in'
+    data_dir.mkdir()
+    for key, (r, cfg) in refs.items():
+        (models_dir / key).mkdir(parents=True)
+        synth.save_checkpoint(r.cpu(), str(models_dir / key / 'weights.ckpt'))
+        json.dump(cfg, open(models_dir / key / 'config.json', 'w'))
+        r.cuda()
+    for i, f in enumerate(synth.synthetic_frames(340, 5, 200)):
+        Image.fromarray(f).save(data_dir / f'frame_{i}.png')
+    from oct_segmentation_b200 import config
+    outs = {}
+    for mode, extra in (('hold', []), ('stream', ['stream_chunk=2', 'io_workers=3'])):
+        save_dir = tmp_path / mode
+        cfg = config.compose(os.path.join(os.path.dirname(os.path.dirname(__file__)), 'configs'), 'predict',
+                             [f'data_dir={data_dir}', f'models_dir={models_dir}', f'save_dir={save_dir}',
+                              'output_size=[256,256]', 'device=cuda', 'batch_size=2'] + extra)
+        pred.main(cfg)
+        outs[mode] = save_dir
+    assert sorted(os.listdir(outs['hold'])) == sorted(os.listdir(outs['stream']))
+    assert len(os.listdir(outs['hold'])) == 11
+    for name in os.listdir(outs['hold']):
+        if name.endswith('.png'):
+            assert np.array_equal(np.array(Image.open(outs['hold'] / name)), np.array(Image.open(outs['stream'] / name))), name
+    assert json.load(open(outs['hold'] / 'quantities.json')) == json.load(open(outs['stream'] / 'quantities.json'))

@@ -62,11 +62,28 @@ def main():
     print(json.dumps(dict(kernel='radial_thickness', frames=N, ms=round(ms, 4))), flush=True)
     big = [torch.randint(0, 255, (N, HO, HO, 3), dtype=torch.uint8, device='cuda') for _ in range(sets)]
     overs = [torch.empty_like(b_) for b_ in big]
-    ms = timeit([lambda i=i: prepost.overlay(big[i], masks[i], [0, 1, 2, 3], overs[i]) for i in range(sets)])
+    # OCT-shaped masks: lumen disc, fibrous-cap arc, lipid wedge behind it, a few vasa-vasorum blobs (the noise
+    # masks left by the post-processing bench above are the worst case: every pixel is an object boundary)
+    yy, xx = torch.meshgrid(torch.arange(HO, device='cuda'), torch.arange(HO, device='cuda'), indexing='ij')
+    rr = ((yy - HO / 2) ** 2 + (xx - HO / 2) ** 2).float().sqrt()
+    ang = torch.atan2((yy - HO / 2).float(), (xx - HO / 2).float())
+    shaped = torch.zeros(N, HO, HO, 4, dtype=torch.uint8, device='cuda')
+    shaped[..., 0] = (rr < 0.22 * HO).to(torch.uint8)
+    shaped[..., 1] = ((rr >= 0.22 * HO) & (rr < 0.26 * HO) & (ang.abs() < 1.0)).to(torch.uint8)
+    shaped[..., 2] = ((rr >= 0.26 * HO) & (rr < 0.36 * HO) & (ang.abs() < 0.9)).to(torch.uint8)
+    shaped[..., 3] = (((yy - 0.2 * HO) ** 2 + (xx - 0.3 * HO) ** 2 < 64) | ((yy - 0.75 * HO) ** 2 + (xx - 0.7 * HO) ** 2 < 100)).to(torch.uint8)
     b = N * HO * HO * (3 + 4 + 3)
-    print(json.dumps(dict(kernel='overlay', Ho=HO, frames=N, ms=round(ms, 4), GBps=round(b / ms / 1e6, 1),
+    for what, mm in (('OCT-shaped masks', [shaped] * sets), ('noise masks (worst case)', masks)):
+        ms = timeit([lambda i=i: prepost.overlay(big[i], mm[i], [0, 1, 2, 3], overs[i]) for i in range(sets)])
+        print(json.dumps(dict(kernel='overlay', masks=what, impl=os.environ.get('OCTSEG_OVERLAY_IMPL', 'default'), Ho=HO, frames=N,
+                              ms=round(ms, 4), GBps=round(b / ms / 1e6, 1), frac_of_hbm=round(b / ms / 1e6 / peak, 3))), flush=True)
+    K = 5
+    folds = [[torch.randn(N, 1, 896, 896, device='cuda') for _ in range(K)] for _ in range(2)]
+    fouts = [torch.empty(N, 1, 896, 896, dtype=torch.uint8, device='cuda') for _ in range(2)]
+    ms = timeit([lambda i=i: prepost.fold_average_threshold(folds[i], fouts[i]) for i in range(2)])
+    b = N * 896 * 896 * (4 * K + 1)
+    print(json.dumps(dict(kernel='fold_average_threshold', K=K, S=896, frames=N, ms=round(ms, 4), GBps=round(b / ms / 1e6, 1),
                           frac_of_hbm=round(b / ms / 1e6 / peak, 3))), flush=True)
-
 
 if __name__ == '__main__':
     main()
