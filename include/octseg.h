@@ -233,6 +233,17 @@ int octseg_overlay(const uint8_t* img, const uint8_t* mask, uint8_t* out, int32_
    pointers to fp32 tensors of n elements each (16-byte aligned); out: DEVICE uint8 [n] (4-byte aligned). */
 int octseg_fold_average_threshold(const float* const* h_logits, int32_t K, int64_t n, uint8_t* out, void* stream);
 
+/* calculate_thickness_contour (src/app/tools/analysis.py:21-57), device part: per (frame, class) the largest outer
+   border of cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) (== max(contours, key=contourArea)), same
+   points in the same order.  mask: DEVICE uint8 [N][H][W][4] (non-zero = object).  Outputs (DEVICE):
+   sums int64 [N][4][4] = a00, a10, a01 (the integer accumulators of cv2's polygon moments: m00 = |a00|/2, ...)
+   and the start pixel index y*W+x (-1: no border with non-zero area); nverts int32 [N][4] = kept points of that
+   border (may exceed cap: only the first cap are stored); verts int16 [N][4][cap][2] = x, y.
+   The host finishes centroid (int-truncated), distances, median / min / max.  (H+2)*ceil((W+2)/32)*4 bytes of
+   shared memory must fit 226 KB (1000 x 1000: 128 KB). */
+int octseg_contour_largest(const uint8_t* mask, int32_t N, int32_t H, int32_t W, int64_t* sums, int32_t* nverts,
+                           int16_t* verts, int32_t cap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

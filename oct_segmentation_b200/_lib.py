@@ -24,7 +24,7 @@ EXPORTS = [
     'octseg_stem_pack', 'octseg_maxpool3x3s2', 'octseg_dwconv', 'octseg_se_hidden',
     'octseg_se_gate', 'octseg_se_scale_weights', 'octseg_preprocess_resize_bgr', 'octseg_postprocess',
     'octseg_radial_thickness', 'octseg_overlay', 'octseg_preprocess_resize_gray',
-    'octseg_fold_average_threshold',
+    'octseg_fold_average_threshold', 'octseg_contour_largest',
 ]
 
 
@@ -99,6 +99,8 @@ def load() -> C.CDLL:
                                    C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
                                    C.c_int32, C.c_void_p]
     lib.octseg_fold_average_threshold.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.octseg_contour_largest.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int32, C.c_void_p]
     for name in EXPORTS:
         if name not in ('octseg_last_error',):
             getattr(lib, name).restype = C.c_int

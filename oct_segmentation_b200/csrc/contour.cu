@@ -1,0 +1,108 @@
+// calculate_thickness_contour (src/app/tools/analysis.py:21-57) on the GPU: per (frame, class) the largest outer
+// border of cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE), bit-exact (same points in the same order),
+// with the integer accumulators of cv2's polygon moments; the host finishes centroid / distances / median.
+//
+// One block per (class, frame).  The class's bit plane (1 bit per pixel, one-pixel zero frame: 128 KB at
+// 1000 x 1000) is packed into shared memory with warp ballots, so every probe of the border walk is a
+// shared-memory bit test instead of a global byte load.  Pass 1: every "tip" pixel (set, West and the three pixels
+// above empty) starts a walk on its own thread; walks that are not an outer border's first pixel stop at the first
+// raster-earlier pixel they meet, completed walks compete by (|a00|, start index) through one 64-bit atomicMax
+// (ties go to the later start: cv2 returns contours in reverse discovery order and Python's max keeps the first).
+// The largest outer border over ALL components is the largest EXTERNAL one (a component nested in a hole is
+// strictly inside a larger border), so no hierarchy is needed.  Pass 2: one thread re-walks the winner and writes
+// its points.  Latency-bound by design (a 3000-pixel lumen border is a 3000-step dependent chain); the work that
+// parallelises -- packing, tip search, all the small walks -- is spread over the block.
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "common.h"
+#include "contour_core.h"
+
+namespace octseg {
+
+constexpr int kContourThreads = 512;
+
+__global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const uint32_t* __restrict__ mask, int H, int W,
+                                                                          int pitch, long long* __restrict__ sums,
+                                                                          int* __restrict__ nverts,
+                                                                          int16_t* __restrict__ verts, int cap) {
+  extern __shared__ uint32_t pl[];  // (H + 2) x pitch
+  __shared__ unsigned long long best;
+  const int c = blockIdx.x, n = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kContourThreads / 32;
+  for (int i = tid; i < pitch; i += kContourThreads) pl[i] = 0u, pl[(H + 1) * pitch + i] = 0u;
+  if (tid == 0) best = 0ull;
+  const uint32_t* mimg = mask + static_cast<size_t>(n) * H * W;
+  const uint32_t sel = 0xffu << (8 * c);
+  for (int it = warp; it < H * pitch; it += kWarps) {
+    const int y = it / pitch, k = it - y * pitch;
+    const int x = 32 * k + lane - 1;
+    const bool on = x >= 0 && x < W && (__ldg(mimg + static_cast<size_t>(y) * W + x) & sel) != 0u;
+    const uint32_t w = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) pl[(y + 1) * pitch + k] = w;
+  }
+  __syncthreads();
+
+  const long long max_steps = 4ll * H * W + 16;
+  unsigned long long mine = 0ull;
+  for (int i = tid; i < H * pitch; i += kContourThreads) {
+    const int y = i / pitch, k = i - y * pitch;
+    uint32_t tips = tip_bits(pl, pitch, y + 1, k);
+    while (tips) {
+      const int b = __ffs(tips) - 1;
+      tips &= tips - 1;
+      const int x = 32 * k + b - 1;
+      ContourSums s;
+      if (!trace_border<false>(pl, pitch, x, y, s, nullptr, 0, max_steps)) continue;
+      const unsigned long long area = static_cast<unsigned long long>(s.a00 < 0 ? -s.a00 : s.a00);
+      if (area > 0) mine = max(mine, (area << 32) | static_cast<unsigned>(y * W + x));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+  if (lane == 0 && mine) atomicMax(&best, mine);
+  __syncthreads();
+  if (tid == 0) {
+    const size_t o = static_cast<size_t>(n) * 4 + c;
+    ContourSums s;
+    s.a00 = s.a10 = s.a01 = 0;
+    s.nverts = 0;
+    long long start = -1;
+    if (best) {
+      start = static_cast<long long>(best & 0xffffffffull);
+      trace_border<true>(pl, pitch, static_cast<int>(start % W), static_cast<int>(start / W), s, verts + o * cap * 2, cap, max_steps);
+    }
+    sums[o * 4] = s.a00;
+    sums[o * 4 + 1] = s.a10;
+    sums[o * 4 + 2] = s.a01;
+    sums[o * 4 + 3] = start;
+    nverts[o] = s.nverts;
+  }
+}
+
+}  // namespace octseg
+
+using namespace octseg;
+
+extern "C" int octseg_contour_largest(const uint8_t* mask, int32_t N, int32_t H, int32_t W, int64_t* sums, int32_t* nverts,
+                                      int16_t* verts, int32_t cap, void* stream) {
+  if (!mask || !sums || !nverts || !verts) return fail(OCTSEG_EINVAL, "contour_largest: null argument");
+  if (reinterpret_cast<uintptr_t>(mask) & 3) return fail(OCTSEG_EINVAL, "contour_largest: mask must be 4-byte aligned");
+  if (N <= 0 || H <= 0 || W <= 0) return OCTSEG_OK;
+  if (N > 65535 || H > 32766 || W > 32766 || cap < 0) return fail(OCTSEG_EINVAL, "contour_largest: N <= 65535, H, W <= 32766, cap >= 0");
+  const int pitch = (W + 2 + 31) / 32;
+  const size_t smem = static_cast<size_t>(H + 2) * pitch * 4;
+  if (smem > 226 * 1024)
+    return fail(OCTSEG_EINVAL, "contour_largest: the %d x %d bit plane (%zu bytes) does not fit shared memory", H, W, smem);
+  static unsigned long long configured = 0;  // bit d = attribute set on device d
+  int dev = 0;
+  OCTSEG_CUDA(cudaGetDevice(&dev));
+  if (!((configured >> (dev & 63)) & 1ull)) {
+    OCTSEG_CUDA(cudaFuncSetAttribute(contour_largest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    configured |= 1ull << (dev & 63);
+  }
+  contour_largest_kernel<<<dim3(4, N), kContourThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint32_t*>(mask), H, W, pitch, reinterpret_cast<long long*>(sums), nverts, verts, cap);
+  return check_launch("contour_largest_kernel");
+}

@@ -1,0 +1,107 @@
+// Border following on a bit plane: the arithmetic core of octseg_contour_largest (csrc/contour.cu), written as
+// host+device code so tests/contour_core_harness.cpp can run the very same functions on the CPU against cv2.
+//
+// cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) as used by calculate_thickness_contour
+// (src/app/tools/analysis.py:21-57) is Suzuki-Abe border following (OpenCV 4.8.1 contours.cpp, icvFetchContour;
+// third-party, restated from its published algorithm):
+//   * an outer border starts at the raster-first pixel of an 8-connected component; from there the first non-zero
+//     neighbour is searched CLOCKWISE starting after West, then each step searches COUNTER-CLOCKWISE starting
+//     after the direction it arrived from; the walk ends when it re-enters the start pixel from the first
+//     neighbour found;
+//   * CHAIN_APPROX_SIMPLE keeps a point only when the step direction leaving it differs from the one before.
+// A walk started at any other "tip" (left and the three upper neighbours empty) meets a raster-earlier pixel and
+// is abandoned there, so completed walks are exactly the outer borders, one per component.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define OCTSEG_HD __host__ __device__ __forceinline__
+#else
+#define OCTSEG_HD inline
+#endif
+
+namespace octseg {
+
+// plane: (H + 2) rows x pitch words, pixel (x, y) at bit (x + 1) of row (y + 1); the one-pixel frame is zero
+OCTSEG_HD uint32_t plane_get(const uint32_t* pl, int pitch, int x, int y) {
+  return (pl[(y + 1) * pitch + ((x + 1) >> 5)] >> ((x + 1) & 31)) & 1u;
+}
+
+struct ContourSums {
+  long long a00, a10, a01;  // cv2 contourMoments' integer accumulators (m00 = a00/2, m10 = a10/6, m01 = a01/6 up to sign)
+  int nverts;
+};
+
+// direction codes of cv2 (y grows downwards): 0 E, 1 NE, 2 N, 3 NW, 4 W, 5 SW, 6 S, 7 SE
+OCTSEG_HD void code_delta(int s, int& dx, int& dy) {
+  // dx: {1, 1, 0, -1, -1, -1, 0, 1}, dy: {0, -1, -1, -1, 0, 1, 1, 1}; packed 2 bits per entry (value + 1)
+  dx = static_cast<int>((0x901Au >> (2 * s)) & 3u) - 1;
+  dy = static_cast<int>((0xA901u >> (2 * s)) & 3u) - 1;
+}
+
+// Walks the border that starts at (x0, y0) (a pixel whose West neighbour is empty).  Returns false when the walk
+// meets a pixel that precedes the start in raster order (not an outer border's first pixel) or exceeds max_steps.
+// EMIT: also write the kept points (x, y as int16 pairs, at most cap of them; sums.nverts counts all) and a10/a01.
+template <bool EMIT>
+OCTSEG_HD bool trace_border(const uint32_t* pl, int pitch, int x0, int y0, ContourSums& sums, int16_t* verts, int cap,
+                            long long max_steps) {
+  sums.a00 = sums.a10 = sums.a01 = 0;
+  sums.nverts = 0;
+  int s = 4, dx, dy;
+  do {
+    s = (s - 1) & 7;
+    code_delta(s, dx, dy);
+  } while (!plane_get(pl, pitch, x0 + dx, y0 + dy) && s != 4);
+  if (s == 4) {  // single-pixel component
+    sums.nverts = 1;
+    if (EMIT && cap > 0) verts[0] = static_cast<int16_t>(x0), verts[1] = static_cast<int16_t>(y0);
+    return true;
+  }
+  const int x1 = x0 + dx, y1 = y0 + dy;
+  int x3 = x0, y3 = y0, prev_s = s ^ 4;
+  int fx = 0, fy = 0, px = 0, py = 0;  // first and previous kept point
+  for (long long step = 0; step < max_steps; ++step) {
+    int x4, y4;
+    for (;;) {
+      ++s;
+      code_delta(s & 7, dx, dy);
+      x4 = x3 + dx, y4 = y3 + dy;
+      if (plane_get(pl, pitch, x4, y4)) break;
+    }
+    s &= 7;
+    if (s != prev_s) {
+      if (sums.nverts == 0) {
+        fx = x3, fy = y3;
+      } else {
+        const long long dxy = static_cast<long long>(px) * y3 - static_cast<long long>(x3) * py;
+        sums.a00 += dxy;
+        if (EMIT) sums.a10 += dxy * (px + x3), sums.a01 += dxy * (py + y3);
+      }
+      if (EMIT && sums.nverts < cap) verts[2 * sums.nverts] = static_cast<int16_t>(x3), verts[2 * sums.nverts + 1] = static_cast<int16_t>(y3);
+      ++sums.nverts;
+      px = x3, py = y3;
+      prev_s = s;
+    }
+    if (y4 < y0 || (y4 == y0 && x4 < x0)) return false;
+    if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) {
+      const long long dxy = static_cast<long long>(px) * fy - static_cast<long long>(fx) * py;  // closing edge last -> first
+      sums.a00 += dxy;
+      if (EMIT) sums.a10 += dxy * (px + fx), sums.a01 += dxy * (py + fy);
+      return true;
+    }
+    x3 = x4, y3 = y4;
+    s = (s + 4) & 7;
+  }
+  return false;
+}
+
+// candidate start bits of one plane word: pixel set, West empty, the three pixels above empty
+OCTSEG_HD uint32_t tip_bits(const uint32_t* pl, int pitch, int row /* plane row = y + 1 */, int k) {
+  const uint32_t* r = pl + row * pitch + k;
+  const uint32_t* u = r - pitch;
+  const uint32_t cur = r[0], west = (cur << 1) | (k > 0 ? r[-1] >> 31 : 0u);
+  const uint32_t up = u[0], upw = (up << 1) | (k > 0 ? u[-1] >> 31 : 0u), upe = (up >> 1) | (k < pitch - 1 ? u[1] << 31 : 0u);
+  return cur & ~west & ~up & ~upw & ~upe;
+}
+
+}  // namespace octseg

@@ -196,6 +196,44 @@ def fold_average_threshold(logits: Sequence[torch.Tensor], out: Optional[torch.T
     return out
 
 
+CONTOUR_CAP = 16384   # kept border points per (frame, class) the device buffer holds
+
+
+def contour_largest(mask: torch.Tensor, cap: int = CONTOUR_CAP):
+    """mask: uint8 CUDA (N, H, W, 4), non-zero = object.  Per (frame, class) the largest outer border in
+    cv2's CHAIN_APPROX_SIMPLE form (== max(findContours(RETR_EXTERNAL), key=contourArea), analysis.py:25-35):
+    returns device (sums int64 (N, 4, 4) = a00, a10, a01, start index | -1; nverts int32 (N, 4); verts int16
+    (N, 4, cap, 2) as x, y)."""
+    assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+    N, H, W, _ = mask.shape
+    sums = torch.empty(N, 4, 4, dtype=torch.int64, device=mask.device)
+    nverts = torch.empty(N, 4, dtype=torch.int32, device=mask.device)
+    verts = torch.empty(N, 4, cap, 2, dtype=torch.int16, device=mask.device)
+    with torch.cuda.device(mask.device):
+        _lib.check(_lib.load().octseg_contour_largest(mask.data_ptr(), N, H, W, sums.data_ptr(), nverts.data_ptr(),
+                                                      verts.data_ptr(), cap, _lib.stream_ptr()), 'contour_largest')
+    return sums, nverts, verts
+
+
+def thickness_from_contour(sums: np.ndarray, nverts: int, verts: np.ndarray) -> Dict[str, float]:
+    """Host finish of calculate_thickness_contour (src/app/tools/analysis.py:37-57) from the device result of one
+    (frame, class): centroid from cv2's polygon moments (m00 = a00 * +-0.5, m10 = a10 * +-(1/6), same double
+    operations as contourMoments), int-truncated; distances centroid -> kept border points; median / min / max."""
+    a00, a10, a01 = int(sums[0]), int(sums[1]), int(sums[2])
+    if nverts == 0 or a00 == 0:
+        return {'median': 0, 'min': 0, 'max': 0}
+    if nverts > verts.shape[0]:
+        raise RuntimeError(f'contour of {nverts} points exceeds the device buffer ({verts.shape[0]}); raise `cap`')
+    sign = 1.0 if a00 > 0 else -1.0
+    m00 = float(a00) * (sign * 0.5)
+    m10 = float(a10) * (sign * 0.16666666666666666666666666666667)
+    m01 = float(a01) * (sign * 0.16666666666666666666666666666667)
+    cx, cy = int(m10 / m00), int(m01 / m00)
+    pts = verts[:nverts].astype(np.int64)
+    d = np.sqrt((pts[:, 0] - cx) ** 2 + (pts[:, 1] - cy) ** 2)
+    return {'median': float(np.median(d)), 'min': float(np.min(d)), 'max': float(np.max(d))}
+
+
 def dicom_ratio(h: int) -> int:
     return int(h * 150 // 1000)
 

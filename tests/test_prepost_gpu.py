@@ -196,3 +196,82 @@ def test_fold_average_threshold_vs_oracle(K, shape):
     assert sure.mean() > 0.999 and np.array_equal(got[sure], want[sure])
     if K == 1:
         assert np.array_equal(got, (logits[0] > 0).astype(np.uint8))
+
+
+def _gpu_contour_thickness(mask4, cap=P.CONTOUR_CAP):
+    sums, nverts, verts = (t.cpu().numpy() for t in P.contour_largest(torch.from_numpy(np.ascontiguousarray(mask4)).cuda(), cap))
+    return sums, nverts, verts
+
+
+@pytest.mark.parametrize('H,W', [(1, 1), (5, 3), (31, 33), (64, 64), (70, 129), (200, 255)])
+def test_contour_largest_equals_cv2(H, W):
+    """octseg_contour_largest vs cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) + max(contourArea): same points
+    in the same order, same thickness dict as calculate_thickness_contour (analysis.py:21-57); noise at several
+    densities, blobs, nested components, arbitrary non-zero bytes, empty and full planes."""
+    rng = np.random.default_rng(H * 31 + W)
+    N = 6
+    m = np.zeros((N, H, W, 4), np.uint8)
+    for n in range(N):
+        for c in range(4):
+            p = (rng.random((H, W)) < rng.choice([0.05, 0.3, 0.5, 0.7, 0.95])).astype(np.uint8)
+            if (n + c) % 2:
+                p = cv2.dilate(p, np.ones((3, 3), np.uint8))
+            if c == 3:
+                p = p * rng.integers(1, 256, (H, W)).astype(np.uint8)
+            m[n, :, :, c] = p
+    m[0, :, :, 0] = 0
+    m[0, :, :, 1] = 1
+    sums, nverts, verts = _gpu_contour_thickness(m)
+    for n in range(N):
+        for c in range(4):
+            ch = np.ascontiguousarray(m[n, :, :, c])
+            contours, _ = cv2.findContours(ch, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+            best = max(contours, key=cv2.contourArea) if contours else None
+            if best is None or cv2.contourArea(best) == 0:
+                assert nverts[n, c] == 0 and sums[n, c, 3] == -1
+            else:
+                assert np.array_equal(verts[n, c, :nverts[n, c]], best.reshape(-1, 2)), (n, c)
+                assert abs(int(sums[n, c, 0])) == 2 * cv2.contourArea(best)
+            assert P.thickness_from_contour(sums[n, c], int(nverts[n, c]), verts[n, c]) == R.thickness_contour(ch), (n, c)
+
+
+def test_contour_thickness_matches_reference_function_goldens():
+    """tests/golden/quantities_ref.npz: calculate_thickness_contour's own outputs on the reference's 750 x 750 demo masks."""
+    d = np.load(os.path.join(G, 'masks_app_demo.npz'))
+    q = np.load(os.path.join(G, 'quantities_ref.npz'))
+    masks = np.stack([unpack(p, d['shape']) for p in d['packed']])
+    sums, nverts, verts = _gpu_contour_thickness(masks)
+    for k in range(masks.shape[0]):
+        for c in range(4):
+            t = P.thickness_from_contour(sums[k, c], int(nverts[k, c]), verts[k, c])
+            assert t['median'] == q['q'][k, c, 3] and t['min'] == q['q'][k, c, 4], (k, c)
+
+
+def test_contour_thickness_full_size():
+    """1000 x 1000: OCT-shaped masks and noise against the cv2 oracle; a disc's border is found whole (every kept
+    point within one pixel of the radius); capacity overflow is reported, never truncated silently."""
+    H = W = 1000
+    yy, xx = np.mgrid[:H, :W]
+    rr = np.sqrt((yy - 500.0) ** 2 + (xx - 480.0) ** 2)
+    m = np.zeros((2, H, W, 4), np.uint8)
+    m[0, :, :, 0] = rr < 220
+    m[0, :, :, 1] = (rr >= 220) & (rr < 260) & (np.abs(np.arctan2(yy - 500.0, xx - 480.0)) < 1.0)
+    m[0, :, :, 2] = (np.random.default_rng(1).random((H, W)) < 0.3)      # below the 8-connected percolation threshold
+    m[0, :, :, 3] = ((yy - 200) ** 2 + (xx - 300) ** 2 < 64) | ((yy - 750) ** 2 + (xx - 700) ** 2 < 100)
+    m[1, 0, :, 0] = 1
+    m[1, :, 0, 0] = 1
+    m[1, -1, :, 0] = 1
+    m[1, :, -1, 0] = 1                                    # a frame-sized ring: the border walks all four image edges
+    m[1, 3:-3:2, 3:-3, 1] = 1
+    m[1, 3:-3, 3, 1] = 1                                  # a comb with ~ 2000 kept points
+    sums, nverts, verts = _gpu_contour_thickness(m)
+    for n in range(2):
+        for c in range(4):
+            ch = np.ascontiguousarray(m[n, :, :, c])
+            assert P.thickness_from_contour(sums[n, c], int(nverts[n, c]), verts[n, c]) == R.thickness_contour(ch), (n, c)
+    v = verts[0, 0, :nverts[0, 0]].astype(np.float64)
+    assert np.all(np.abs(np.sqrt((v[:, 1] - 500) ** 2 + (v[:, 0] - 480) ** 2) - 220) < 1.5)
+    s2, n2, v2 = _gpu_contour_thickness(m[1:], cap=64)
+    assert n2[0, 1] > 64
+    with pytest.raises(RuntimeError):
+        P.thickness_from_contour(s2[0, 1], int(n2[0, 1]), v2[0, 1])

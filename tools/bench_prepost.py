@@ -77,6 +77,9 @@ def main():
         ms = timeit([lambda i=i: prepost.overlay(big[i], mm[i], [0, 1, 2, 3], overs[i]) for i in range(sets)])
         print(json.dumps(dict(kernel='overlay', masks=what, impl=os.environ.get('OCTSEG_OVERLAY_IMPL', 'default'), Ho=HO, frames=N,
                               ms=round(ms, 4), GBps=round(b / ms / 1e6, 1), frac_of_hbm=round(b / ms / 1e6 / peak, 3))), flush=True)
+    for what, mm in (('OCT-shaped masks', shaped), ('noise masks (worst case)', masks[0])):
+        ms = timeit([lambda: prepost.contour_largest(mm)], reps=3)
+        print(json.dumps(dict(kernel='contour_largest', masks=what, frames=N, ms=round(ms, 4))), flush=True)
     K = 5
     folds = [[torch.randn(N, 1, 896, 896, device='cuda') for _ in range(K)] for _ in range(2)]
     fouts = [torch.empty(N, 1, 896, 896, dtype=torch.uint8, device='cuda') for _ in range(2)]
