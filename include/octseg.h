@@ -239,8 +239,8 @@ int octseg_fold_average_threshold(const float* const* h_logits, int32_t K, int64
    sums int64 [N][4][4] = a00, a10, a01 (the integer accumulators of cv2's polygon moments: m00 = |a00|/2, ...)
    and the start pixel index y*W+x (-1: no border with non-zero area); nverts int32 [N][4] = kept points of that
    border (may exceed cap: only the first cap are stored); verts int16 [N][4][cap][2] = x, y.
-   The host finishes centroid (int-truncated), distances, median / min / max.  (H+2)*ceil((W+2)/32)*4 bytes of
-   shared memory must fit 226 KB (1000 x 1000: 128 KB). */
+   The host finishes centroid (int-truncated), distances, median / min / max.  (H+2)*(ceil((W+1)/32)+1)*4 bytes of
+   shared memory must fit 226 KB (1000 x 1000: 132 KB). */
 int octseg_contour_largest(const uint8_t* mask, int32_t N, int32_t H, int32_t W, int64_t* sums, int32_t* nverts,
                            int16_t* verts, int32_t cap, void* stream);
 

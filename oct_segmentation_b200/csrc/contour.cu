@@ -2,7 +2,7 @@
 // border of cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE), bit-exact (same points in the same order),
 // with the integer accumulators of cv2's polygon moments; the host finishes centroid / distances / median.
 //
-// One block per (class, frame).  The class's bit plane (1 bit per pixel, one-pixel zero frame: 128 KB at
+// One block per (class, frame).  The class's bit plane (1 bit per pixel, one-pixel zero frame: 132 KB at
 // 1000 x 1000) is packed into shared memory with warp ballots, so every probe of the border walk is a
 // shared-memory bit test instead of a global byte load.  Pass 1: every "tip" pixel (set, West and the three pixels
 // above empty) starts a walk on its own thread; walks that are not an outer border's first pixel stop at the first
@@ -32,16 +32,48 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kContourThreads / 32;
   for (int i = tid; i < pitch; i += kContourThreads) pl[i] = 0u, pl[(H + 1) * pitch + i] = 0u;
-  if (tid == 0) best = 0ull;
+  if (tid == 0) best = 0ull, pl[(H + 2) * pitch] = 0u;
   const uint32_t* mimg = mask + static_cast<size_t>(n) * H * W;
-  const uint32_t sel = 0xffu << (8 * c);
-  for (int it = warp; it < H * pitch; it += kWarps) {
-    const int y = it / pitch, k = it - y * pitch;
-    const int x = 32 * k + lane - 1;
-    const bool on = x >= 0 && x < W && (__ldg(mimg + static_cast<size_t>(y) * W + x) & sel) != 0u;
-    const uint32_t w = __ballot_sync(0xffffffffu, on);
-    if (lane == 0) pl[(y + 1) * pitch + k] = w;
+  // pack: one item = 128 pixels of a row (4 plane words).  A lane loads 4 pixels (16 bytes) and keeps the 4 presence
+  // bits of class c; the nibbles of the 8 lanes of a word are OR-reduced with redux.sync over that lane group.
+  // Four items are loaded before any is reduced: the loop is bound by load latency, not by issue.
+  const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
+  const int units = (pitch - 1 + 3) / 4, items = H * units;
+  const unsigned gm = 0xffu << (lane & 24);
+  for (int base = warp; base < items; base += 4 * kWarps) {
+    uint4 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int it = base + j * kWarps;
+      q[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (it < items) {
+        const int y = it / units, x = 128 * (it - y * units) + 4 * lane;
+        if (x < W) {
+          const uint32_t* src = mimg + static_cast<size_t>(y) * W + x;
+          if (vec_ok) {
+            q[j] = __ldg(reinterpret_cast<const uint4*>(src));
+          } else {
+            q[j].x = __ldg(src);
+            if (x + 1 < W) q[j].y = __ldg(src + 1);
+            if (x + 2 < W) q[j].z = __ldg(src + 2);
+            if (x + 3 < W) q[j].w = __ldg(src + 3);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int it = base + j * kWarps;
+      if (it >= items) break;  // warp-uniform
+      const int y = it / units, u = it - y * units;
+      const uint32_t nib = ((q[j].x >> (8 * c)) & 0xffu ? 1u : 0u) | ((q[j].y >> (8 * c)) & 0xffu ? 2u : 0u) |
+                           ((q[j].z >> (8 * c)) & 0xffu ? 4u : 0u) | ((q[j].w >> (8 * c)) & 0xffu ? 8u : 0u);
+      const uint32_t w = __reduce_or_sync(gm, nib << (4 * (lane & 7)));
+      const int k = 1 + 4 * u + (lane >> 3);
+      if ((lane & 7) == 0 && k < pitch) pl[(y + 1) * pitch + k] = w;
+    }
   }
+  for (int y = tid; y < H; y += kContourThreads) pl[(y + 1) * pitch] = 0u;
   __syncthreads();
 
   const long long max_steps = 4ll * H * W + 16;
@@ -52,7 +84,7 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
     while (tips) {
       const int b = __ffs(tips) - 1;
       tips &= tips - 1;
-      const int x = 32 * k + b - 1;
+      const int x = 32 * k + b - 32;
       ContourSums s;
       if (!trace_border<false>(pl, pitch, x, y, s, nullptr, 0, max_steps)) continue;
       const unsigned long long area = static_cast<unsigned long long>(s.a00 < 0 ? -s.a00 : s.a00);
@@ -91,8 +123,8 @@ extern "C" int octseg_contour_largest(const uint8_t* mask, int32_t N, int32_t H,
   if (reinterpret_cast<uintptr_t>(mask) & 3) return fail(OCTSEG_EINVAL, "contour_largest: mask must be 4-byte aligned");
   if (N <= 0 || H <= 0 || W <= 0) return OCTSEG_OK;
   if (N > 65535 || H > 32766 || W > 32766 || cap < 0) return fail(OCTSEG_EINVAL, "contour_largest: N <= 65535, H, W <= 32766, cap >= 0");
-  const int pitch = (W + 2 + 31) / 32;
-  const size_t smem = static_cast<size_t>(H + 2) * pitch * 4;
+  const int pitch = plane_pitch(W);
+  const size_t smem = (static_cast<size_t>(H + 2) * pitch + 1) * 4;
   if (smem > 226 * 1024)
     return fail(OCTSEG_EINVAL, "contour_largest: the %d x %d bit plane (%zu bytes) does not fit shared memory", H, W, smem);
   static unsigned long long configured = 0;  // bit d = attribute set on device d

@@ -22,9 +22,35 @@
 
 namespace octseg {
 
-// plane: (H + 2) rows x pitch words, pixel (x, y) at bit (x + 1) of row (y + 1); the one-pixel frame is zero
+// plane: (H + 2) rows x pitch words (+ 1 spare word at the end), pitch = plane_pitch(W); pixel (x, y) at bit (x + 32) of row (y + 1): word 0 of
+// a row, rows 0 and H + 1 and the bits from W on are zero, so probes one pixel outside the image need no bounds test
+// and a word holds 32 pixels starting at a multiple of 32 (16-byte mask loads pack without crossing words)
+OCTSEG_HD int plane_pitch(int W) { return (W + 1 + 31) / 32 + 1; }
 OCTSEG_HD uint32_t plane_get(const uint32_t* pl, int pitch, int x, int y) {
-  return (pl[(y + 1) * pitch + ((x + 1) >> 5)] >> ((x + 1) & 31)) & 1u;
+  return (pl[(y + 1) * pitch + ((x + 32) >> 5)] >> (x & 31)) & 1u;
+}
+
+OCTSEG_HD int ctz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ffs(static_cast<int>(v)) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+
+// bits x-1, x, x+1 of plane row `row` (bit 0 = x-1); the word after the row's last is the next row's zero word 0
+OCTSEG_HD uint32_t row3(const uint32_t* pl, int pitch, int row, int x) {
+  const int p = x + 31;  // plane bit of x - 1
+  const uint32_t* w = pl + row * pitch + (p >> 5);
+  const unsigned long long v = (static_cast<unsigned long long>(w[1]) << 32) | w[0];
+  return static_cast<uint32_t>(v >> (p & 31)) & 7u;
+}
+
+// bit d = the neighbour of (x, y) in cv2 direction d (0 E, 1 NE, 2 N, 3 NW, 4 W, 5 SW, 6 S, 7 SE) is set
+OCTSEG_HD uint32_t neighbours8(const uint32_t* pl, int pitch, int x, int y) {
+  const uint32_t up = row3(pl, pitch, y, x), mid = row3(pl, pitch, y + 1, x), dn = row3(pl, pitch, y + 2, x);
+  return (mid >> 2) | ((up >> 2) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((mid & 1u) << 4) | ((dn & 1u) << 5) |
+         (((dn >> 1) & 1u) << 6) | ((dn >> 2) << 7);
 }
 
 struct ContourSums {
@@ -61,13 +87,12 @@ OCTSEG_HD bool trace_border(const uint32_t* pl, int pitch, int x0, int y0, Conto
   int x3 = x0, y3 = y0, prev_s = s ^ 4;
   int fx = 0, fy = 0, px = 0, py = 0;  // first and previous kept point
   for (long long step = 0; step < max_steps; ++step) {
-    int x4, y4;
-    for (;;) {
-      ++s;
-      code_delta(s & 7, dx, dy);
-      x4 = x3 + dx, y4 = y3 + dy;
-      if (plane_get(pl, pitch, x4, y4)) break;
-    }
+    // the 8 neighbours of (x3, y3) as one byte (bit d = direction d), then the first one counter-clockwise after s
+    const uint32_t nb = neighbours8(pl, pitch, x3, y3);
+    const uint32_t rot = ((nb | (nb << 8)) >> ((s + 1) & 7)) & 0xffu;  // never 0: the pixel we came from is set
+    s = s + 1 + ctz32(rot);
+    code_delta(s & 7, dx, dy);
+    const int x4 = x3 + dx, y4 = y3 + dy;
     s &= 7;
     if (s != prev_s) {
       if (sums.nverts == 0) {

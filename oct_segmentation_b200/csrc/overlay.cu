@@ -9,7 +9,7 @@
 //
 // overlay_kernel (the product path): the morphology runs on BIT PLANES -- one 32-bit word = 32 pixels of one
 // row of one class -- so a dilation / erosion row is a handful of funnel shifts and ORs / ANDs for 32 pixels.
-// One block = 128 x TY output pixels; region = tile + 7 halo rows and one halo word (32 px) per side:
+// One block = 128 x TY output pixels (TY = 32); region = tile + 7 halo rows and one halo word (32 px) per side:
 //   S0  mask words (4 class bytes per pixel, 16-byte loads) -> bit planes M   (nibbles OR-reduced over 8 lanes)
 //   S1  D  = dilate5(M), image exterior forced to 1 (erode's border value)
 //   S2  E  = erode5(D);  Cd = E inside / 0 outside, Ce = E inside / 1 outside, Cr = Cd + reflected columns
@@ -443,6 +443,6 @@ extern "C" int octseg_overlay(const uint8_t* img, const uint8_t* mask, uint8_t* 
     overlay_bytes_kernel<<<grid, dim3(kOvX, kOvY), 0, static_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("overlay_bytes_kernel");
   }
-  if (impl && !strcmp(impl, "ty32")) return launch_overlay<32>(p, static_cast<cudaStream_t>(stream));
-  return launch_overlay<64>(p, static_cast<cudaStream_t>(stream));
+  if (impl && !strcmp(impl, "ty64")) return launch_overlay<64>(p, static_cast<cudaStream_t>(stream));
+  return launch_overlay<32>(p, static_cast<cudaStream_t>(stream));  // 128 x 32 tiles: 0.40 vs 0.47 ms per 32 frames at 1000 x 1000
 }

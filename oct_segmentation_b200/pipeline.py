@@ -27,9 +27,16 @@ MODELS_META = {
 }
 
 
+def _copy(o):
+    if o is None:
+        return None
+    return tuple(a.copy() for a in o) if isinstance(o, tuple) else o.copy()
+
+
 class EnsemblePipeline:
     def __init__(self, models: Dict[str, Tuple[object, Dict]], classes: Sequence[str], output_size: Sequence[int],
-                 device, batch: int, src_hw: Optional[Tuple[int, int]] = None, thickness: bool = False):
+                 device, batch: int, src_hw: Optional[Tuple[int, int]] = None, thickness: bool = False,
+                 contour: bool = False):
         """models: {model_dir: (OCTSegmentationModel, cfg with 'input_size')} for every model_dir the
         requested classes need.  output_size: cv2 convention (width, height), as in the reference.
         Opt-in K-way probability averaging (north-star "ensemble averaging"; never the default -- the reference
@@ -43,6 +50,7 @@ class EnsemblePipeline:
         self.Wo, self.Ho = int(output_size[0]), int(output_size[1])
         self.batch = batch
         self.thickness = thickness
+        self.contour = contour      # also return the largest outer border per class (contour thickness, analysis.py:21-57)
         self.src_hw = tuple(src_hw) if src_hw is not None else (self.Ho, self.Wo)
         self.model_dirs = []
         for c in self.classes:
@@ -77,11 +85,13 @@ class EnsemblePipeline:
             self.counts = torch.zeros(batch, 4, dtype=torch.int32, device=self.device)
         all_nets = [net for d in self.model_dirs for net in self.fold_nets[d]]
         self.macs_per_frame = sum(net.macs for net in all_nets) / batch
-        self.launches_per_batch = (sum(net.launches + 1 for net in all_nets) + len(self.fold_planes) + 1 + int(thickness))
+        self.launches_per_batch = (sum(net.launches + 1 for net in all_nets) + len(self.fold_planes) + 1 + int(thickness) + int(contour))
 
     # ------------------------------------------------------------------ device-resident step
     def run_device(self, frames_dev: torch.Tensor):
-        """frames_dev: uint8 CUDA (batch, Hs, Ws, 3) RGB.  Returns device (mask, label, counts[, radii])."""
+        """frames_dev: uint8 CUDA (batch, Hs, Ws, 3) RGB.  Returns device (mask, label, counts, radii | None) and,
+        when the pipeline was built with contour=True, a fifth element (sums, nverts, verts) of
+        ``prepost.contour_largest``."""
         class_planes = {}
         cur = torch.cuda.current_stream(self.device)
         self.ev_in.record(cur)
@@ -104,6 +114,8 @@ class EnsemblePipeline:
         P.postprocess(class_planes, self.order, self.Ho, self.Wo, self.batch, self.device,
                       mask=self.mask, label=self.label, counts=self.counts)
         radii = P.radial_thickness(self.mask) if self.thickness else None
+        if self.contour:
+            return self.mask, self.label, self.counts, radii, P.contour_largest(self.mask)
         return self.mask, self.label, self.counts, radii
 
     # ------------------------------------------------------------------ host-to-host step
@@ -117,7 +129,14 @@ class EnsemblePipeline:
                 'counts': torch.empty(self.batch, 4, dtype=torch.int32).pin_memory(),
                 'radii': torch.empty(self.batch, 4, 360, dtype=torch.int32).pin_memory(),
             }
+            if self.contour:
+                self._pinned.update(self._contour_pinned())
         return self._pinned
+
+    def _contour_pinned(self):
+        return {'c_sums': torch.empty(self.batch, 4, 4, dtype=torch.int64).pin_memory(),
+                'c_nverts': torch.empty(self.batch, 4, dtype=torch.int32).pin_memory(),
+                'c_verts': torch.empty(self.batch, 4, P.CONTOUR_CAP, 2, dtype=torch.int16).pin_memory()}
 
     def run_host(self, frames: np.ndarray, copy: bool = True):
         """frames: uint8 (n <= batch, Hs, Ws, 3) host array.  Returns host (mask, label, counts[, radii])
@@ -132,7 +151,9 @@ class EnsemblePipeline:
             self.frames_dev[:n].copy_(hb['frames'][:n], non_blocking=True)
             if n < self.batch:
                 self.frames_dev[n:].zero_()
-            mask, label, counts, radii = self.run_device(self.frames_dev)
+            mask, label, counts, radii, *extra = self.run_device(self.frames_dev)
+            for key, t in zip(('c_sums', 'c_nverts', 'c_verts'), extra[0] if extra else ()):
+                hb[key][:n].copy_(t[:n], non_blocking=True)
             hb['mask'][:n].copy_(mask[:n], non_blocking=True)
             hb['label'][:n].copy_(label[:n], non_blocking=True)
             hb['counts'][:n].copy_(counts[:n], non_blocking=True)
@@ -141,8 +162,10 @@ class EnsemblePipeline:
             torch.cuda.current_stream().synchronize()
         out = [hb['mask'][:n].numpy(), hb['label'][:n].numpy(), hb['counts'][:n].numpy(),
                hb['radii'][:n].numpy() if radii is not None else None]
+        if self.contour:
+            out.append(tuple(hb[key][:n].numpy() for key in ('c_sums', 'c_nverts', 'c_verts')))
         if copy:
-            out = [o.copy() if o is not None else None for o in out]
+            out = [_copy(o) for o in out]
         return tuple(out)
 
     # ------------------------------------------------------------------ pipelined host-to-host stream
@@ -162,6 +185,7 @@ class EnsemblePipeline:
                         'dev_mask': torch.empty_like(self.mask), 'dev_label': torch.empty_like(self.label),
                         'dev_counts': torch.empty_like(self.counts),
                         'dev_radii': torch.empty(self.batch, 4, 360, dtype=torch.int32, device=self.device),
+                        **(self._contour_pinned() if self.contour else {}),
                         'ev_h2d': torch.cuda.Event(), 'ev_in_free': torch.cuda.Event(),
                         'ev_out_ready': torch.cuda.Event(), 'ev_d2h': torch.cuda.Event(), 'used': False,
                     })
@@ -184,8 +208,10 @@ class EnsemblePipeline:
             S['ev_d2h'].synchronize()
             out = [S['pin_mask'][:n].numpy(), S['pin_label'][:n].numpy(), S['pin_counts'][:n].numpy(),
                    S['pin_radii'][:n].numpy() if with_radii else None]
+            if self.contour:
+                out.append(tuple(S[key][:n].numpy() for key in ('c_sums', 'c_nverts', 'c_verts')))
             if copy:
-                out = [o.copy() if o is not None else None for o in out]
+                out = [_copy(o) for o in out]
             return tuple(out)
 
         with torch.cuda.device(self.device):
@@ -208,9 +234,11 @@ class EnsemblePipeline:
                 if n < self.batch:
                     self.frames_dev[n:].zero_()
                 S['ev_in_free'].record(cur)
-                mask, label, counts, radii = self.run_device(self.frames_dev)
+                mask, label, counts, radii, *extra = self.run_device(self.frames_dev)
                 if S['used']:
                     cur.wait_event(S['ev_d2h'])             # batch i-2's results have left the device staging buffers
+                if extra:                                   # fresh tensors per call: kept alive in S until their D2H is done
+                    S['dev_contour'] = extra[0]
                 S['dev_mask'][:n].copy_(mask[:n], non_blocking=True)
                 S['dev_label'][:n].copy_(label[:n], non_blocking=True)
                 S['dev_counts'][:n].copy_(counts[:n], non_blocking=True)
@@ -224,6 +252,9 @@ class EnsemblePipeline:
                     S['pin_counts'][:n].copy_(S['dev_counts'][:n], non_blocking=True)
                     if radii is not None:
                         S['pin_radii'][:n].copy_(S['dev_radii'][:n], non_blocking=True)
+                    for key, t in zip(('c_sums', 'c_nverts', 'c_verts'), S.get('dev_contour', ())):
+                        S[key][:n].copy_(t[:n], non_blocking=True)
+                        t.record_stream(d2h)
                     S['ev_d2h'].record(d2h)
                 S['used'] = True
                 pending.append((k, n, radii is not None))

@@ -85,17 +85,18 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
     n = frames.shape[0]
     batch = min(batch_size, n)
     pipe = EnsemblePipeline(models, classes, output_size, dev, batch, src_hw=frames.shape[1:3],
-                            thickness=quantities is not None)
+                            thickness=quantities is not None, contour=quantities is not None)
     spans = [(lo, min(lo + batch, n)) for lo in range(0, n, batch)]
     # copies of batch i+1 / i-1 overlap the compute of batch i (EnsemblePipeline.stream_host)
-    for (lo, hi), (mask, label, counts, radii) in zip(spans, pipe.stream_host(frames[lo:hi] for lo, hi in spans)):
+    for (lo, hi), (mask, label, counts, radii, *contours) in zip(spans, pipe.stream_host(frames[lo:hi] for lo, hi in spans)):
         for i in range(lo, hi):
             for class_name in classes:
                 idx = CLASS_IDS[class_name] - 1
                 masks[i][:, :, idx] = mask[i - lo, :, :, idx]
         if quantities is not None:
             ratio = P.dicom_ratio(pipe.Ho)
-            quantities.extend(P.quantities_from_counts(counts, pipe.Ho, pipe.Wo, ratio, radii))
+            quantities.extend(P.quantities_from_counts(counts, pipe.Ho, pipe.Wo, ratio, radii,
+                                                       contours[0] if contours else None))
     return masks
 
 

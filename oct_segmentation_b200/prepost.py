@@ -238,10 +238,14 @@ def dicom_ratio(h: int) -> int:
     return int(h * 150 // 1000)
 
 
-def quantities_from_counts(counts: np.ndarray, H: int, W: int, ratio: int, radii: Optional[np.ndarray] = None) -> List[Dict]:
+def quantities_from_counts(counts: np.ndarray, H: int, W: int, ratio: int, radii: Optional[np.ndarray] = None,
+                           contours=None) -> List[Dict]:
     """Per-frame, per-class table from the device reductions (host side, cheap):
     present <=> 0 < nnz < H*W (== np.unique(ch).shape[0] == 2, analysis.py:189);
-    area = sqrt(nnz // ratio) (analysis.py:199-200); radial thickness median/min over rays that hit."""
+    area = sqrt(nnz // ratio) (analysis.py:199-200); radial thickness median/min over rays that hit;
+    with ``contours`` (host (sums, nverts, verts) of ``contour_largest``) also the reference table's
+    thickness_mean = contour median / ratio and thickness_min = contour min / ratio (analysis.py:202-207), under the
+    keys contour_thickness_mean / contour_thickness_min, for present classes."""
     rows = []
     for n in range(counts.shape[0]):
         row = {}
@@ -256,6 +260,10 @@ def quantities_from_counts(counts: np.ndarray, H: int, W: int, ratio: int, radii
                 q['thickness_median'] = float(np.median(r)) if r.size else 0
                 q['thickness_min'] = int(r.min()) if r.size else 0
                 q['thickness_max'] = int(r.max()) if r.size else 0
+            if contours is not None and q['present']:
+                t = thickness_from_contour(contours[0][n, c], int(contours[1][n, c]), contours[2][n, c])
+                q['contour_thickness_mean'] = t['median'] / ratio
+                q['contour_thickness_min'] = t['min'] / ratio
             row[name] = q
         rows.append(row)
     return rows

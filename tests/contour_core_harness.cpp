@@ -11,11 +11,11 @@ using namespace octseg;
 
 extern "C" int contour_largest_cpu(const uint8_t* mask, int H, int W, long long* sums4, int* nverts, int16_t* verts, int cap,
                                    int* n_outer) {
-  const int pitch = (W + 2 + 31) / 32;
-  std::vector<uint32_t> pl(static_cast<size_t>(H + 2) * pitch, 0u);
+  const int pitch = plane_pitch(W);
+  std::vector<uint32_t> pl(static_cast<size_t>(H + 2) * pitch + 1, 0u);
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x)
-      if (mask[static_cast<size_t>(y) * W + x]) pl[(y + 1) * pitch + ((x + 1) >> 5)] |= 1u << ((x + 1) & 31);
+      if (mask[static_cast<size_t>(y) * W + x]) pl[(y + 1) * pitch + ((x + 32) >> 5)] |= 1u << (x & 31);
   unsigned long long best = 0;
   bool have = false;
   *n_outer = 0;
@@ -25,7 +25,7 @@ extern "C" int contour_largest_cpu(const uint8_t* mask, int H, int W, long long*
       while (tips) {
         const int b = __builtin_ctz(tips);
         tips &= tips - 1;
-        const int x = 32 * k + b - 1;
+        const int x = 32 * k + b - 32;
         ContourSums s;
         if (!trace_border<false>(pl.data(), pitch, x, y, s, nullptr, 0, 4LL * H * W + 16)) continue;
         ++*n_outer;

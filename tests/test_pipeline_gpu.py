@@ -203,3 +203,35 @@ def test_streaming_main_equals_hold_everything_main(tmp_path, model_pairs):
         if name.endswith('.png'):
             assert np.array_equal(np.array(Image.open(outs['hold'] / name)), np.array(Image.open(outs['stream'] / name))), name
     assert json.load(open(outs['hold'] / 'quantities.json')) == json.load(open(outs['stream'] / 'quantities.json'))
+
+
+def test_pipeline_contour_quantities(model_pairs):
+    """contour=True: the 5th result carries the largest outer border per class; the table's contour thickness equals
+    calculate_thickness_contour (analysis.py:21-57, 202-207) on the mask the GPU produced; stream_host == run_host."""
+    _, ours = model_pairs
+    Ho = 250
+    frames = synth.synthetic_frames(350, 3, 250)
+    pipe = EnsemblePipeline(ours, CLASSES, [Ho, Ho], 'cuda:0', 2, src_hw=(250, 250), thickness=True, contour=True)
+    spans = [(0, 2), (2, 3)]
+    want = [pipe.run_host(frames[lo:hi]) for lo, hi in spans]
+    got = list(pipe.stream_host(frames[lo:hi] for lo, hi in spans))
+    ratio = P.dicom_ratio(Ho)
+    for g, w in zip(got, want):
+        assert len(g) == len(w) == 5
+        for a, b in zip(g[:4], w[:4]):
+            assert np.array_equal(a, b)
+        mask, _, counts, radii, contours = g
+        for a, b in zip(contours, w[4]):
+            assert a.shape == b.shape
+        rows = P.quantities_from_counts(counts, Ho, Ho, ratio, radii, contours)
+        rows_w = P.quantities_from_counts(w[2], Ho, Ho, ratio, w[3], w[4])
+        assert rows == rows_w
+        for n, row in enumerate(rows):
+            for c, name in enumerate(CLASSES):
+                ch = np.ascontiguousarray(mask[n, :, :, c])
+                if row[name]['present']:
+                    t = R.thickness_contour(ch)
+                    assert row[name]['contour_thickness_mean'] == t['median'] / ratio
+                    assert row[name]['contour_thickness_min'] == t['min'] / ratio
+                else:
+                    assert 'contour_thickness_mean' not in row[name]
