@@ -34,43 +34,42 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
   for (int i = tid; i < pitch; i += kContourThreads) pl[i] = 0u, pl[(H + 1) * pitch + i] = 0u;
   if (tid == 0) best = 0ull, pl[(H + 2) * pitch] = 0u;
   const uint32_t* mimg = mask + static_cast<size_t>(n) * H * W;
-  // pack: one item = 128 pixels of a row (4 plane words).  A lane loads 4 pixels (16 bytes) and keeps the 4 presence
-  // bits of class c; the nibbles of the 8 lanes of a word are OR-reduced with redux.sync over that lane group.
-  // Four items are loaded before any is reduced: the loop is bound by load latency, not by issue.
+  // pack: a warp takes whole rows; one step = 128 pixels (4 plane words): a lane loads 4 pixels (16 bytes) and keeps
+  // the 4 presence bits of class c, lane pairs join nibbles into bytes and two more xor-shuffles OR the 4 bytes of a
+  // word together.  Up to 4 steps of a row are loaded before any is combined: the loop is bound by load latency.
   const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
-  const int units = (pitch - 1 + 3) / 4, items = H * units;
-  const unsigned gm = 0xffu << (lane & 24);
-  for (int base = warp; base < items; base += 4 * kWarps) {
-    uint4 q[4];
+  const int units = (pitch - 1 + 3) / 4;
+  const uint32_t sel = 0xffu << (8 * c);
+  for (int y = warp; y < H; y += kWarps) {
+    const uint32_t* row = mimg + static_cast<size_t>(y) * W;
+    uint32_t* prow = pl + (y + 1) * pitch;
+    for (int u0 = 0; u0 < units; u0 += 4) {
+      uint4 q[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int it = base + j * kWarps;
-      q[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (it < items) {
-        const int y = it / units, x = 128 * (it - y * units) + 4 * lane;
-        if (x < W) {
-          const uint32_t* src = mimg + static_cast<size_t>(y) * W + x;
+      for (int j = 0; j < 4; ++j) {
+        const int x = 128 * (u0 + j) + 4 * lane;
+        q[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (u0 + j < units && x < W) {
           if (vec_ok) {
-            q[j] = __ldg(reinterpret_cast<const uint4*>(src));
+            q[j] = __ldg(reinterpret_cast<const uint4*>(row + x));
           } else {
-            q[j].x = __ldg(src);
-            if (x + 1 < W) q[j].y = __ldg(src + 1);
-            if (x + 2 < W) q[j].z = __ldg(src + 2);
-            if (x + 3 < W) q[j].w = __ldg(src + 3);
+            q[j].x = __ldg(row + x);
+            if (x + 1 < W) q[j].y = __ldg(row + x + 1);
+            if (x + 2 < W) q[j].z = __ldg(row + x + 2);
+            if (x + 3 < W) q[j].w = __ldg(row + x + 3);
           }
         }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int it = base + j * kWarps;
-      if (it >= items) break;  // warp-uniform
-      const int y = it / units, u = it - y * units;
-      const uint32_t nib = ((q[j].x >> (8 * c)) & 0xffu ? 1u : 0u) | ((q[j].y >> (8 * c)) & 0xffu ? 2u : 0u) |
-                           ((q[j].z >> (8 * c)) & 0xffu ? 4u : 0u) | ((q[j].w >> (8 * c)) & 0xffu ? 8u : 0u);
-      const uint32_t w = __reduce_or_sync(gm, nib << (4 * (lane & 7)));
-      const int k = 1 + 4 * u + (lane >> 3);
-      if ((lane & 7) == 0 && k < pitch) pl[(y + 1) * pitch + k] = w;
+      for (int j = 0; j < 4; ++j) {
+        if (u0 + j >= units) break;  // warp-uniform
+        const uint32_t nib = ((q[j].x & sel) ? 1u : 0u) | ((q[j].y & sel) ? 2u : 0u) | ((q[j].z & sel) ? 4u : 0u) | ((q[j].w & sel) ? 8u : 0u);
+        uint32_t v = (nib | (__shfl_xor_sync(0xffffffffu, nib, 1) << 4)) << (4 * (lane & 6));  // even lane 2b: byte b
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        const int k = 1 + 4 * (u0 + j) + (lane >> 3);
+        if ((lane & 7) == 0 && k < pitch) prow[k] = v;
+      }
     }
   }
   for (int y = tid; y < H; y += kContourThreads) pl[(y + 1) * pitch] = 0u;

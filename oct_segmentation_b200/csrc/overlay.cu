@@ -15,7 +15,7 @@
 //   S2  E  = erode5(D);  Cd = E inside / 0 outside, Ce = E inside / 1 outside, Cr = Cd + reflected columns
 //   S3  RIM = dilate7(Cd) & ~erode7(Ce);  ANY / ALL = OR / AND of the 5x5 (reflected) window of Cr
 //   S4  one warp = 32 pixels of a row: classes whose RIM|ANY word is 0 are skipped warp-uniformly, pixels with a
-//       uniform window take k = 256, only object-boundary pixels compute the binomial sum (5 windows, popcounts).
+//       (one ACT word per 32 pixels says which classes are near) -- uniform window take k = 256, only object-boundary pixels compute the binomial sum (5 windows, popcounts).
 // overlay_bytes_kernel is the first, byte-lane version (4 classes = 4 bytes of a word, 32 x 8 tiles), kept as an
 // A/B reference (OCTSEG_OVERLAY_IMPL=bytes).
 #include <cuda_runtime.h>
@@ -202,23 +202,24 @@ __global__ void __launch_bounds__(256) overlay_kernel(const OverlayParams p) {
   uint32_t* RIM = Cr + 4 * PL;
   uint32_t* ANY = RIM + 4 * TP;
   uint32_t* ALL = ANY + 4 * TP;
-  uint8_t* lut = reinterpret_cast<uint8_t*>(ALL + 4 * TP);
+  uint32_t* ACT = ALL + 4 * TP;  // per tile word: bit c = class c has rim or fill pixels among these 32
+  uint8_t* lut = reinterpret_cast<uint8_t*>(ACT + TP);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.z, H = p.H, W = p.W;
   const int x0 = blockIdx.x * (32 * kTileWords), y0 = blockIdx.y * TY;
   const int xr0 = x0 - 32, yr0 = y0 - 7;
   const uint32_t* mimg = p.mask + static_cast<size_t>(n) * H * W;
   for (int i = tid; i < 257; i += 256) lut[i] = p.fill_lut[i];
+  for (int i = tid; i < TP; i += 256) ACT[i] = 0u;
 
-  // S0: pack.  A lane loads 4 pixels (16 bytes); byte c of `t` = the 4 presence bits of class c; the nibbles of
-  // the 8 lanes of a word are OR-reduced with redux.sync over that lane group.
+  // S0: pack.  A lane loads 4 pixels (16 bytes); the 8 lanes of a plane word exchange their bits with three shuffles.
   const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0;
   for (int it = warp; it < RH * 2; it += 8) {
-    const int r = it >> 1, u = it & 1;
-    if (u == 1 && lane >= 16) continue;  // second unit of a row = words 4, 5 only (whole lane groups drop out)
-    const int y = yr0 + r, x = xr0 + 128 * u + 4 * lane;
+    const int r = it >> 1, u_idx = it & 1;
+    const int y = yr0 + r, x = xr0 + 128 * u_idx + 4 * lane;
+    const bool live = !(u_idx == 1 && lane >= 16);  // second unit of a row = words 4, 5 only
     uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (y >= 0 && y < H && x >= 0 && x < W) {
+    if (live && y >= 0 && y < H && x >= 0 && x < W) {
       const uint32_t* src = mimg + static_cast<size_t>(y) * W + x;
       if (vec_ok) {
         q = __ldg(reinterpret_cast<const uint4*>(src));
@@ -230,15 +231,15 @@ __global__ void __launch_bounds__(256) overlay_kernel(const OverlayParams p) {
       }
     }
     const uint32_t t = __vminu4(q.x, kOnes) + 2u * __vminu4(q.y, kOnes) + 4u * __vminu4(q.z, kOnes) + 8u * __vminu4(q.w, kOnes);
-    const int sh = 4 * (lane & 7);
-    const unsigned gm = 0xffu << (lane & 24);
-    uint32_t mine = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t v = __reduce_or_sync(gm, ((t >> (8 * c)) & 0xfu) << sh);
-      if ((lane & 7) == c) mine = v;
-    }
-    if ((lane & 7) < 4) M[(lane & 7) * PL + r * kRW + 4 * u + (lane >> 3)] = mine;
+    // byte c of t = the 4 presence bits of class c for this lane's 4 pixels.  Pair lanes (nibbles -> bytes: 8 pixels),
+    // then transpose the 4 x 4 byte matrix held by the even lanes of each 8-lane group (rows = byte position in the
+    // word, columns = classes) with two shuffle + byte-permute rounds: even lane 2k ends up with class k's word.
+    uint32_t u = t | (__shfl_xor_sync(0xffffffffu, t, 1) << 4);
+    uint32_t v = __shfl_xor_sync(0xffffffffu, u, 2);
+    u = __byte_perm(u, v, (lane & 2) ? 0x3715u : 0x6240u);
+    v = __shfl_xor_sync(0xffffffffu, u, 4);
+    u = __byte_perm(u, v, (lane & 4) ? 0x3276u : 0x5410u);
+    if (live && !(lane & 1)) M[((lane & 7) >> 1) * PL + r * kRW + 4 * u_idx + (lane >> 3)] = u;
   }
   __syncthreads();
 
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(256) overlay_kernel(const OverlayParams p) {
       RIM[c * TP + r * kTileWords + j] = rim;
       ANY[c * TP + r * kTileWords + j] = any;
       ALL[c * TP + r * kTileWords + j] = all;
+      if (rim | any) atomicOr(&ACT[r * kTileWords + j], 1u << c);
     }
   }
   __syncthreads();
@@ -354,11 +356,14 @@ __global__ void __launch_bounds__(256) overlay_kernel(const OverlayParams p) {
       rgb[1] = p.img[pix * 3 + 1];
       rgb[2] = p.img[pix * 3 + 2];
     }
-    for (int i = 0; i < p.n_order; ++i) {
+    const uint32_t act_classes = a_none == 0 ? ACT[it] : 0xfu;  // warp-uniform
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i >= p.n_order) break;
       const int c = p.order[i];
-      const int o = c * TP + r * kTileWords + j;
+      if (!((act_classes >> c) & 1u)) continue;  // nothing of this class near these 32 pixels
+      const int o = c * TP + it;
       const uint32_t rimw = RIM[o], anyw = ANY[o];
-      if ((rimw | anyw) == 0u && a_none == 0) continue;  // warp-uniform: nothing of this class near these 32 pixels
       const int a2 = ((rimw >> lane) & 1u) ? p.rim_alpha : 0;
       int a1 = a_none;
       if ((anyw >> lane) & 1u) {
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(256) overlay_kernel(const OverlayParams p) {
 
 template <int TY>
 static int launch_overlay(const OverlayParams& p, cudaStream_t stream) {
-  constexpr size_t smem = (static_cast<size_t>(5 * 4 * (TY + 14) * kRW + 3 * 4 * TY * kTileWords)) * 4 + 272;
+  constexpr size_t smem = (static_cast<size_t>(5 * 4 * (TY + 14) * kRW + 13 * TY * kTileWords)) * 4 + 272;
   static unsigned long long configured = 0;  // bit d = done on device d (the attribute is per device)
   int dev = 0;
   OCTSEG_CUDA(cudaGetDevice(&dev));
