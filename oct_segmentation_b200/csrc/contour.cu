@@ -28,11 +28,13 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
                                                                           int16_t* __restrict__ verts, int cap) {
   extern __shared__ uint32_t pl[];  // (H + 2) x pitch
   __shared__ unsigned long long best;
+  __shared__ int owner;              // start index of the walk that wrote its points during pass 1 (-1: none)
+  __shared__ ContourSums owner_sums;
   const int c = blockIdx.x, n = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kContourThreads / 32;
   for (int i = tid; i < pitch; i += kContourThreads) pl[i] = 0u, pl[(H + 1) * pitch + i] = 0u;
-  if (tid == 0) best = 0ull, pl[(H + 2) * pitch] = 0u;
+  if (tid == 0) best = 0ull, owner = -1, pl[(H + 2) * pitch] = 0u;
   const uint32_t* mimg = mask + static_cast<size_t>(n) * H * W;
   // pack: a warp takes whole rows; one step = 128 pixels (4 plane words): a lane loads 4 pixels (16 bytes) and keeps
   // the 4 presence bits of class c, lane pairs join nibbles into bytes and two more xor-shuffles OR the 4 bytes of a
@@ -76,6 +78,9 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
   __syncthreads();
 
   const long long max_steps = 4ll * H * W + 16;
+  constexpr long long kShortWalk = 48;
+  const size_t o = static_cast<size_t>(n) * 4 + c;
+  int16_t* out_verts = verts + o * cap * 2;
   unsigned long long mine = 0ull;
   for (int i = tid; i < H * pitch; i += kContourThreads) {
     const int y = i / pitch, k = i - y * pitch;
@@ -85,7 +90,18 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
       tips &= tips - 1;
       const int x = 32 * k + b - 32;
       ContourSums s;
-      if (!trace_border<false>(pl, pitch, x, y, s, nullptr, 0, max_steps)) continue;
+      WalkResult res = trace_border<false>(pl, pitch, x, y, s, nullptr, 0, kShortWalk);
+      if (res == kWalkBudget) {
+        // a long border: the first such walk of the block writes its points straight into the output (in an
+        // OCT mask it is the one large object, so the winner rarely has to be walked a second time)
+        if (atomicCAS(&owner, -1, y * W + x) == -1) {
+          res = trace_border<true>(pl, pitch, x, y, s, out_verts, cap, max_steps);
+          owner_sums = s;
+        } else {
+          res = trace_border<false>(pl, pitch, x, y, s, nullptr, 0, max_steps);
+        }
+      }
+      if (res != kWalkDone) continue;
       const unsigned long long area = static_cast<unsigned long long>(s.a00 < 0 ? -s.a00 : s.a00);
       if (area > 0) mine = max(mine, (area << 32) | static_cast<unsigned>(y * W + x));
     }
@@ -95,14 +111,16 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
   if (lane == 0 && mine) atomicMax(&best, mine);
   __syncthreads();
   if (tid == 0) {
-    const size_t o = static_cast<size_t>(n) * 4 + c;
     ContourSums s;
     s.a00 = s.a10 = s.a01 = 0;
     s.nverts = 0;
     long long start = -1;
     if (best) {
       start = static_cast<long long>(best & 0xffffffffull);
-      trace_border<true>(pl, pitch, static_cast<int>(start % W), static_cast<int>(start / W), s, verts + o * cap * 2, cap, max_steps);
+      if (start == owner)
+        s = owner_sums;
+      else
+        trace_border<true>(pl, pitch, static_cast<int>(start % W), static_cast<int>(start / W), s, out_verts, cap, max_steps);
     }
     sums[o * 4] = s.a00;
     sums[o * 4 + 1] = s.a10;

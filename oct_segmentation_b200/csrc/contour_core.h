@@ -65,11 +65,13 @@ OCTSEG_HD void code_delta(int s, int& dx, int& dy) {
   dy = static_cast<int>((0xA901u >> (2 * s)) & 3u) - 1;
 }
 
-// Walks the border that starts at (x0, y0) (a pixel whose West neighbour is empty).  Returns false when the walk
-// meets a pixel that precedes the start in raster order (not an outer border's first pixel) or exceeds max_steps.
+// Walks the border that starts at (x0, y0) (a pixel whose West neighbour is empty).  Returns kWalkDone for a
+// completed outer border, kWalkNotFirst when the walk meets a pixel that precedes the start in raster order (the
+// start is not an outer border's first pixel), kWalkBudget when max_steps ran out first.
 // EMIT: also write the kept points (x, y as int16 pairs, at most cap of them; sums.nverts counts all) and a10/a01.
+enum WalkResult { kWalkNotFirst = 0, kWalkDone = 1, kWalkBudget = 2 };
 template <bool EMIT>
-OCTSEG_HD bool trace_border(const uint32_t* pl, int pitch, int x0, int y0, ContourSums& sums, int16_t* verts, int cap,
+OCTSEG_HD WalkResult trace_border(const uint32_t* pl, int pitch, int x0, int y0, ContourSums& sums, int16_t* verts, int cap,
                             long long max_steps) {
   sums.a00 = sums.a10 = sums.a01 = 0;
   sums.nverts = 0;
@@ -81,7 +83,7 @@ OCTSEG_HD bool trace_border(const uint32_t* pl, int pitch, int x0, int y0, Conto
   if (s == 4) {  // single-pixel component
     sums.nverts = 1;
     if (EMIT && cap > 0) verts[0] = static_cast<int16_t>(x0), verts[1] = static_cast<int16_t>(y0);
-    return true;
+    return kWalkDone;
   }
   const int x1 = x0 + dx, y1 = y0 + dy;
   int x3 = x0, y3 = y0, prev_s = s ^ 4;
@@ -107,17 +109,17 @@ OCTSEG_HD bool trace_border(const uint32_t* pl, int pitch, int x0, int y0, Conto
       px = x3, py = y3;
       prev_s = s;
     }
-    if (y4 < y0 || (y4 == y0 && x4 < x0)) return false;
+    if (y4 < y0 || (y4 == y0 && x4 < x0)) return kWalkNotFirst;
     if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) {
       const long long dxy = static_cast<long long>(px) * fy - static_cast<long long>(fx) * py;  // closing edge last -> first
       sums.a00 += dxy;
       if (EMIT) sums.a10 += dxy * (px + fx), sums.a01 += dxy * (py + fy);
-      return true;
+      return kWalkDone;
     }
     x3 = x4, y3 = y4;
     s = (s + 4) & 7;
   }
-  return false;
+  return kWalkBudget;
 }
 
 // candidate start bits of one plane word: pixel set, West empty, the three pixels above empty

@@ -27,7 +27,7 @@ extern "C" int contour_largest_cpu(const uint8_t* mask, int H, int W, long long*
         tips &= tips - 1;
         const int x = 32 * k + b - 32;
         ContourSums s;
-        if (!trace_border<false>(pl.data(), pitch, x, y, s, nullptr, 0, 4LL * H * W + 16)) continue;
+        if (trace_border<false>(pl.data(), pitch, x, y, s, nullptr, 0, 4LL * H * W + 16) != kWalkDone) continue;
         ++*n_outer;
         const unsigned long long area = static_cast<unsigned long long>(s.a00 < 0 ? -s.a00 : s.a00);
         const unsigned long long key = (area << 32) | static_cast<unsigned>(y * W + x);
