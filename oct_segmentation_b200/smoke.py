@@ -42,6 +42,15 @@ def run_smoke() -> None:
     want_mask = plane.cpu().numpy()[:, idx][:, :, idx]
     assert np.array_equal(mask[..., 3].cpu().numpy(), want_mask), 'postprocess kernel differs from the oracle'
     assert np.array_equal(counts[:, 3].cpu().numpy(), want_mask.reshape(2, -1).sum(1))
+    # overlay + contour kernels vs the numpy / cv2 oracle on that mask (bit-exact)
+    over = P.overlay(torch.from_numpy(frames).to(dev), mask, [3])
+    m_host = mask.cpu().numpy()
+    for n in range(2):
+        assert np.array_equal(over[n].cpu().numpy(), R.overlay(frames[n], m_host[n], ['Vasa vasorum'])), 'overlay kernel differs'
+    sums, nverts, verts = (t.cpu().numpy() for t in P.contour_largest(mask))
+    for n in range(2):
+        got_t = P.thickness_from_contour(sums[n, 3], int(nverts[n, 3]), verts[n, 3])
+        assert got_t == R.thickness_contour(np.ascontiguousarray(m_host[n, :, :, 3])), 'contour kernel differs from cv2'
     torch.cuda.synchronize()
-    print(f'smoke ok: {key} logits rel-L2 vs fp32 oracle {err:.3e}; pre/post kernels bit-exact; '
+    print(f'smoke ok: {key} logits rel-L2 vs fp32 oracle {err:.3e}; pre/post/overlay/contour kernels bit-exact; '
           f'{ours.model.compiled(2, S, S, dev, "f32", "f32_nchw").launches} launches')
