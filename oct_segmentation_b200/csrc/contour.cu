@@ -38,17 +38,17 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
   const uint32_t* mimg = mask + static_cast<size_t>(n) * H * W;
   // pack: a warp takes whole rows; one step = 128 pixels (4 plane words): a lane loads 4 pixels (16 bytes) and keeps
   // the 4 presence bits of class c, lane pairs join nibbles into bytes and two more xor-shuffles OR the 4 bytes of a
-  // word together.  Up to 4 steps of a row are loaded before any is combined: the loop is bound by load latency.
+  // word together.  Up to 8 steps of a row (1024 pixels) are loaded before any is combined: the loop is bound by load latency.
   const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
   const int units = (pitch - 1 + 3) / 4;
   const uint32_t sel = 0xffu << (8 * c);
   for (int y = warp; y < H; y += kWarps) {
     const uint32_t* row = mimg + static_cast<size_t>(y) * W;
     uint32_t* prow = pl + (y + 1) * pitch;
-    for (int u0 = 0; u0 < units; u0 += 4) {
-      uint4 q[4];
+    for (int u0 = 0; u0 < units; u0 += 8) {
+      uint4 q[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const int x = 128 * (u0 + j) + 4 * lane;
         q[j] = make_uint4(0u, 0u, 0u, 0u);
         if (u0 + j < units && x < W) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         if (u0 + j >= units) break;  // warp-uniform
         const uint32_t nib = ((q[j].x & sel) ? 1u : 0u) | ((q[j].y & sel) ? 2u : 0u) | ((q[j].z & sel) ? 4u : 0u) | ((q[j].w & sel) ? 8u : 0u);
         uint32_t v = (nib | (__shfl_xor_sync(0xffffffffu, nib, 1) << 4)) << (4 * (lane & 6));  // even lane 2b: byte b
@@ -84,10 +84,12 @@ __global__ void __launch_bounds__(kContourThreads) contour_largest_kernel(const 
   unsigned long long mine = 0ull;
   for (int i = tid; i < H * pitch; i += kContourThreads) {
     const int y = i / pitch, k = i - y * pitch;
-    uint32_t tips = tip_bits(pl, pitch, y + 1, k);
+    uint32_t cur, touch;
+    uint32_t tips = tip_bits(pl, pitch, y + 1, k, cur, touch);
     while (tips) {
       const int b = __ffs(tips) - 1;
       tips &= tips - 1;
+      if (tip_run_touches(cur, touch, b)) continue;
       const int x = 32 * k + b - 32;
       ContourSums s;
       WalkResult res = trace_border<false>(pl, pitch, x, y, s, nullptr, 0, kShortWalk);

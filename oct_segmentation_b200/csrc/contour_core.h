@@ -122,13 +122,25 @@ OCTSEG_HD WalkResult trace_border(const uint32_t* pl, int pitch, int x0, int y0,
   return kWalkBudget;
 }
 
-// candidate start bits of one plane word: pixel set, West empty, the three pixels above empty
-OCTSEG_HD uint32_t tip_bits(const uint32_t* pl, int pitch, int row /* plane row = y + 1 */, int k) {
+// candidate start bits of one plane word: pixel set, West empty, the three pixels above empty.  `cur` and `touch`
+// (bit x = some pixel of the row above in columns x-1..x+1 is set) feed tip_run_touches.
+OCTSEG_HD uint32_t tip_bits(const uint32_t* pl, int pitch, int row /* plane row = y + 1 */, int k, uint32_t& cur, uint32_t& touch) {
   const uint32_t* r = pl + row * pitch + k;
   const uint32_t* u = r - pitch;
-  const uint32_t cur = r[0], west = (cur << 1) | (k > 0 ? r[-1] >> 31 : 0u);
+  cur = r[0];
+  const uint32_t west = (cur << 1) | (k > 0 ? r[-1] >> 31 : 0u);
   const uint32_t up = u[0], upw = (up << 1) | (k > 0 ? u[-1] >> 31 : 0u), upe = (up >> 1) | (k < pitch - 1 ? u[1] << 31 : 0u);
-  return cur & ~west & ~up & ~upw & ~upe;
+  touch = up | upw | upe;
+  return cur & ~west & ~touch;
+}
+
+// The horizontal run of set pixels that starts at tip bit b (as far as it lies in this word) touches the row above:
+// the tip is 8-connected to a raster-earlier pixel, so it is not its component's first pixel and needs no walk.
+// (Sound filter, not a complete one: tips joined to earlier pixels only through lower rows still walk and stop at
+// the first earlier pixel they meet.)  On a disc it removes every tip of the upper-left arc but the top one.
+OCTSEG_HD bool tip_run_touches(uint32_t cur, uint32_t touch, int b) {
+  const uint32_t run = ((cur + (1u << b)) ^ cur) & cur;
+  return (run & touch) != 0u;
 }
 
 }  // namespace octseg

@@ -21,10 +21,12 @@ extern "C" int contour_largest_cpu(const uint8_t* mask, int H, int W, long long*
   *n_outer = 0;
   for (int y = 0; y < H; ++y)
     for (int k = 0; k < pitch; ++k) {
-      uint32_t tips = tip_bits(pl.data(), pitch, y + 1, k);
+      uint32_t cur, touch;
+      uint32_t tips = tip_bits(pl.data(), pitch, y + 1, k, cur, touch);
       while (tips) {
         const int b = __builtin_ctz(tips);
         tips &= tips - 1;
+        if (tip_run_touches(cur, touch, b)) continue;
         const int x = 32 * k + b - 32;
         ContourSums s;
         if (trace_border<false>(pl.data(), pitch, x, y, s, nullptr, 0, 4LL * H * W + 16) != kWalkDone) continue;
