@@ -243,6 +243,11 @@ def main(cfg) -> None:
     if table is not None:
         with open(os.path.join(save_dir, 'quantities.json'), 'w') as f:
             json.dump(table, f, indent=1)
+        # the per-class object table of get_analysis (src/app/tools/analysis.py:185-213): slices, object ids, areas, thickness
+        names = list(table)
+        with open(os.path.join(save_dir, 'objects.json'), 'w') as f:
+            json.dump({'ratio': P.dicom_ratio(int(cfg.output_size[1])), 'images': names,
+                       'objects': P.objects_table([table[k] for k in names], names)}, f, indent=1)
     log.info(f'Overall computation time: {time.time() - start:.1f} s')
     log.info('Complete')
 

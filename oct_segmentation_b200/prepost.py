@@ -267,3 +267,33 @@ def quantities_from_counts(counts: np.ndarray, H: int, W: int, ratio: int, radii
             row[name] = q
         rows.append(row)
     return rows
+
+
+def objects_table(rows: Sequence[Dict], image_names: Optional[Sequence[str]] = None) -> Dict[str, Dict[str, list]]:
+    """The `objects` dict of get_analysis (src/app/tools/analysis.py:139-154, loop :185-213) from the per-frame rows
+    of ``quantities_from_counts`` (frames in slice order, all ranks gathered): per class the slices where it is
+    present, their object ids (consecutive slices share an id, a gap starts the next: :191-198), area (:199-200)
+    and, when the rows carry contour thickness, thickness_mean / thickness_min (:202-207).  Host side by design:
+    a sequential scan over N x 4 booleans after the gather."""
+    objects = {name: {'object_id': [], 'slice': [], 'area': [], 'thickness_mean': [], 'thickness_min': [], 'img_name': []}
+               for name in CLASS_NAMES}
+    for idx, row in enumerate(rows):
+        for name in CLASS_NAMES:
+            q = row[name]
+            if not q['present']:
+                continue
+            obj = objects[name]
+            if len(obj['object_id']) == 0:
+                obj['object_id'].append(0)
+            elif idx == obj['slice'][-1] + 1:
+                obj['object_id'].append(obj['object_id'][-1])
+            else:
+                obj['object_id'].append(obj['object_id'][-1] + 1)
+            obj['slice'].append(idx)
+            obj['area'].append(q['area'])
+            if 'contour_thickness_mean' in q:
+                obj['thickness_mean'].append(q['contour_thickness_mean'])
+                obj['thickness_min'].append(q['contour_thickness_min'])
+            if image_names is not None:
+                obj['img_name'].append(image_names[idx])
+    return objects

@@ -154,3 +154,40 @@ def test_stem_space_to_depth_weights_equal_the_stride2_conv(k, pad, H, W):
     got = F.conv2d(xp, w2)
     assert got.shape == want.shape
     assert torch.allclose(got, want, atol=1e-4, rtol=1e-4)
+
+
+def test_objects_table_follows_get_analysis():
+    """prepost.objects_table vs the oracle's restatement of analysis.py:185-207 (object ids of consecutive slices,
+    area, contour thickness) on the reference's demo masks, with rows built the way the product builds them."""
+    import os
+    from oct_segmentation_b200 import prepost as P
+    from oracle import prepost_ref as R
+    from tests.test_oracle_prepost import G, unpack
+    d = np.load(os.path.join(G, 'masks_app_demo.npz'))
+    masks = [unpack(p, d['shape']) for p in d['packed']]
+    masks = masks[:3] + [np.zeros_like(masks[0])] + masks[3:6]          # a gap starts new objects
+    H, W = masks[0].shape[:2]
+    ratio = P.dicom_ratio(H)
+    rows = []
+    for m in masks:
+        row = {}
+        for c, name in enumerate(P.CLASS_NAMES):
+            ch = np.ascontiguousarray(m[:, :, c])
+            nnz = int(np.count_nonzero(ch))
+            q = {'nnz': nnz, 'present': 0 < nnz < H * W}
+            if q['present']:
+                t = R.thickness_contour(ch)
+                q.update(area=pow(nnz // ratio, 0.5), contour_thickness_mean=t['median'] / ratio, contour_thickness_min=t['min'] / ratio)
+            row[name] = q
+        rows.append(row)
+    got = P.objects_table(rows, [f's{i}' for i in range(len(masks))])
+    for c, name in enumerate(P.CLASS_NAMES):
+        present = [R.class_present(np.ascontiguousarray(m[:, :, c])) for m in masks]
+        assert got[name]['slice'] == [i for i, p in enumerate(present) if p]
+        assert got[name]['object_id'] == R.object_ids(present)
+        want = [R.frame_quantities(m, ratio)[name] for m, p in zip(masks, present) if p]
+        assert got[name]['area'] == [w['area'] for w in want]
+        assert got[name]['thickness_mean'] == [w['thickness_mean'] for w in want]
+        assert got[name]['thickness_min'] == [w['thickness_min'] for w in want]
+        assert got[name]['img_name'] == [f's{i}' for i, p in enumerate(present) if p]
+    assert any(len(set(got[n]['object_id'])) > 1 for n in P.CLASS_NAMES)

@@ -198,11 +198,14 @@ def test_streaming_main_equals_hold_everything_main(tmp_path, model_pairs):
         pred.main(cfg)
         outs[mode] = save_dir
     assert sorted(os.listdir(outs['hold'])) == sorted(os.listdir(outs['stream']))
-    assert len(os.listdir(outs['hold'])) == 11
+    assert len(os.listdir(outs['hold'])) == 12          # 5 x (mask, overlay) + quantities.json + objects.json
     for name in os.listdir(outs['hold']):
         if name.endswith('.png'):
             assert np.array_equal(np.array(Image.open(outs['hold'] / name)), np.array(Image.open(outs['stream'] / name))), name
-    assert json.load(open(outs['hold'] / 'quantities.json')) == json.load(open(outs['stream'] / 'quantities.json'))
+    for name in ('quantities.json', 'objects.json'):
+        assert json.load(open(outs['hold'] / name)) == json.load(open(outs['stream'] / name))
+    obj = json.load(open(outs['hold'] / 'objects.json'))
+    assert obj['images'] == [f'frame_{i}' for i in range(5)] and set(obj['objects']) == set(CLASSES)
 
 
 def test_pipeline_contour_quantities(model_pairs):
