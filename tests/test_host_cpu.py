@@ -191,3 +191,45 @@ def test_objects_table_follows_get_analysis():
         assert got[name]['thickness_min'] == [w['thickness_min'] for w in want]
         assert got[name]['img_name'] == [f's{i}' for i, p in enumerate(present) if p]
     assert any(len(set(got[n]['object_id'])) > 1 for n in P.CLASS_NAMES)
+
+
+def _objects_worker(rank, world, counts_all, port, q):
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oct_segmentation_b200 import prepost as P
+    n_total = counts_all.shape[0]
+    lo, hi = parallel.shard_range(n_total, rank, world)
+    table = parallel.gather_table(torch.from_numpy(counts_all[lo:hi].copy()), n_total)     # each rank: its own frames
+    if rank == 0:
+        rows = P.quantities_from_counts(table.numpy(), 100, 100, P.dicom_ratio(100))
+        q.put(P.objects_table(rows))
+    dist.destroy_process_group()
+
+
+def test_object_ids_continue_across_the_shard_boundary_world_size_2_gloo():
+    """Frame-sharded ranks gather their per-frame counts; object-id run tracking (analysis.py:191-198) runs on the
+    gathered table, so a plaque spanning the shard boundary keeps one id -- identical to the single-rank table."""
+    from oct_segmentation_b200 import prepost as P
+    from oracle import prepost_ref as R
+    n_total = 9
+    counts = np.zeros((n_total, 4), np.int32)
+    counts[2:7, 0] = 500                       # frames 2..6: crosses the boundary between rank 0 ([0, 5)) and rank 1
+    counts[[0, 1, 5, 8], 2] = 40               # three runs
+    counts[:, 3] = 100 * 100                   # full plane: not "present" (analysis.py:189)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 77
+    procs = [ctx.Process(target=_objects_worker, args=(r, 2, counts, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got['Lumen']['slice'] == [2, 3, 4, 5, 6] and got['Lumen']['object_id'] == [0] * 5
+    assert got['Lipid core']['slice'] == [0, 1, 5, 8] and got['Lipid core']['object_id'] == [0, 0, 1, 2]
+    assert got['Vasa vasorum']['slice'] == [] and got['Fibrous cap']['slice'] == []
+    for c, name in enumerate(P.CLASS_NAMES):
+        present = [0 < int(v) < 100 * 100 for v in counts[:, c]]
+        assert got[name]['object_id'] == R.object_ids(present)
+    assert got == P.objects_table(P.quantities_from_counts(counts, 100, 100, P.dicom_ratio(100)))
