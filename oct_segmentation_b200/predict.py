@@ -85,7 +85,8 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
     n = frames.shape[0]
     batch = min(batch_size, n)
     pipe = EnsemblePipeline(models, classes, output_size, dev, batch, src_hw=frames.shape[1:3],
-                            thickness=quantities is not None, contour=quantities is not None)
+                            thickness=quantities is not None,
+                            contour=quantities is not None and P.contour_fits(int(output_size[1]), int(output_size[0])))
     spans = [(lo, min(lo + batch, n)) for lo in range(0, n, batch)]
     # copies of batch i+1 / i-1 overlap the compute of batch i (EnsemblePipeline.stream_host)
     for (lo, hi), (mask, label, counts, radii, *contours) in zip(spans, pipe.stream_host(frames[lo:hi] for lo, hi in spans)):

@@ -199,6 +199,13 @@ def fold_average_threshold(logits: Sequence[torch.Tensor], out: Optional[torch.T
 CONTOUR_CAP = 16384   # kept border points per (frame, class) the device buffer holds
 
 
+def contour_fits(H: int, W: int) -> bool:
+    """octseg_contour_largest keeps one class's bit plane in shared memory (include/octseg.h): 1000 x 1000 needs
+    132 KB, the limit of 226 KB is reached near 1330 x 1330."""
+    pitch = (W + 1 + 31) // 32 + 1
+    return ((H + 2) * pitch + 1) * 4 <= 226 * 1024
+
+
 def contour_largest(mask: torch.Tensor, cap: int = CONTOUR_CAP):
     """mask: uint8 CUDA (N, H, W, 4), non-zero = object.  Per (frame, class) the largest outer border in
     cv2's CHAIN_APPROX_SIMPLE form (== max(findContours(RETR_EXTERNAL), key=contourArea), analysis.py:25-35):

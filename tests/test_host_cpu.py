@@ -233,3 +233,12 @@ def test_object_ids_continue_across_the_shard_boundary_world_size_2_gloo():
         present = [0 < int(v) < 100 * 100 for v in counts[:, c]]
         assert got[name]['object_id'] == R.object_ids(present)
     assert got == P.objects_table(P.quantities_from_counts(counts, 100, 100, P.dicom_ratio(100)))
+
+
+def test_contour_fits_matches_the_c_abi_limit():
+    from oct_segmentation_b200 import prepost as P
+    assert P.contour_fits(1000, 1000) and P.contour_fits(1024, 1024) and not P.contour_fits(2048, 2048)
+    lib = _lib.load()
+    one = ctypes.c_void_p(16)         # never dereferenced: the size check comes first and no kernel is launched
+    rc = lib.octseg_contour_largest(one, 1, 2048, 2048, one, one, one, 8, None)
+    assert rc != 0 and b'shared memory' in lib.octseg_last_error()
