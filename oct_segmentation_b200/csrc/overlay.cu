@@ -10,12 +10,14 @@
 // overlay_kernel (the product path): the morphology runs on BIT PLANES -- one 32-bit word = 32 pixels of one
 // row of one class -- so a dilation / erosion row is a handful of funnel shifts and ORs / ANDs for 32 pixels.
 // One block = 128 x TY output pixels (TY = 32); region = tile + 7 halo rows and one halo word (32 px) per side:
-//   S0  mask words (4 class bytes per pixel, 16-byte loads) -> bit planes M   (nibbles OR-reduced over 8 lanes)
+//   S0  mask words (4 class bytes per pixel, 16-byte loads) -> bit planes M: the 8 lanes of a plane word exchange
+//       their bits with three shuffles + two byte permutes (a 4 x 4 byte transpose yields all four classes at once)
 //   S1  D  = dilate5(M), image exterior forced to 1 (erode's border value)
 //   S2  E  = erode5(D);  Cd = E inside / 0 outside, Ce = E inside / 1 outside, Cr = Cd + reflected columns
-//   S3  RIM = dilate7(Cd) & ~erode7(Ce);  ANY / ALL = OR / AND of the 5x5 (reflected) window of Cr
-//   S4  one warp = 32 pixels of a row: classes whose RIM|ANY word is 0 are skipped warp-uniformly, pixels with a
-//       (one ACT word per 32 pixels says which classes are near) -- uniform window take k = 256, only object-boundary pixels compute the binomial sum (5 windows, popcounts).
+//   S3  RIM = dilate7(Cd) & ~erode7(Ce);  ANY / ALL = OR / AND of the 5x5 (reflected) window of Cr;
+//       ACT = per 32-pixel word, the classes with any RIM | ANY bit
+//   S4  one warp = 32 pixels of a row: classes absent from the ACT word are skipped warp-uniformly, pixels with a
+//       uniform window take k = 256, only object-boundary pixels compute the binomial sum (5 windows, popcounts).
 // overlay_bytes_kernel is the first, byte-lane version (4 classes = 4 bytes of a word, 32 x 8 tiles), kept as an
 // A/B reference (OCTSEG_OVERLAY_IMPL=bytes).
 #include <cuda_runtime.h>
