@@ -13,10 +13,17 @@ algorithms with state-dict-key compatible module trees (App
   * timm-regnetx_064 encoder       = timm 0.9.2 RegNet (Bottleneck, group width 56, no SE)
   * efficientnet-b7 encoder        = efficientnet_pytorch 0.7.1 EfficientNet with *static* same padding
 
-PARITY UNPINNED for logits: the reference ships no golden tensors, tests or weights for this
-path.  What pins this file instead: parameter counts that reproduce the DVC
-checkpoint sizes and the widely quoted smp totals (tests/test_oracle_models.py), MAC counts
-(App. D) and output shapes.
+PARITY UNPINNED against the reference's own logits: it ships no golden tensors, tests or weights
+for this path.  What pins this file instead:
+  * numerically, against an independent implementation (tests/test_oracle_vs_torchvision.py):
+    the RegNetX-6.4GF encoder equals torchvision's RegNet under a key-rename map, the
+    EfficientNet-B7 encoder equals torchvision's efficientnet_b7 on every block (stride-2 layers
+    through a pad-and-crop shim that turns torchvision's symmetric padding into
+    efficientnet_pytorch's static "same" padding), resnet101 is torchvision's class itself;
+  * structurally: parameter counts that reproduce the DVC checkpoint sizes and the widely quoted
+    smp totals (tests/test_oracle_models.py), MAC counts (App. D) and output shapes.
+The smp decoders/heads have no independent implementation available offline; they are pinned by the
+parameter totals and by the wiring spec of SURVEY.md App. A only.
 """
 from __future__ import annotations
 
