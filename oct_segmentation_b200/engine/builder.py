@@ -2,9 +2,12 @@
 
 A ``Builder`` is used once per (network, batch, resolution, input dtype): lowering code
 (engine/lower.py) calls ``conv`` / ``stem`` / ``maxpool`` / ``dwconv`` / ``se_project`` in
-network order; each call allocates its output activation (NHWC bf16), creates whatever plan the
-kernel needs and appends a closure to ``ops``.  ``run()`` replays the list on the current
-stream; ``CompiledNet`` (engine/network.py) captures that replay in a CUDA graph.
+network order; each call records one op: the activations it reads and writes (symbolic ``Act``
+buffers) and a ``make`` closure.  ``finalize()`` then places every activation in ONE arena by
+liveness (a buffer's bytes are reused as soon as its last reader has run -- only feature taps that
+a test wants to inspect are pinned), binds the tensors and calls every ``make`` (which creates the
+kernel plan with the final device pointers).  ``run()`` replays the op list on the current stream;
+``CompiledNet`` (engine/network.py) captures that replay in a CUDA graph.
 """
 from __future__ import annotations
 
@@ -49,37 +52,136 @@ def stem_s2d_weights(w: torch.Tensor, k: int, pad: Tuple[int, int]) -> Tuple[tor
     return w2, q0
 
 
+class _Op:
+    __slots__ = ('name', 'make', 'reads', 'writes', 'tc_macs')
+
+    def __init__(self, name, make, reads, writes, tc_macs):
+        self.name, self.make, self.reads, self.writes, self.tc_macs = name, make, reads, writes, tc_macs
+
+
+def plan_arena(items: Sequence[Tuple[int, int, int]], align: int = 256) -> Tuple[List[int], int]:
+    """items: (nbytes, first_op, last_op) with inclusive op-index intervals.  Returns (offsets, arena bytes).
+    Greedy first-fit over the buffers sorted by size: each buffer takes the lowest offset that is free of every
+    already-placed buffer whose lifetime overlaps its own."""
+    order = sorted(range(len(items)), key=lambda i: (-items[i][0], items[i][1]))
+    offsets = [0] * len(items)
+    placed: List[int] = []
+    top = 0
+    for i in order:
+        size, lo, hi = items[i]
+        size = (size + align - 1) // align * align
+        busy = sorted((offsets[j], offsets[j] + (items[j][0] + align - 1) // align * align) for j in placed
+                      if not (items[j][2] < lo or hi < items[j][1]))
+        off = 0
+        for b0, b1 in busy:
+            if off + size <= b0:
+                break
+            off = max(off, b1)
+        offsets[i] = off
+        placed.append(i)
+        top = max(top, off + size)
+    return offsets, top
+
+
 class Builder:
-    def __init__(self, device: torch.device, N: int):
+    def __init__(self, device: torch.device, N: int, reuse: bool = True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.N = N
+        self.reuse = reuse           # False: every activation keeps its own bytes (in-situ checks read dead inputs)
         self.ops: List[Callable[[], None]] = []
         self.op_names: List[str] = []
         self.op_macs: List[Optional[int]] = []   # algorithmic MACs of tensor-core launches, None otherwise
         self.macs = 0              # algorithmic MACs of the reference graph (dense count)
         self.tc_launches = 0
         self.launches = 0
-        self.act_bytes = 0
+        self.act_bytes = 0         # sum of all activation buffers (what a no-reuse allocation would take)
+        self.arena_bytes = 0       # bytes actually allocated for them
+        self._records: List[_Op] = []
+        self._acts: List[Act] = []
+        self._pinned: List[Act] = []
         self._keep: List[object] = []
+        self._final = False
 
     # ------------------------------------------------------------------ buffers
     def new_act(self, H: int, W: int, C: int) -> Act:
-        t = torch.zeros(self.N, H, W, pad8(C), dtype=torch.bfloat16, device=self.device)
-        self.act_bytes += t.numel() * 2
-        return Act(t, C)
+        a = Act.symbolic((self.N, H, W, pad8(C)), C)
+        self._acts.append(a)
+        self.act_bytes += a.nbytes
+        return a
 
-    def _add(self, name: str, fn: Callable[[], None], tc_macs: Optional[int] = None) -> None:
-        self.ops.append(fn)
+    def new_scratch(self, shape: Tuple[int, ...], dtype: torch.dtype) -> Act:
+        """Arena-resident temporary that is not an activation (e.g. the per-image projection weights)."""
+        a = Act.symbolic(tuple(shape), 0, dtype)
+        self._acts.append(a)
+        self.act_bytes += a.nbytes
+        return a
+
+    def pin(self, acts: Sequence[Act]) -> None:
+        """Keep these buffers intact until the end of the network (feature taps read by diagnostics)."""
+        self._pinned += list(acts)
+
+    def _add(self, name: str, make: Callable[[], Callable[[], None]], reads: Sequence[Act] = (),
+             writes: Sequence[Act] = (), tc_macs: Optional[int] = None, launches: int = 1) -> None:
+        assert not self._final, 'builder already finalized'
+        self._records.append(_Op(name, make, [a for a in reads if a is not None], list(writes), tc_macs))
         self.op_names.append(name)
         self.op_macs.append(tc_macs)
-        self.launches += 1
+        self.launches += launches
+
+    def plan_buffers(self) -> Tuple[List[Act], List[int], int]:
+        """Liveness of every arena buffer over the recorded op list -> (buffers, byte offsets, arena bytes).
+        Pure host arithmetic (no device needed)."""
+        n_ops = len(self._records)
+        first, last = {}, {}
+        for i, op in enumerate(self._records):
+            for a in op.writes:
+                first.setdefault(id(a), i)
+                last[id(a)] = max(last.get(id(a), i), i)
+            for a in op.reads:
+                if a._t is None:
+                    assert id(a) in first, f'{op.name} reads a buffer nobody wrote'
+                    last[id(a)] = i
+        for a in self._pinned:
+            if id(a) in first:
+                last[id(a)] = n_ops
+        acts = [a for a in self._acts if id(a) in first]
+        if not self.reuse:
+            items = [(a.nbytes, 0, n_ops) for a in acts]
+        else:
+            items = [(a.nbytes, first[id(a)], last[id(a)]) for a in acts]
+        offsets, total = plan_arena(items)
+        return acts, offsets, total
+
+    def finalize(self) -> None:
+        """Place the activations (liveness-based arena), bind them and create every kernel plan."""
+        if self._final:
+            return
+        acts, offsets, total = self.plan_buffers()
+        self.arena_bytes = total
+        with torch.cuda.device(self.device):
+            self._arena = torch.zeros(max(total, 256), dtype=torch.uint8, device=self.device)
+        for a, off in zip(acts, offsets):
+            a.t = self._arena[off:off + a.nbytes].view(a.dtype).view(a.shape)
+        self._final = True
+        self.ops = [op.make() for op in self._records]
+        self._records = []
 
     def run(self) -> None:
+        self.finalize()
         for op in self.ops:
             op()
 
     # ------------------------------------------------------------------ tensor-core conv
+    def _add_conv(self, name: str, geom, make_plan: Callable[[], ConvPlan], reads, writes) -> None:
+        def make():
+            plan = make_plan()
+            self._keep.append(plan)
+            return plan.run
+        self.macs += geom.macs
+        self.tc_launches += 1
+        self._add(name, make, reads, writes, tc_macs=geom.macs)
+
     def conv(self, srcs: Sequence[Tuple[Act, bool]], w: torch.Tensor, b: Optional[torch.Tensor], *, name: str,
              stride: int = 1, pad: Tuple[int, int] = (0, 0), groups: int = 1, transposed: bool = False,
              act: str = 'none', res: Optional[Act] = None, res_mode: str = 'none',
@@ -87,6 +189,7 @@ class Builder:
              out_tensor: Optional[torch.Tensor] = None) -> Optional[Act]:
         cout = w.shape[1] if transposed else w.shape[0]
         bf16_out = out_mode == 'bf16_nhwc'
+        reads = [a for a, _ in srcs] + [res]
         # narrow stride-1 convs: pack f adjacent pixels into one GEMM row (same memory, wider view)
         f = 0
         if (not transposed and groups == 1 and stride == 1 and not any(up for _, up in srcs) and out_hw is None
@@ -96,27 +199,26 @@ class Builder:
             a0 = srcs[0][0]
             cout_store = pad8(cout) if bf16_out else cout
             wp, bp = pack_conv_weights(w, b, [a.C for a, _ in srcs], [a.Cp for a, _ in srcs], f, pad[1], cout_store)
-            views = [a.t.view(a.N, a.H, a.W // f, f * a.Cp) for a, _ in srcs]
-            spec = [((v.shape[0], v.shape[1], v.shape[2], v.shape[3], v.shape[3]), False) for v in views]
+            spec = [((a.N, a.H, a.W // f, f * a.Cp, f * a.Cp), False) for a, _ in srcs]
             geom, packed = plan_conv(spec, wp, stride=1, pad=(pad[0], 1 if w.shape[3] > 1 else 0), out_bf16=bf16_out)
             geom.macs = a0.N * a0.H * a0.W * cout * w.shape[1] * w.shape[2] * w.shape[3]     # dense count of the real op
             bias_rows = pad_bias(bp, geom, f * cout_store)
-            out_act, res_t = None, None
+            out_act = None
             if bf16_out:
                 out_act = self.new_act(a0.H, a0.W, cout)
-                out_t = out_act.t.view(a0.N, a0.H, a0.W // f, f * cout_store)
-                if res is not None:
-                    res_t = res.t.view(a0.N, a0.H, a0.W // f, f * cout_store)
-                plan = ConvPlan(geom, packed, bias_rows, views, out_t, out_mode=out_mode, act=act, res=res_t,
-                                res_mode=res_mode, name=name)
             else:
                 assert out_tensor is not None and tuple(out_tensor.shape) == (self.N, cout, a0.H, a0.W) and res is None
-                plan = ConvPlan(geom, packed, bias_rows, views, out_tensor, out_mode=out_mode, act=act, name=name,
+
+            def make_plan():
+                views = [a.t.view(a.N, a.H, a.W // f, f * a.Cp) for a, _ in srcs]
+                if bf16_out:
+                    out_t = out_act.t.view(a0.N, a0.H, a0.W // f, f * cout_store)
+                    res_t = res.t.view(a0.N, a0.H, a0.W // f, f * cout_store) if res is not None else None
+                    return ConvPlan(geom, packed, bias_rows, views, out_t, out_mode=out_mode, act=act, res=res_t,
+                                    res_mode=res_mode, name=name)
+                return ConvPlan(geom, packed, bias_rows, views, out_tensor, out_mode=out_mode, act=act, name=name,
                                 out_pack=f, out_ldc=cout)
-            self._keep.append(plan)
-            self.macs += geom.macs
-            self.tc_launches += 1
-            self._add(name, plan.run, tc_macs=geom.macs)
+            self._add_conv(name, geom, make_plan, reads, [out_act] if out_act is not None else [])
             return out_act
 
         # narrow decoder conv over cat([up(x), skips...]): the half-resolution tile grid of the fused form
@@ -142,12 +244,9 @@ class Builder:
             cin = w.shape[0] if transposed else w.shape[1]
             geom.macs = a0.N * a0.H * a0.W * cin * cout * (16 if transposed else 36)   # dense count of the real op
             out_act = self.new_act(2 * a0.H, 2 * a0.W, cout)
-            plan = ConvPlan(geom, packed, pad_bias(bp, geom, 4 * cs), [a0.t], out_act.t, act=act, name=name,
-                            out_ldc=out_act.Cp, d2s=cs)
-            self._keep.append(plan)
-            self.macs += geom.macs
-            self.tc_launches += 1
-            self._add(name, plan.run, tc_macs=geom.macs)
+            bias_rows = pad_bias(bp, geom, 4 * cs)
+            self._add_conv(name, geom, lambda: ConvPlan(geom, packed, bias_rows, [a0.t], out_act.t, act=act, name=name,
+                                                        out_ldc=out_act.Cp, d2s=cs), reads, [out_act])
             return out_act
 
         spec = [((a.N, a.H, a.W, a.C, a.Cp), up) for a, up in srcs]
@@ -157,16 +256,14 @@ class Builder:
         out_act = None
         if bf16_out:
             out_act = self.new_act(geom.out_H, geom.out_W, cout)
-            out_t = out_act.t
         else:
-            out_t = out_tensor
-            assert out_t is not None and tuple(out_t.shape) == (self.N, cout, geom.out_H, geom.out_W)
-        plan = ConvPlan(geom, packed, bias_rows, [a.t for a, _ in srcs], out_t, out_mode=out_mode, act=act,
-                        res=res.t if res is not None else None, res_mode=res_mode, name=name)
-        self._keep.append(plan)
-        self.macs += geom.macs
-        self.tc_launches += 1
-        self._add(name, plan.run, tc_macs=geom.macs)
+            assert out_tensor is not None and tuple(out_tensor.shape) == (self.N, cout, geom.out_H, geom.out_W)
+
+        def make_plan():
+            return ConvPlan(geom, packed, bias_rows, [a.t for a, _ in srcs], out_act.t if bf16_out else out_tensor,
+                            out_mode=out_mode, act=act, res=res.t if res is not None else None, res_mode=res_mode,
+                            name=name)
+        self._add_conv(name, geom, make_plan, reads, [out_act] if out_act is not None else [])
         return out_act
 
     # ------------------------------------------------------------------ CUDA-core kernels
@@ -191,13 +288,14 @@ class Builder:
         def pack_op():
             _lib.check(lib.octseg_stem_pack(x.data_ptr(), dt, sn, sc, sh, sw, N, H, W, mean_a, istd_a,
                                             x2.t.data_ptr(), _lib.stream_ptr()), name + '.pack')
-        self._add(name + '.pack', pack_op)
+        self._add(name + '.pack', lambda: pack_op, [], [x2])
         w2, q0 = stem_s2d_weights(w, k, pad)
         assert q0[0] <= 0 and q0[1] <= 0
         out = self.conv([(x2, False)], w2, b, name=name, pad=(-q0[0], -q0[1]), out_hw=out_hw, act=act)
         real = N * out_hw[0] * out_hw[1] * cout * 3 * k * k        # algorithmic MACs: the dense count of the real op
         self.macs += real - self.op_macs[-1]
         self.op_macs[-1] = real
+        self._records[-1].tc_macs = real
         return out
 
     def maxpool(self, x: Act, *, name: str) -> Act:
@@ -208,7 +306,7 @@ class Builder:
         def op():
             _lib.check(lib.octseg_maxpool3x3s2(x.t.data_ptr(), out.t.data_ptr(), x.N, x.H, x.W, x.Cp, Ho, Wo,
                                                _lib.stream_ptr()), name)
-        self._add(name, op)
+        self._add(name, lambda: op, [x], [out])
         return out
 
     def dwconv(self, x: Act, w: torch.Tensor, b: torch.Tensor, *, name: str, k: int, stride: int,
@@ -225,7 +323,7 @@ class Builder:
                                          x.W, x.C, k, stride, pad[0], pad[1], out_hw[0], out_hw[1], a,
                                          pool.data_ptr() if pool is not None else None, _lib.stream_ptr()), name)
         self.macs += x.N * out_hw[0] * out_hw[1] * x.C * k * k
-        self._add(name, op)
+        self._add(name, lambda: op, [x], [out])
         return out
 
     def se_project(self, x: Act, pool: torch.Tensor, w1, b1, w2, b2, wp: torch.Tensor, bp: torch.Tensor, *,
@@ -244,13 +342,11 @@ class Builder:
         geom, packed32 = plan_conv(spec, wp, out_hw=(x.H, x.W), packed_dtype=torch.float32)
         rows, Ktot = packed32.shape[1], packed32.shape[2]
         base = packed32[0].contiguous().to(dev)                                    # fp32 [rows][Ktot]
-        wn = torch.zeros(N, rows, Ktot, dtype=torch.bfloat16, device=dev)
+        wn = self.new_scratch((N, rows, Ktot), torch.bfloat16)                     # per-image weights: dead after the conv
         cout = wp.shape[0]
         out = self.new_act(x.H, x.W, cout)
-        plan = ConvPlan(geom, wn, pad_bias(bp, geom, cout), [x.t], out.t, act='none',
-                        res=res.t if res is not None else None, res_mode='before_act' if res is not None else 'none',
-                        per_image_weights=True, name=name)
-        self._keep += [plan, w1d, b1d, w2d, b2d, hidden, gate, base, wn]
+        bias_rows = pad_bias(bp, geom, cout)
+        self._keep += [w1d, b1d, w2d, b2d, hidden, gate, base]
         lib, inv_hw = self.lib, 1.0 / float(x.H * x.W)
 
         def gate_op():
@@ -259,11 +355,12 @@ class Builder:
                                             N, C_mid, cr, st), name + '.se_hidden')
             _lib.check(lib.octseg_se_gate(hidden.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gate.data_ptr(),
                                           pool.data_ptr(), N, C_mid, cr, st), name + '.se_gate')
-            _lib.check(lib.octseg_se_scale_weights(gate.data_ptr(), base.data_ptr(), wn.data_ptr(), N, rows, Ktot,
+            _lib.check(lib.octseg_se_scale_weights(gate.data_ptr(), base.data_ptr(), wn.t.data_ptr(), N, rows, Ktot,
                                                    C_mid, st), name + '.se_scale_weights')
-        self.macs += geom.macs + N * 2 * C_mid * cr
-        self.tc_launches += 1
-        self._add(name + '.se', gate_op)
-        self.launches += 2                      # gate_op is three launches
-        self._add(name, plan.run, tc_macs=geom.macs)
+        self.macs += N * 2 * C_mid * cr
+        self._add(name + '.se', lambda: gate_op, [], [wn], launches=3)
+        self._add_conv(name, geom, lambda: ConvPlan(geom, wn.t, bias_rows, [x.t], out.t, act='none',
+                                                    res=res.t if res is not None else None,
+                                                    res_mode='before_act' if res is not None else 'none',
+                                                    per_image_weights=True, name=name), [x, res, wn], [out])
         return out

@@ -42,20 +42,49 @@ def pad8(c: int) -> int:
     return (c + 7) // 8 * 8
 
 
-@dataclass
 class Act:
-    """NHWC bf16 activation: ``t`` has shape (N, H, W, Cp) with Cp = pad8(C); pad channels are 0."""
-    t: torch.Tensor
-    C: int
+    """NHWC bf16 activation of shape (N, H, W, Cp) with Cp = pad8(C); pad channels are 0.
+
+    ``Act(tensor, C)`` wraps an existing tensor.  ``Act.symbolic(shape, C)`` is a buffer the Builder places in
+    its activation arena later (engine/builder.py: liveness-based reuse); ``t`` is bound by ``Builder.finalize``."""
+
+    def __init__(self, t: Optional[torch.Tensor], C: int, shape: Optional[Tuple[int, ...]] = None,
+                 dtype: torch.dtype = torch.bfloat16):
+        self._t = t
+        self.C = C
+        self.shape = tuple(t.shape) if t is not None else tuple(shape)
+        self.dtype = t.dtype if t is not None else dtype
+
+    @classmethod
+    def symbolic(cls, shape: Tuple[int, ...], C: int, dtype: torch.dtype = torch.bfloat16) -> 'Act':
+        return cls(None, C, shape, dtype)
 
     @property
-    def N(self): return self.t.shape[0]
+    def t(self) -> torch.Tensor:
+        if self._t is None:
+            raise RuntimeError('activation buffer is not placed yet (Builder.finalize() binds arena buffers)')
+        return self._t
+
+    @t.setter
+    def t(self, value: torch.Tensor) -> None:
+        self._t = value
+        self.shape = tuple(value.shape)
+
     @property
-    def H(self): return self.t.shape[1]
+    def nbytes(self) -> int:
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n * torch.empty((), dtype=self.dtype).element_size()
+
     @property
-    def W(self): return self.t.shape[2]
+    def N(self): return self.shape[0]
     @property
-    def Cp(self): return self.t.shape[3]
+    def H(self): return self.shape[1]
+    @property
+    def W(self): return self.shape[2]
+    @property
+    def Cp(self): return self.shape[3]
 
 
 @dataclass

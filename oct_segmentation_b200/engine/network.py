@@ -17,7 +17,7 @@ from .lower import DECODER_LOWERING, ENCODER_LOWERING, lower_head
 class CompiledNet:
     def __init__(self, model, N: int, H: int, W: int, device, in_dtype: str = 'f32', out_mode: str = 'f32_nchw',
                  norm: Optional[Tuple[Sequence[float], Sequence[float]]] = None, use_graph: bool = True,
-                 builder_cls=Builder):
+                 builder_cls=Builder, **builder_kw):
         if H % 32 or W % 32:
             raise RuntimeError(f'Wrong input shape height={H}, width={W}. Expected image height and width '
                                f'divisible by 32.')
@@ -34,14 +34,17 @@ class CompiledNet:
             x_view = self.x_nhwc.permute(0, 3, 1, 2)
             odt = torch.float32 if out_mode == 'f32_nchw' else torch.uint8
             self.out = torch.zeros(N, classes, H, W, dtype=odt, device=self.device)
-            b = builder_cls(self.device, N)
+            b = builder_cls(self.device, N, **builder_kw)
             feats = ENCODER_LOWERING[model.encoder.kind](b, model.encoder, x_view, in_dtype, norm)
             y = DECODER_LOWERING[model.decoder.kind](b, model.decoder, feats)
             lower_head(b, model.segmentation_head, y, self.out, out_mode)
             self.feats, self.dec_out = feats, y        # kept for per-stage parity diagnostics
+            b.pin(list(feats) + [y])                   # (pinned: not recycled by the activation arena)
+            b.finalize()                               # liveness-based arena, kernel plans with final pointers
         self.builder = b
         self.macs = b.macs
         self.launches = b.launches
+        self.act_bytes, self.arena_bytes = b.act_bytes, b.arena_bytes
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
 

@@ -197,8 +197,9 @@ class EnsemblePipeline:
         """Pipelined form of ``run_host`` over an iterable of host batches (uint8 (n <= batch, Hs, Ws, 3)):
         the H2D copy of batch i+1 and the D2H copy of batch i-1 run on their own streams under the compute
         of batch i (two sets of pinned and device staging buffers).  Yields host (mask, label, counts,
-        radii) per batch, in order.  With copy=False the arrays are views of pinned buffers that stay valid
-        until the generator has been advanced twice more."""
+        radii) per batch, in order.  With copy=False the arrays are views of pinned buffers that are valid only
+        until the generator is advanced again: batch j is yielded during iteration j+1, and the next advance
+        (iteration j+2) enqueues new D2H copies into the same staging set."""
         sets = self._stream_sets()
         h2d, d2h = self._copy_streams
         pending = []

@@ -71,9 +71,13 @@ def preprocess_images(images: List[Image.Image], input_size: int, device: str = 
 
 def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Sequence[int], classes: Sequence[str],
             models_dir: str, device: str, batch_size: int = 16, models: Dict = None,
-            quantities: List = None) -> List[np.ndarray]:
+            quantities: List = None, pipe: EnsemblePipeline = None) -> List[np.ndarray]:
     """Perform segmentation for given images using specified models; fills and returns ``masks``
-    (the caller's float64 HxWx4 arrays), channel CLASS_IDS[name]-1 per requested class."""
+    (the caller's float64 HxWx4 arrays), channel CLASS_IDS[name]-1 per requested class.
+
+    ``pipe``: an EnsemblePipeline from ``make_pipeline`` to reuse across calls (the streaming main() builds it
+    once: networks are compiled for ``batch_size`` frames, staging buffers and streams are allocated once;
+    a short last batch is zero-filled, never recompiled)."""
     if device != 'cuda':
         raise RuntimeError('the B200 build of segment() runs on CUDA only (device resolved to %r)' % device)
     if not images:
@@ -83,10 +87,12 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
         models = load_models(models_dir, classes, device)
     frames = np.stack([np.array(img.convert('RGB') if img.mode != 'RGB' else img) for img in images])
     n = frames.shape[0]
-    batch = min(batch_size, n)
-    pipe = EnsemblePipeline(models, classes, output_size, dev, batch, src_hw=frames.shape[1:3],
-                            thickness=quantities is not None,
-                            contour=quantities is not None and P.contour_fits(int(output_size[1]), int(output_size[0])))
+    if pipe is None:
+        pipe = make_pipeline(models, classes, output_size, min(batch_size, n), frames.shape[1:3], quantities is not None, dev)
+    elif (pipe.src_hw != tuple(frames.shape[1:3]) or pipe.classes != list(classes)
+          or (pipe.Wo, pipe.Ho) != (int(output_size[0]), int(output_size[1])) or (quantities is not None and not pipe.thickness)):
+        raise ValueError('segment(): the pipeline passed in was built for a different frame size / class list / output size')
+    batch = pipe.batch
     spans = [(lo, min(lo + batch, n)) for lo in range(0, n, batch)]
     # copies of batch i+1 / i-1 overlap the compute of batch i (EnsemblePipeline.stream_host)
     for (lo, hi), (mask, label, counts, radii, *contours) in zip(spans, pipe.stream_host(frames[lo:hi] for lo, hi in spans)):
@@ -99,6 +105,14 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
             quantities.extend(P.quantities_from_counts(counts, pipe.Ho, pipe.Wo, ratio, radii,
                                                        contours[0] if contours else None))
     return masks
+
+
+def make_pipeline(models: Dict, classes: Sequence[str], output_size: Sequence[int], batch: int, src_hw, quantities: bool,
+                  dev=None) -> EnsemblePipeline:
+    """The batched GPU pipeline segment() drives: one compiled network per model for ``batch`` frames of ``src_hw``."""
+    dev = torch.device('cuda:0') if dev is None else dev
+    return EnsemblePipeline(models, classes, output_size, dev, batch, src_hw=tuple(src_hw), thickness=quantities,
+                            contour=quantities and P.contour_fits(int(output_size[1]), int(output_size[0])))
 
 
 def list_images(data_path: str) -> List[str]:
@@ -220,6 +234,9 @@ def main(cfg) -> None:
         models = load_models(models_dir, cfg.classes, device) if paths else {}
         table = {} if want_quantities else None
         spans = [(lo, min(lo + chunk, len(paths))) for lo in range(0, len(paths), chunk)]
+        # ONE pipeline for the whole run: data_processing resizes every frame to output_size, so all chunks share it
+        pipe = make_pipeline(models, cfg.classes, cfg.output_size, min(batch_size, chunk),
+                             (int(cfg.output_size[1]), int(cfg.output_size[0])), want_quantities) if paths else None
         with ThreadPoolExecutor(max_workers=int(cfg.get('io_workers', 8))) as io, \
                 ThreadPoolExecutor(max_workers=2) as stage:
             def load(span):
@@ -232,7 +249,7 @@ def main(cfg) -> None:
                 quantities = [] if want_quantities else None
                 masks = segment(images=images, masks=masks, output_size=cfg.output_size, classes=cfg.classes,
                                 models_dir=models_dir, device=device, batch_size=batch_size, models=models,
-                                quantities=quantities)
+                                quantities=quantities, pipe=pipe)
                 if want_quantities:
                     table.update(zip(names, quantities))
                 if saving is not None:

@@ -43,6 +43,8 @@ encoders = SimpleNamespace(get_preprocessing_params=get_preprocessing_params, ge
 class SegmentationModel(nn.Module):
     """Parameter tree (.encoder/.decoder/.segmentation_head) + engine-backed forward."""
 
+    MAX_COMPILED = 4     # compiled (batch, size, dtype, mode) plans kept per model; each owns an activation arena
+
     def _post_init(self):
         M.init_decoder(self.decoder)
         M.init_head(self.segmentation_head)
@@ -69,10 +71,12 @@ class SegmentationModel(nn.Module):
     def compiled(self, N: int, H: int, W: int, device, in_dtype: str = 'f32', out_mode: str = 'f32_nchw',
                  norm=None, use_graph: bool = True) -> CompiledNet:
         key = (N, H, W, str(device), in_dtype, out_mode, None if norm is None else (tuple(norm[0]), tuple(norm[1])))
-        net = self._compiled.get(key)
+        net = self._compiled.pop(key, None)
         if net is None:
             net = CompiledNet(self, N, H, W, device, in_dtype, out_mode, norm, use_graph)
-            self._compiled[key] = net
+            while len(self._compiled) >= self.MAX_COMPILED:        # least recently used plan (and its arena) goes
+                self._compiled.pop(next(iter(self._compiled)))
+        self._compiled[key] = net                                  # most recently used last
         return net
 
     def forward(self, x: torch.Tensor, _norm=None) -> torch.Tensor:

@@ -197,7 +197,9 @@ class MBConvBlock(nn.Module):
             x = x * torch.sigmoid(x)
         x = self._bn1(self._depthwise_conv(x))
         x = x * torch.sigmoid(x)
-        s = F.adaptive_avg_pool2d(x, 1)
+        # efficientnet_pytorch: F.adaptive_avg_pool2d(x, 1).  Its CUDA backward is not deterministic, so the
+        # (test-only) seeded fits of oracle/synth.py take the same mean through a reduction that is
+        s = x.mean((2, 3), keepdim=True) if self.training else F.adaptive_avg_pool2d(x, 1)
         s = self._se_reduce(s)
         s = s * torch.sigmoid(s)
         s = self._se_expand(s)

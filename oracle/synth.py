@@ -8,6 +8,8 @@ zeros outside it); generator per SURVEY.md §8d.
 """
 from __future__ import annotations
 
+import contextlib
+import math
 from typing import Dict, List, Sequence
 
 import numpy as np
@@ -118,32 +120,53 @@ def phantom_targets(start: int, count: int, size: int, n_classes: int) -> np.nda
     return out
 
 
-def fit_model(model: 'model_ref.OCTSegmentationModelRef', device, steps: int = 120, size: int = 128, batch: int = 8,
-              lr: float = 2e-3, seed: int = 0, target_loss: float = 0.0, max_steps: int = 0) -> float:
-    """Short seeded fit of the WHOLE oracle network on phantom targets (Adam, BCE-with-logits), so
-    that masks are structured and |logit| is large away from object boundaries -- the regime a
-    trained checkpoint is in (after `steps` steps it keeps going until the smoothed loss drops below
-    `target_loss` or `max_steps` is reached), and the one in which Dice between two implementations is meaningful
-    (SURVEY.md S7 'hard parts').  Returns the final loss.  Leaves the model in eval mode."""
+@contextlib.contextmanager
+def deterministic_torch():
+    """Bit-reproducible training on one GPU model + software stack: deterministic cuDNN/cuBLAS algorithms only
+    (CUBLAS_WORKSPACE_CONFIG must be set before CUDA starts -- tests/conftest.py does).  The same seeds then give
+    the same fitted weights on every B200 lease, so a parity gate built on them does not depend on the lease."""
+    prev = (torch.are_deterministic_algorithms_enabled(), torch.is_deterministic_algorithms_warn_only_enabled(),
+            torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    try:
+        yield
+    finally:
+        torch.use_deterministic_algorithms(prev[0], warn_only=prev[1])
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = prev[2], prev[3]
+
+
+def fit_model(model: 'model_ref.OCTSegmentationModelRef', device, steps: int = 300, size: int = 128, batch: int = 8,
+              lr: float = 2e-3, seed: int = 0, pool: int = 32, log=None) -> float:
+    """Short seeded, DETERMINISTIC fit of the WHOLE oracle network on phantom targets (Adam, BCE-with-logits, cosine
+    learning-rate decay, a fixed number of steps) at the resolution the checkpoint will be used at, so that masks are
+    structured and |logit| is large away from object boundaries -- the regime a trained checkpoint is in, and the one
+    in which Dice between two implementations is meaningful (SURVEY.md S7 'hard parts').  Frames `1000 .. 1000+pool`
+    of the synthetic generator are cycled.  Returns the smoothed final loss.  Leaves the model in eval mode."""
     torch.manual_seed(seed)
     net = model.model.to(device)
     net.train()
     opt = torch.optim.Adam(net.parameters(), lr=lr)
     n_classes = len(model.classes)
-    loss_v, ema = float('nan'), None
-    for step in range(max(steps, max_steps)):
-        idx = 1000 + step * batch
-        frames = synthetic_frames(idx, batch, size)[..., ::-1].copy()
-        x = torch.from_numpy(frames).to(device).permute(0, 3, 1, 2).float()
-        t = torch.from_numpy(phantom_targets(idx, batch, size, n_classes)).to(device)
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(net(x), t)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        loss_v = loss.item()
-        ema = loss_v if ema is None else 0.9 * ema + 0.1 * loss_v
-        if step + 1 >= steps and (target_loss <= 0.0 or ema < target_loss):
-            break
+    pool = max(pool, batch)
+    frames = torch.from_numpy(synthetic_frames(1000, pool, size)[..., ::-1].copy())
+    targets = torch.from_numpy(phantom_targets(1000, pool, size, n_classes))
+    ema = None
+    with deterministic_torch():
+        for step in range(steps):
+            for g in opt.param_groups:
+                g['lr'] = lr * (0.05 + 0.95 * 0.5 * (1.0 + math.cos(math.pi * step / steps)))
+            idx = [(step * batch + j) % pool for j in range(batch)]
+            x = frames[idx].to(device).permute(0, 3, 1, 2).float()
+            t = targets[idx].to(device)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(net(x), t)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            v = loss.item()
+            ema = v if ema is None else 0.9 * ema + 0.1 * v
+            if log is not None and (step % 25 == 0 or step == steps - 1):
+                log(f'step {step}: loss {v:.4f} (smoothed {ema:.4f})')
     net.eval()
     model.eval()
-    return loss_v
+    return float(ema)

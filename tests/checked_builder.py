@@ -17,7 +17,7 @@ def _rel(a, b):
 
 class CheckedBuilder(Builder):
     def __init__(self, device, N):
-        super().__init__(device, N)
+        super().__init__(device, N, reuse=False)     # the references re-read inputs that would otherwise be dead
         self.ref = Bf16Builder(N, device)
         self.checks = []
         self._pools = {}        # '<name>.se' -> live SE pool tensor (the gate kernel zeroes it after use)
@@ -76,6 +76,7 @@ class CheckedBuilder(Builder):
     @torch.no_grad()
     def run_checked(self):
         """Runs the op list one launch at a time; returns [(name, rel_l2)]."""
+        self.finalize()
         checks = {}
         for name, r, g in self.checks:          # a split conv registers its inner launch, then the whole op: keep the latter
             checks[name.replace('[mask]', '')] = (name, r, g)

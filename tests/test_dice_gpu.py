@@ -1,19 +1,56 @@
-"""GPU: mask-level parity on a FITTED synthetic checkpoint.  The fp32 oracle network is fitted for a
-few dozen Adam steps on phantom targets (on the GPU, in this test), its weights are loaded into the
-B200 engine, and both implementations segment unseen synthetic frames.
+"""GPU: mask-level parity on FITTED synthetic checkpoints at the shipped sizes (BASELINE.json
+north_star: per-class Dice >= 0.999 against the reference PyTorch implementation on the same frames,
+bit-exact areas wherever the masks match).
 
-Bars (BASELINE.json north_star): per-class Dice >= 0.999 between the two implementations' masks;
-pixel areas (non-zero counts) equal wherever the masks are equal; logits rel-L2 <= 3e-2 (bf16
-storage vs fp32 -- a fitted network no longer amplifies rounding noise the way the BN-calibrated
-random one does)."""
+The reference's trained weights are not available offline, and a randomly initialised network has
+near-zero logits whose sign is decided by rounding.  So each fp32 oracle network (oracle/smp_ref.py)
+is fitted ONCE per session for a few hundred seeded Adam steps on phantom targets AT THE RESOLUTION IT
+SHIPS AT (LM 512, FC_LC / VV 896), with deterministic cuDNN/cuBLAS algorithms: the same seeds give the
+same weights on every B200 lease (`test_fit_is_deterministic` checks that the recipe is bit-reproducible).
+The weights are loaded into the B200 engine and both implementations segment unseen synthetic frames.
+
+Bars, written here:
+  * logits rel-L2 <= 2e-2 end to end (bf16 storage vs fp32 -- fitted nets reach ~1e-3);
+  * per-class Dice >= 0.999 between the two implementations' masks;
+  * per frame and class, pixel areas equal wherever the two masks are equal;
+  * the same through the product's `segment()` (pre-processing, three networks, routing, nearest resize
+    to output_size 1000 x 1000) against the oracle's restatement of src/predict.py:61-101.
+
+These tests run LAST (tests/conftest.py) so that a mask-level failure cannot hide kernel-level results.
+"""
 import numpy as np
 import pytest
 import torch
+from PIL import Image
 
 from oct_segmentation_b200.model import OCTSegmentationModel
-from oracle import synth
+from oracle import model_ref, synth
 
 pytestmark = pytest.mark.gpu
+
+# (fit resolution = shipped input size, batch, steps): sized so that all three fits take ~1-2 minutes on a B200
+FIT = {'LM': (512, 2, 300), 'VV': (896, 1, 300), 'FC_LC': (896, 1, 400)}
+_CACHE = {}
+
+
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def fitted(key):
+    """(oracle model on cuda, product model on cuda, final smoothed loss) -- fitted once per session."""
+    if key not in _CACHE:
+        _no_tf32()
+        size, batch, steps = FIT[key]
+        ref = synth.make_model(key, calib_size=128, calib_frames=2)
+        loss = synth.fit_model(ref, 'cuda', steps=steps, size=size, batch=batch)
+        cfg = synth.MODEL_CONFIGS[key]
+        ours = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
+                                    in_channels=3, classes=cfg['classes'], encoder_weights=None)
+        ours.load_state_dict(ref.state_dict(), strict=True)
+        _CACHE[key] = (ref.cuda().eval(), ours.cuda().eval(), loss)
+    return _CACHE[key]
 
 
 def dice(a, b):
@@ -21,39 +58,81 @@ def dice(a, b):
     return 2.0 * inter / max(a.sum().item() + b.sum().item(), 1)
 
 
-@pytest.mark.parametrize('key,size,steps', [('VV', 256, 150), ('LM', 256, 200), ('FC_LC', 256, 400)])
-def test_fitted_checkpoint_dice(key, size, steps):
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    ref = synth.make_model(key, calib_size=128, calib_frames=2)
-    loss = synth.fit_model(ref, 'cuda', steps=steps, size=128, batch=8, target_loss=0.005, max_steps=1500)
+def test_fit_is_deterministic():
+    """Two runs of the seeded fit recipe give bit-identical weights (so every lease tests the same checkpoint)."""
+    _no_tf32()
+    sds = []
+    for _ in range(2):
+        m = synth.make_model('VV', calib_size=64, calib_frames=1)
+        synth.fit_model(m, 'cuda', steps=6, size=64, batch=2, pool=4)
+        sds.append({k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+    bad = [k for k in sds[0] if not torch.equal(sds[0][k], sds[1][k])]
+    assert not bad, f'{len(bad)} tensors differ between two seeded fits, e.g. {bad[:3]}'
+
+
+@pytest.mark.parametrize('key,frames_n', [('VV', 3), ('LM', 4), ('FC_LC', 3)])
+def test_fitted_checkpoint_dice_at_shipped_size(key, frames_n):
+    ref, ours, loss = fitted(key)
     cfg = synth.MODEL_CONFIGS[key]
-    ours = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
-                                in_channels=3, classes=cfg['classes'], encoder_weights=None)
-    ours.load_state_dict(ref.state_dict(), strict=True)
-    ours = ours.cuda().eval()
-    frames = synth.synthetic_frames(5000, 8, size)[..., ::-1].copy()
+    size = cfg['input_size']
+    frames = synth.synthetic_frames(5000, frames_n, size)[..., ::-1].copy()        # unseen frames, BGR like predict()
     x = torch.from_numpy(frames).cuda().permute(0, 3, 1, 2).float()
     with torch.no_grad():
-        want = ref.model(x)
+        want = torch.cat([ref.model(x[i:i + 1]) for i in range(frames_n)])
         got = ours.model(x)
     rel = ((got - want).norm() / want.norm()).item()
     band = (want.abs() < 0.25).float().mean().item()
-    report = [f'fit loss {loss:.4f}', f'logits rel-L2 {rel:.2e}', f'|logit|<0.25 on {100 * band:.2f}% of pixels']
+    report = [f'fit loss {loss:.4f}', f'{size}x{size}', f'logits rel-L2 {rel:.2e}', f'|logit|<0.25 on {100 * band:.2f}% of pixels']
     ok = True
     for c, name in enumerate(cfg['classes']):
         a, b = want[:, c] > 0, got[:, c] > 0
         d = dice(a, b)
         frac = a.float().mean().item()
         diff = (a != b).sum().item()
-        report.append(f'{name}: dice {d:.5f}, positive {100 * frac:.1f}%, {diff} differing px, '
-                      f'areas {int(a.sum())} vs {int(b.sum())}')
+        report.append(f'{name}: dice {d:.5f}, positive {100 * frac:.1f}%, {diff} differing px '
+                      f'({(a & ~b).sum().item()} lost, {(~a & b).sum().item()} gained), areas {int(a.sum())} vs {int(b.sum())}')
         assert frac > 0.005, f'{name}: fitted oracle predicts an empty mask ({frac})'
         ok &= d >= 0.999
-        per_frame_equal = [(a[n] == b[n]).all().item() for n in range(a.shape[0])]
-        for n, eq in enumerate(per_frame_equal):
-            if eq:
+        for n in range(a.shape[0]):
+            if (a[n] == b[n]).all().item():
                 assert int(a[n].sum()) == int(b[n].sum())
     print(f'\n{key}: ' + '; '.join(report))
-    assert rel <= 3e-2, report
+    assert rel <= 2e-2, report
+    assert ok, report
+
+
+def test_segment_ensemble_dice_at_output_size():
+    """All three fitted models through the product's segment() vs the oracle's restatement of the reference's segment()
+    (src/predict.py:61-101): PIL bicubic to 1000 x 1000, cv2 bilinear + BGR to each model's size, network, threshold,
+    nearest resize, class routing.  Per-class Dice >= 0.999; areas bit-exact per frame wherever the masks match."""
+    from oct_segmentation_b200 import predict as P
+    _no_tf32()
+    classes = ['Lumen', 'Fibrous cap', 'Lipid core', 'Vasa vasorum']
+    out_size = [1000, 1000]
+    n = 3
+    rgb = synth.synthetic_frames(7000, n, 512)
+    images = [Image.fromarray(f).resize(tuple(out_size)) for f in rgb]               # data_processing (src/data/utils.py:187)
+    ours_models, ref_models = {}, {}
+    for key in ('LM', 'FC_LC', 'VV'):
+        ref, ours, _ = fitted(key)
+        ours_models[key] = (ours, synth.MODEL_CONFIGS[key])
+        ref_models[key] = (ref, synth.MODEL_CONFIGS[key])
+    masks_ours = [np.zeros((out_size[0], out_size[1], 4)) for _ in range(n)]
+    masks_ref = [np.zeros((out_size[0], out_size[1], 4)) for _ in range(n)]
+    P.segment(images, masks_ours, out_size, classes, models_dir='', device='cuda', batch_size=n, models=ours_models)
+    model_ref.segment_with_models(images, masks_ref, out_size, classes, ref_models, 'cuda')
+    report, ok = [], True
+    for name in classes:
+        c = model_ref.CLASS_IDS[name] - 1
+        a = torch.from_numpy(np.stack([m[:, :, c] for m in masks_ref]) != 0)
+        b = torch.from_numpy(np.stack([m[:, :, c] for m in masks_ours]) != 0)
+        assert set(np.unique(np.stack([m[:, :, c] for m in masks_ours]))) <= {0.0, 1.0}
+        d = dice(a, b)
+        report.append(f'{name}: dice {d:.5f}, {int((a != b).sum())} differing px, areas {int(a.sum())} vs {int(b.sum())}')
+        assert a.float().mean().item() > 0.003, f'{name}: empty oracle mask'
+        ok &= d >= 0.999
+        for i in range(n):
+            if (a[i] == b[i]).all().item():
+                assert int(a[i].sum()) == int(b[i].sum())
+    print('\nsegment(): ' + '; '.join(report))
     assert ok, report

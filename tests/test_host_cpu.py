@@ -242,3 +242,63 @@ def test_contour_fits_matches_the_c_abi_limit():
     one = ctypes.c_void_p(16)         # never dereferenced: the size check comes first and no kernel is launched
     rc = lib.octseg_contour_largest(one, 1, 2048, 2048, one, one, one, 8, None)
     assert rc != 0 and b'shared memory' in lib.octseg_last_error()
+
+
+def test_arena_planner_never_overlaps_live_buffers():
+    """engine.builder.plan_arena: buffers whose op intervals intersect never share bytes; the arena stays
+    close to the peak of live bytes."""
+    import random
+    from oct_segmentation_b200.engine.builder import plan_arena
+    rnd = random.Random(0)
+    items = []
+    for _ in range(200):
+        lo = rnd.randint(0, 300)
+        items.append((rnd.randint(1, 1000) * 1000, lo, lo + rnd.randint(0, 25)))
+    offs, total = plan_arena(items)
+    for i in range(len(items)):
+        assert offs[i] % 256 == 0
+        for j in range(i):
+            if not (items[i][2] < items[j][1] or items[j][2] < items[i][1]):
+                a0, a1, b0, b1 = offs[i], offs[i] + items[i][0], offs[j], offs[j] + items[j][0]
+                assert a1 <= b0 or b1 <= a0, (i, j)
+    peak = max(sum(s for s, lo, hi in items if lo <= t <= hi) for t in range(330))
+    assert peak <= total <= 1.5 * peak
+
+
+def test_activation_arena_of_a_lowered_network_reuses_dead_buffers():
+    """Lowering records reads/writes per op; plan_buffers places the VV network's activations by liveness:
+    the arena is several times smaller than one-buffer-per-activation, pinned feature taps keep their bytes,
+    and no two simultaneously live buffers overlap."""
+    import torch
+    from oct_segmentation_b200 import synthetic
+    from oct_segmentation_b200.engine.builder import Builder
+    from oct_segmentation_b200.engine.lower import DECODER_LOWERING, ENCODER_LOWERING, lower_head
+    from oct_segmentation_b200.model import OCTSegmentationModel
+    cfg = synthetic.MODEL_CONFIGS['VV']
+    m = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
+                             in_channels=3, classes=cfg['classes'], encoder_weights=None).model
+    b = Builder('cpu', 1)
+    S = 64
+    x = torch.zeros(1, S, S, 3, dtype=torch.uint8).permute(0, 3, 1, 2)
+    feats = ENCODER_LOWERING[m.encoder.kind](b, m.encoder, x, 'u8', None)
+    y = DECODER_LOWERING[m.decoder.kind](b, m.decoder, feats)
+    lower_head(b, m.segmentation_head, y, torch.zeros(1, 1, S, S, dtype=torch.uint8), 'u8_nchw')
+    b.pin(list(feats) + [y])
+    acts, offs, total = b.plan_buffers()
+    assert len(acts) == len(b._acts) and total < 0.4 * b.act_bytes
+    # recompute liveness independently and check the placement
+    first, last = {}, {}
+    for i, op in enumerate(b._records):
+        for a in op.writes:
+            first.setdefault(id(a), i)
+        for a in list(op.reads) + list(op.writes):
+            last[id(a)] = i
+    for a in list(feats) + [y]:
+        last[id(a)] = len(b._records)
+    spans = [(offs[k], offs[k] + a.nbytes, first[id(a)], last[id(a)]) for k, a in enumerate(acts)]
+    for i in range(len(spans)):
+        for j in range(i):
+            a0, a1, alo, ahi = spans[i]
+            b0, b1, blo, bhi = spans[j]
+            if not (ahi < blo or bhi < alo):
+                assert a1 <= b0 or b1 <= a0

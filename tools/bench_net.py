@@ -38,7 +38,7 @@ def main():
     ms = e0.elapsed_time(e1) / reps
     print(json.dumps(dict(net=key, batch=N, size=size, ms_per_batch=round(ms, 3), frames_per_s=round(N / ms * 1e3, 1),
                           tflops_algorithmic=round(2 * net.macs / ms / 1e9, 1), launches=net.launches,
-                          act_GB=round(net.builder.act_bytes / 1e9, 2))), flush=True)
+                          act_GB=round(net.builder.act_bytes / 1e9, 2), arena_GB=round(net.builder.arena_bytes / 1e9, 2))), flush=True)
     # per-op breakdown (eager, one event pair per op)
     b = net.builder
     times = []
