@@ -1,23 +1,27 @@
 #!/usr/bin/env python
 """bench.py — frames/s of the hybrid-ensemble inference hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--config C] [--impl ours|reference]
 
-A step = one pass of the hot path over one batch of B synthetic 512x512 RGB frames per GPU:
-bilinear resize+BGR -> LM (U-Net++/resnet101 @512) + FC_LC (LinkNet/efficientnet-b7 @896) +
-VV (U-Net/regnetx_064 @896) -> threshold -> nearest resize to 1000x1000 + class routing +
-label map + per-class pixel counts (+ radial thickness).  One process per GPU (torchrun for
-N > 1), frames sharded by rank, no data-path collective; one final gather of the per-frame
-counts table.
+A step = one pass of the hot path over one batch of B synthetic RGB frames per GPU.  `--config`:
+  ensemble (default, BASELINE config 4, the workload the metric is quoted on): bilinear resize+BGR -> LM (U-Net++/
+      resnet101 @512) + FC_LC (LinkNet/efficientnet-b7 @896) + VV (U-Net/regnetx_064 @896) -> threshold -> nearest
+      resize to 1000x1000 + class routing + label map + per-class pixel counts + radial thickness; B = 32
+  lm (config 2): the U-Net++ LM network alone, B = 32;   fc_lc (config 3): LinkNet FC_LC + threshold + areas, B = 16
+  ensemble1024 (config 5): all three networks at 1024x1024 on 1024x1024 frames, B = 32
+One process per GPU (torchrun for N > 1), frames sharded by rank, no data-path collective; one final gather of the
+per-frame counts table.
 
-Output: ONE JSON line on rank 0 (contract in the task statement): `value` = device-resident
-throughput, `e2e` = same metric through EnsemblePipeline.stream_host (host frames in,
-host masks/labels/counts out, copies inside the timed region), `roofline` for the dominant
-kernel (conv_tc_kernel, tensor-bound), `cpu_baseline` = the CPU oracle port on host cores.
+Output: ONE JSON line on rank 0 (contract in the task statement): `value` = device-resident throughput, `e2e` = same
+metric through EnsemblePipeline.stream_host (host frames in, host masks/labels/counts out, copies inside the timed
+region), `roofline` for the dominant kernel (conv_tc_kernel, tensor-bound) plus `kernels` (every kernel family: the
+fused MBConv kernel, depthwise, SE, stem pack, maxpool against the tensor and HBM peaks), `per_network` (LM / FC_LC /
+VV: ms per frame, algorithmic TFLOP/s, fraction of peak, activation arena) and `prepost` (HBM fractions of the
+pre/post kernels), `cpu_baseline` = the CPU oracle port on host cores.
 
-`--impl reference` times the reference's own CPU implementation of the path restated in
-oracle/ (the original cannot be installed offline: smp/timm/efficientnet_pytorch/lightning/
-hydra are absent) on all host threads, batch 1 per call as src/predict.py does.
+`--impl reference` times the reference's own CPU implementation of the path restated in oracle/ (the original cannot
+be installed offline: smp/timm/efficientnet_pytorch/lightning/hydra are absent) on all host threads,
+batch 1 per call as src/predict.py does.
 """
 from __future__ import annotations
 
@@ -37,12 +41,29 @@ import torch
 import torch.distributed as dist
 
 CLASSES = ['Lumen', 'Fibrous cap', 'Lipid core', 'Vasa vasorum']
-SRC = 512
-OUT_SIZE = [1000, 1000]
-WORKLOAD = ('hybrid ensemble LM(UnetPlusPlus/resnet101@512)+FC_LC(LinkNet/efficientnet-b7@896)+'
-            'VV(Unet/timm-regnetx_064@896), routing+label map+pixel counts+radial thickness at 1000x1000, '
-            'synthetic 512x512 RGB frames')
 METRIC = 'frames/s, LM+FC_LC+VV ensemble inference'
+
+# BASELINE.json configs[1..4] (configs[0] is the reference's own CPU case = `--impl reference`)
+CONFIGS = {
+    # config 4 (the one the metric is quoted on): full hybrid ensemble, reference-shipped sizes
+    'ensemble': dict(classes=CLASSES, src=512, out=[1000, 1000], input_size=None, batch=32, keys=('LM', 'FC_LC', 'VV'),
+                     workload='hybrid ensemble LM(UnetPlusPlus/resnet101@512)+FC_LC(LinkNet/efficientnet-b7@896)+'
+                              'VV(Unet/timm-regnetx_064@896), routing+label map+pixel counts+radial thickness at 1000x1000, '
+                              'synthetic 512x512 RGB frames'),
+    # config 2: U-Net++ LM single class, batch 32
+    'lm': dict(classes=['Lumen'], src=512, out=[1000, 1000], input_size=None, batch=32, keys=('LM',),
+               workload='LM only: UnetPlusPlus/resnet101@512 single-class, threshold+nearest resize+pixel counts at 1000x1000, '
+                        'synthetic 512x512 RGB frames'),
+    # config 3: LinkNet FC_LC two classes + threshold + per-class area
+    'fc_lc': dict(classes=['Fibrous cap', 'Lipid core'], src=512, out=[1000, 1000], input_size=None, batch=16, keys=('FC_LC',),
+                  workload='FC_LC only: LinkNet/efficientnet-b7@896 two-class, threshold+per-class pixel area at 1000x1000, '
+                           'synthetic 512x512 RGB frames'),
+    # config 5: every model at 1024x1024 (fully convolutional), 1024x1024 sources and outputs, large batch
+    'ensemble1024': dict(classes=CLASSES, src=1024, out=[1024, 1024], input_size=1024, batch=32, keys=('LM', 'FC_LC', 'VV'),
+                         workload='hybrid ensemble with all three models at 1024x1024 (LM UnetPlusPlus/resnet101, FC_LC '
+                                  'LinkNet/efficientnet-b7, VV Unet/timm-regnetx_064), routing+label map+pixel counts+radial '
+                                  'thickness at 1024x1024, synthetic 1024x1024 RGB frames'),
+}
 
 
 def peaks():
@@ -95,23 +116,26 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def cpu_oracle_frames_per_s(n_frames: int, warmup: int):
+def cpu_oracle_frames_per_s(n_frames: int, warmup: int, cfg: dict):
     """The reference path restated in oracle/ (batch 1 per call, FC_LC run once per class exactly like
     src/predict.py:70-100), timed on the host cores.  Returns (frames/s, seconds per frame list)."""
     from oracle import model_ref, synth
     torch.set_num_threads(os.cpu_count() or 1)
     models = {}
-    for key in ('LM', 'FC_LC', 'VV'):
+    for key in cfg['keys']:
         m = synth.make_model(key, calib_size=128, calib_frames=1)
-        models[key] = (m, synth.MODEL_CONFIGS[key])
+        mc = dict(synth.MODEL_CONFIGS[key])
+        if cfg['input_size']:
+            mc['input_size'] = cfg['input_size']
+        models[key] = (m, mc)
     from PIL import Image
     times = []
     for i in range(warmup + n_frames):
-        rgb = synth.synthetic_frame(10_000 + i, SRC)
-        img = Image.fromarray(rgb).resize(tuple(OUT_SIZE))          # data_processing (PIL bicubic)
-        mask = np.zeros((OUT_SIZE[0], OUT_SIZE[1], 4))
+        rgb = synth.synthetic_frame(10_000 + i, cfg['src'])
+        img = Image.fromarray(rgb).resize(tuple(cfg['out']))          # data_processing (PIL bicubic)
+        mask = np.zeros((cfg['out'][1], cfg['out'][0], 4))
         t0 = time.perf_counter()
-        model_ref.segment_with_models([img], [mask], OUT_SIZE, CLASSES, models, 'cpu')
+        model_ref.segment_with_models([img], [mask], cfg['out'], cfg['classes'], models, 'cpu')
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -123,13 +147,15 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    fps, times = cpu_oracle_frames_per_s(args.steps, args.warmup)
+    cfg = CONFIGS[args.config]
+    WORKLOAD = cfg['workload']
+    fps, times = cpu_oracle_frames_per_s(args.steps, args.warmup, cfg)
     ms = 1e3 * float(np.mean(times))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch_per_step': 1, 'note': 'reference-as-written: batch 1 per call, each class '
+        'config': {'workload': WORKLOAD, 'name': args.config, 'batch_per_step': 1, 'note': 'reference-as-written: batch 1 per call, each class '
                    'loops its model (FC_LC runs twice), cv2 pre/post on CPU; runs on rank 0 host cores only'},
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                          'sample': f'{args.steps} frames (1 frame per step) through the oracle restatement of src/predict.py'},
@@ -139,11 +165,105 @@ def reference_arm(args):
     emit(line)
 
 
+def lib_sha16() -> str:
+    import hashlib
+    path = os.path.join(ROOT, 'oct_segmentation_b200', 'liboctseg.so')
+    return hashlib.sha1(open(path, 'rb').read()).hexdigest()[:16] if os.path.exists(path) else ''
+
+
+def kernel_rooflines(pipe, B, peak_tf, peak_hbm):
+    """Per-launch CUDA-event timing of every op of every network (instrumented eager passes after the timed region),
+    aggregated by kernel family and by network.  Algorithmic FLOPs = 2 x dense MACs of the smp graph; algorithmic
+    bytes = activations read + written once + weights."""
+    fam, per_net = {}, {}
+    for d in pipe.model_dirs:
+        net = pipe.nets[d]
+        b = net.builder
+        for _ in range(3):                               # standalone graph replay of this network
+            net.run()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            net.run()
+        g1.record()
+        torch.cuda.synchronize()
+        ms_batch = g0.elapsed_time(g1) / 3
+        flops = 2.0 * net.macs
+        per_net[d] = {'ms_per_frame': ms_batch / B, 'gflop_per_frame': flops / B / 1e9, 'tflops_algorithmic': flops / ms_batch / 1e9,
+                      'frac_of_tensor_peak': flops / ms_batch / 1e9 / peak_tf, 'launches': net.launches,
+                      'arena_gb': net.arena_bytes / 1e9, 'activations_without_reuse_gb': net.act_bytes / 1e9}
+        for rep in range(2):
+            evs = []
+            for op in b.ops:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                op()
+                e.record()
+                evs.append((s, e))
+            torch.cuda.synchronize()
+            for (s, e), name, kind, macs, byt in zip(evs, b.op_names, b.op_kinds, b.op_macs, b.op_bytes):
+                f = fam.setdefault(kind, {'ms': 0.0, 'flops': 0.0, 'bytes': 0.0, 'launches': 0})
+                f['ms'] += s.elapsed_time(e)
+                f['flops'] += 2.0 * (macs or b.op_fused_macs.get(name, 0))
+                f['bytes'] += byt
+                f['launches'] += 1
+    total_ms = sum(f['ms'] for f in fam.values())
+    out = {}
+    for kind, f in fam.items():
+        tf, gbs = f['flops'] / (f['ms'] * 1e-3) / 1e12, f['bytes'] / (f['ms'] * 1e-3) / 1e9
+        out[kind] = {'launches_per_batch': f['launches'] // 2, 'ms_per_batch': f['ms'] / 2, 'share_of_network_time': f['ms'] / total_ms,
+                     'tflops_algorithmic': tf, 'frac_of_tensor_peak': tf / peak_tf, 'gbs_algorithmic': gbs,
+                     'frac_of_hbm_peak': gbs / peak_hbm, 'avg_launch_ms': f['ms'] / max(f['launches'], 1),
+                     'flops_per_launch': f['flops'] / max(f['launches'], 1), 'bytes_per_launch': f['bytes'] / max(f['launches'], 1)}
+    return out, per_net
+
+
+def prepost_rooflines(pipe, frames_dev, B, peak_hbm):
+    """HBM roofline of the pre/post kernels on algorithmic bytes, CUDA events, 5 repetitions."""
+    from oct_segmentation_b200 import prepost as P
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    out = {}
+    Hs, Ws = pipe.src_hw
+    pre_ms, pre_bytes = 0.0, 0.0
+    for d in pipe.model_dirs:
+        S = pipe.sizes[d]
+        net = pipe.nets[d]
+        pre_ms += timed(lambda: P.preprocess(frames_dev, S, out=net.x_nhwc))
+        pre_bytes += B * (3.0 * Hs * Ws + 3.0 * S * S)
+    out['preprocess'] = {'ms_per_batch': pre_ms, 'gbs_algorithmic': pre_bytes / pre_ms / 1e6, 'frac_of_hbm_peak': pre_bytes / pre_ms / 1e6 / peak_hbm}
+    planes = {}
+    from oct_segmentation_b200.pipeline import MODELS_META
+    from oct_segmentation_b200.model import CLASS_IDS
+    in_bytes = 0.0
+    for name in pipe.classes:
+        meta = MODELS_META[name]
+        o = pipe.nets[meta['model_dir']].out
+        planes[CLASS_IDS[name] - 1] = o[:, meta['index']]
+        in_bytes += B * o.shape[2] * o.shape[3]
+    post_ms = timed(lambda: P.postprocess(planes, pipe.order, pipe.Ho, pipe.Wo, B, pipe.device, mask=pipe.mask, label=pipe.label,
+                                          counts=pipe.counts))
+    post_bytes = in_bytes + B * 5.0 * pipe.Ho * pipe.Wo
+    out['postprocess'] = {'ms_per_batch': post_ms, 'gbs_algorithmic': post_bytes / post_ms / 1e6, 'frac_of_hbm_peak': post_bytes / post_ms / 1e6 / peak_hbm}
+    return out
+
+
 def ours_arm(args):
     from oct_segmentation_b200 import synthetic
     from oct_segmentation_b200.parallel import gather_table, shard_range
     from oct_segmentation_b200.pipeline import EnsemblePipeline
 
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -152,10 +272,11 @@ def ours_arm(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    B, K, W = args.batch, args.steps, args.warmup
+    B, K, W = args.batch or cfg['batch'], args.steps, args.warmup
+    SRC, OUT_SIZE = cfg['src'], cfg['out']
 
-    models = synthetic.random_models(dev)
-    pipe = EnsemblePipeline(models, CLASSES, OUT_SIZE, dev, B, src_hw=(SRC, SRC), thickness=True)
+    models = synthetic.random_models(dev, keys=cfg['keys'], input_size=cfg['input_size'])
+    pipe = EnsemblePipeline(models, cfg['classes'], OUT_SIZE, dev, B, src_hw=(SRC, SRC), thickness=True)
 
     # this rank's slice of the global synthetic frame list (weak scaling: B*(K+W) frames per rank)
     total = world * B * (K + W)
@@ -163,7 +284,6 @@ def ours_arm(args):
     n_distinct = min(hi - lo, 4 * B)                                     # 4 distinct batches, cycled
     host = torch.from_numpy(synthetic.synthetic_frames(lo, n_distinct, SRC)).pin_memory()
     dev_batches = [host[i:i + B].to(dev) for i in range(0, n_distinct, B)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
 
     def barrier():
         if world > 1:
@@ -199,7 +319,6 @@ def ours_arm(args):
     for _ in pipe.stream_host((host_np[:B] for _ in range(max(min(W, 3), 2))), copy=False):
         pass
     barrier()
-    t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     starts = [(i % (n_distinct // B)) * B for i in range(K)]
@@ -214,61 +333,50 @@ def ours_arm(args):
     h2d = B * SRC * SRC * 3
     d2h = int(mask.nbytes + label.nbytes + counts.nbytes + radii.nbytes)
 
-    # ---------------------------------------------------------------- roofline of the dominant kernel
-    roof = None
+    # ---------------------------------------------------------------- rooflines (rank 0, after the timed regions)
+    roof = kernels = per_net = prepost = None
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
-        tc_ms, tc_flops, other_ms, n_tc = 0.0, 0.0, 0.0, 0
-        for _ in range(2):                                                # instrumented eager passes (per-launch events)
-            for d in pipe.model_dirs:
-                b = pipe.nets[d].builder
-                evs = []
-                for name, op in zip(b.op_names, b.ops):
-                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    s.record()
-                    op()
-                    e.record()
-                    evs.append((name, s, e))
-                torch.cuda.synchronize()
-                for (name, s, e), plan_macs in zip(evs, b.op_macs):
-                    if plan_macs is not None:
-                        tc_ms += s.elapsed_time(e)
-                        tc_flops += 2.0 * plan_macs
-                        n_tc += 1
-                    else:
-                        other_ms += s.elapsed_time(e)
-        achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+        kernels, per_net = kernel_rooflines(pipe, B, peak_tf, peak_hbm)
+        prepost = prepost_rooflines(pipe, dev_batches[0], B, peak_hbm)
+        tc = kernels['conv_tc']
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, 'profiles', 'launches_r1_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'launches_r2_traffic.json')
         if os.path.exists(tpath):                       # dram__bytes_read+write per conv_tc_kernel launch (ncu pass)
             tj = json.load(open(tpath))
-            if tj.get('batch', 16) == B:
-                traffic, traffic_src = tj['dram_bytes_per_launch'], 'profiles/launches_r1_traffic.json'
-        roof = {'bound': 'tensor', 'kernel': 'conv_tc_kernel', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
-                'algorithmic_flops_per_launch': tc_flops / max(n_tc, 1),
-                'launches_measured': n_tc, 'avg_launch_ms': tc_ms / max(n_tc, 1),
-                'share_of_network_time': tc_ms / (tc_ms + other_ms),
+            if tj.get('batch') == B and tj.get('config', 'ensemble') == args.config and tj.get('lib_sha16') == lib_sha16():
+                traffic, traffic_src = tj['dram_bytes_per_launch'], 'profiles/launches_r2_traffic.json'
+            else:
+                traffic_src = 'profiles/launches_r2_traffic.json is from another build/config/batch: not used'
+        roof = {'bound': 'tensor', 'kernel': 'conv_tc_kernel', 'achieved': tc['tflops_algorithmic'], 'peak': peak_tf,
+                'unit': 'TFLOP/s', 'frac': tc['frac_of_tensor_peak'], 'traffic': traffic, 'traffic_source': traffic_src,
+                'peak_source': peak_src, 'algorithmic_flops_per_launch': tc['flops_per_launch'],
+                'launches_measured': 2 * tc['launches_per_batch'], 'avg_launch_ms': tc['avg_launch_ms'],
+                'share_of_network_time': tc['share_of_network_time'],
                 'how': 'algorithmic FLOPs (2 x dense MACs of the smp graph, DESIGN.md) of every conv_tc_kernel launch in one '
-                       'ensemble batch divided by the sum of their CUDA-event durations (eager pass after the timed region)'}
+                       'batch divided by the sum of their CUDA-event durations (eager pass after the timed region); the other '
+                       'kernel families and the per-network figures are under "kernels" / "per_network" / "prepost"'}
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': t_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'batch_per_gpu_per_step': B, 'frames_total': world * B * K,
+            'config': {'workload': cfg['workload'], 'name': args.config, 'batch_per_gpu_per_step': B, 'frames_total': world * B * K,
                        'weights': 'seeded random init of the shipped architectures',
-                       'l2': 'inputs cycle over 4 distinct batches; per-step activations (>10 GB) exceed the 126 MB L2',
+                       'l2': 'inputs cycle over 4 distinct batches; per-step activations (several GB) exceed the 126 MB L2',
                        'parallelism': f'frame-sharded x{world}, final all_gather of the counts table'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': int(pipe.launches_per_batch * K),
             'roofline': roof,
+            'kernels': kernels,
+            'per_network': per_net,
+            'prepost': prepost,
             'gflop_per_frame_algorithmic': 2 * pipe.macs_per_frame / 1e9,
         }
         if not args.no_cpu_baseline and world == 1:
-            fps, times = cpu_oracle_frames_per_s(args.cpu_frames, 1)
+            fps, times = cpu_oracle_frames_per_s(args.cpu_frames, 1, cfg)
             line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
                                     'sample': f'{args.cpu_frames} frames through the oracle restatement of src/predict.py '
                                               f'(batch 1 per call, FC_LC run per class, cv2 pre/post), {sum(times):.1f} s'}
@@ -303,7 +411,9 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--batch', type=int, default=0, help='frames per GPU per step (0 = the config default)')
+    ap.add_argument('--config', default='ensemble', choices=sorted(CONFIGS),
+                    help='ensemble = BASELINE config 4 (the metric); lm / fc_lc / ensemble1024 = configs 2 / 3 / 5')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-frames', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -20,12 +20,12 @@
 #include <cstdint>
 
 #include "common.h"
+#include "dw_core.h"
 #include "ptx_sm100.h"
 
 namespace octseg {
 
 constexpr int kDwThreads = 256;
-constexpr int kDwR = 2, kDwP = 4;  // output rows x pixels per thread
 
 struct DwParams {
   const __nv_bfloat16* weight;  // [K*K][C]
@@ -42,24 +42,6 @@ struct DwParams {
   FastDiv fd_chunk_tiles, fd_tw, fd_cb, fd_rg;  // local index -> chunk; in-chunk index -> (row, tw); chunk -> (cb, row group, n)
   int chunk_rows;
 };
-
-// bf16 pair -> fp32 pair on the ALU pipe only (PRMT + LOP3): the compiler would turn `w << 16` into
-// IMAD.U32, which competes with the FFMA2s for the FMA pipe this kernel is bound by
-__device__ __forceinline__ float2 dw_bf16x2_to_f32x2(uint32_t w) {
-  uint32_t lo;
-  asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(w));
-  return make_float2(__uint_as_float(lo), __uint_as_float(w & 0xffff0000u));
-}
-__device__ __forceinline__ uint32_t dw_cvt_bf16x2(float2 x) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x.y), "f"(x.x));
-  return d;
-}
-__device__ __forceinline__ float dw_tanh(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <int K, int S, int CB, int SH, int SW>
 struct DwCfg {
@@ -81,7 +63,6 @@ __global__ void __launch_bounds__(kDwThreads, DwCfg<K, S, CB, SH, SW>::CTAS)
     dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const DwParams p) {
   using Cfg = DwCfg<K, S, CB, SH, SW>;
   constexpr int R = kDwR, P = kDwP, LANES = Cfg::LANES, IW = Cfg::IW, PIX = Cfg::PIX, NST = Cfg::NST;
-  constexpr int RH = (R - 1) * S + K, RW = (P - 1) * S + K;  // a thread's input window
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
@@ -197,72 +178,9 @@ __global__ void __launch_bounds__(kDwThreads, DwCfg<K, S, CB, SH, SW>::CTAS)
     const uint32_t base = s_stage + stage * Cfg::STAGE + in_off;
 
     float2 acc[R][P][2];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int q = 0; q < P; ++q) {
-        acc[r][q][0] = bias2[0];
-        acc[r][q][1] = bias2[1];
-      }
-#pragma unroll
-    for (int iy = 0; iy < RH; ++iy) {
-      float2 w[R][K][2];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int ky = iy - r * S;
-        if (ky >= 0 && ky < K) {
-#pragma unroll
-          for (int kx = 0; kx < K; ++kx) {
-            float4 ww;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(ww.x), "=f"(ww.y), "=f"(ww.z), "=f"(ww.w)
-                         : "r"(w_off + static_cast<uint32_t>((ky * K + kx) * CB * 4)));
-            w[r][kx][0] = make_float2(ww.x, ww.y);
-            w[r][kx][1] = make_float2(ww.z, ww.w);
-          }
-        }
-      }
-#pragma unroll
-      for (int dx = 0; dx < RW; ++dx) {
-        uint32_t r0, r1;
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
-                     : "=r"(r0), "=r"(r1)
-                     : "r"(base + static_cast<uint32_t>((iy * IW + dx) * PIX)));
-        const float2 f0 = dw_bf16x2_to_f32x2(r0), f1 = dw_bf16x2_to_f32x2(r1);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int ky = iy - r * S;
-          if (ky >= 0 && ky < K) {
-#pragma unroll
-            for (int q = 0; q < P; ++q) {
-              const int kx = dx - q * S;
-              if (kx >= 0 && kx < K) {
-                acc[r][q][0] = __ffma2_rn(f0, w[r][kx][0], acc[r][q][0]);
-                acc[r][q][1] = __ffma2_rn(f1, w[r][kx][1], acc[r][q][1]);
-              }
-            }
-          }
-        }
-      }
-    }
+    dw_patch<K, S, CB, IW, PIX>(base, w_off, bias2, p.act, acc);
 
-    // epilogue: activation, bf16 store (8 bytes per pixel per thread; 16 lanes = one pixel's 128 bytes), SE sums
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-#pragma unroll
-      for (int q = 0; q < P; ++q) {
-        float2 y0 = acc[r][q][0], y1 = acc[r][q][1];
-        if (p.act == OCTSEG_ACT_SWISH) {  // the accumulators hold h = x/2 (see wscale)
-          y0 = __ffma2_rn(y0, make_float2(dw_tanh(y0.x), dw_tanh(y0.y)), y0);
-          y1 = __ffma2_rn(y1, make_float2(dw_tanh(y1.x), dw_tanh(y1.y)), y1);
-        } else if (p.act == OCTSEG_ACT_RELU) {
-          y0 = make_float2(fmaxf(y0.x, 0.f), fmaxf(y0.y, 0.f));
-          y1 = make_float2(fmaxf(y1.x, 0.f), fmaxf(y1.y, 0.f));
-        }
-        acc[r][q][0] = y0;
-        acc[r][q][1] = y1;
-      }
-    }
+    // bf16 store (8 bytes per pixel per thread; 16 lanes = one pixel's 128 bytes), SE sums
     const int oy0 = th * Cfg::TH + sy * R, ox0 = tw * Cfg::TW + sx * P;
     uint8_t* o0 = reinterpret_cast<uint8_t*>(p.out) +
                   static_cast<size_t>((n * p.Ho + oy0) * p.Wo + ox0) * pix_bytes + (cb * CB + lane_c * 4) * 2;

@@ -92,6 +92,9 @@ class Builder:
         self.ops: List[Callable[[], None]] = []
         self.op_names: List[str] = []
         self.op_macs: List[Optional[int]] = []   # algorithmic MACs of tensor-core launches, None otherwise
+        self.op_bytes: List[int] = []            # algorithmic HBM bytes per op: activations read + written once, + weights
+        self.op_kinds: List[str] = []            # kernel family per op: conv_tc | mbconv | dwconv | se | pack | maxpool
+        self.op_fused_macs = {}                  # op name -> dense expand-conv MACs done inside the fused MBConv kernel
         self.macs = 0              # algorithmic MACs of the reference graph (dense count)
         self.tc_launches = 0
         self.launches = 0
@@ -122,11 +125,14 @@ class Builder:
         self._pinned += list(acts)
 
     def _add(self, name: str, make: Callable[[], Callable[[], None]], reads: Sequence[Act] = (),
-             writes: Sequence[Act] = (), tc_macs: Optional[int] = None, launches: int = 1) -> None:
+             writes: Sequence[Act] = (), tc_macs: Optional[int] = None, launches: int = 1, extra_bytes: int = 0,
+             kind: str = '') -> None:
         assert not self._final, 'builder already finalized'
+        self.op_kinds.append(kind or ('conv_tc' if tc_macs is not None else 'other'))
         self._records.append(_Op(name, make, [a for a in reads if a is not None], list(writes), tc_macs))
         self.op_names.append(name)
         self.op_macs.append(tc_macs)
+        self.op_bytes.append(sum(a.nbytes for a in list(reads) + list(writes) if a is not None) + int(extra_bytes))
         self.launches += launches
 
     def plan_buffers(self) -> Tuple[List[Act], List[int], int]:
@@ -173,14 +179,15 @@ class Builder:
             op()
 
     # ------------------------------------------------------------------ tensor-core conv
-    def _add_conv(self, name: str, geom, make_plan: Callable[[], ConvPlan], reads, writes) -> None:
+    def _add_conv(self, name: str, geom, make_plan: Callable[[], ConvPlan], reads, writes, extra_bytes: int = 0) -> None:
         def make():
             plan = make_plan()
             self._keep.append(plan)
             return plan.run
         self.macs += geom.macs
         self.tc_launches += 1
-        self._add(name, make, reads, writes, tc_macs=geom.macs)
+        wbytes = geom.phases * geom.n_tiles_n * geom.BN * geom.Ktot * 2
+        self._add(name, make, reads, writes, tc_macs=geom.macs, extra_bytes=extra_bytes + wbytes)
 
     def conv(self, srcs: Sequence[Tuple[Act, bool]], w: torch.Tensor, b: Optional[torch.Tensor], *, name: str,
              stride: int = 1, pad: Tuple[int, int] = (0, 0), groups: int = 1, transposed: bool = False,
@@ -218,7 +225,8 @@ class Builder:
                                     res_mode=res_mode, name=name)
                 return ConvPlan(geom, packed, bias_rows, views, out_tensor, out_mode=out_mode, act=act, name=name,
                                 out_pack=f, out_ldc=cout)
-            self._add_conv(name, geom, make_plan, reads, [out_act] if out_act is not None else [])
+            self._add_conv(name, geom, make_plan, reads, [out_act] if out_act is not None else [],
+                           extra_bytes=0 if bf16_out else out_tensor.numel() * out_tensor.element_size())
             return out_act
 
         # narrow decoder conv over cat([up(x), skips...]): the half-resolution tile grid of the fused form
@@ -263,7 +271,8 @@ class Builder:
             return ConvPlan(geom, packed, bias_rows, [a.t for a, _ in srcs], out_act.t if bf16_out else out_tensor,
                             out_mode=out_mode, act=act, res=res.t if res is not None else None, res_mode=res_mode,
                             name=name)
-        self._add_conv(name, geom, make_plan, reads, [out_act] if out_act is not None else [])
+        self._add_conv(name, geom, make_plan, reads, [out_act] if out_act is not None else [],
+                       extra_bytes=0 if bf16_out else out_tensor.numel() * out_tensor.element_size())
         return out_act
 
     # ------------------------------------------------------------------ CUDA-core kernels
@@ -288,7 +297,7 @@ class Builder:
         def pack_op():
             _lib.check(lib.octseg_stem_pack(x.data_ptr(), dt, sn, sc, sh, sw, N, H, W, mean_a, istd_a,
                                             x2.t.data_ptr(), _lib.stream_ptr()), name + '.pack')
-        self._add(name + '.pack', lambda: pack_op, [], [x2])
+        self._add(name + '.pack', lambda: pack_op, [], [x2], kind='pack', extra_bytes=N * H * W * 3 * (1 if in_dtype == 'u8' else 4))
         w2, q0 = stem_s2d_weights(w, k, pad)
         assert q0[0] <= 0 and q0[1] <= 0
         out = self.conv([(x2, False)], w2, b, name=name, pad=(-q0[0], -q0[1]), out_hw=out_hw, act=act)
@@ -306,7 +315,7 @@ class Builder:
         def op():
             _lib.check(lib.octseg_maxpool3x3s2(x.t.data_ptr(), out.t.data_ptr(), x.N, x.H, x.W, x.Cp, Ho, Wo,
                                                _lib.stream_ptr()), name)
-        self._add(name, lambda: op, [x], [out])
+        self._add(name, lambda: op, [x], [out], kind='maxpool')
         return out
 
     def dwconv(self, x: Act, w: torch.Tensor, b: torch.Tensor, *, name: str, k: int, stride: int,
@@ -323,7 +332,37 @@ class Builder:
                                          x.W, x.C, k, stride, pad[0], pad[1], out_hw[0], out_hw[1], a,
                                          pool.data_ptr() if pool is not None else None, _lib.stream_ptr()), name)
         self.macs += x.N * out_hw[0] * out_hw[1] * x.C * k * k
-        self._add(name, lambda: op, [x], [out])
+        self._add(name, lambda: op, [x], [out], kind='dwconv')
+        return out
+
+    def mbconv_fits(self, cin: int, k: int, stride: int) -> bool:
+        """Can the fused expand + depthwise kernel take this block (shared-memory budget, supported shape)?"""
+        b = self.lib.octseg_mbconv_smem_bytes(cin, k, stride)
+        return 0 < b <= 227 * 1024
+
+    def mbconv_expand_dw(self, x: Act, we: torch.Tensor, be: torch.Tensor, wd: torch.Tensor, bd: torch.Tensor, *,
+                         name: str, k: int, stride: int, pad: Tuple[int, int], out_hw: Tuple[int, int],
+                         pool: Optional[torch.Tensor]) -> Act:
+        """Expand 1x1 (+swish) -> depthwise k x k (+swish) -> SE sums in one launch (csrc/mbconv.cu); the
+        expanded tensor is never written.  we: folded [Cmid, Cin, 1, 1]; wd: folded [Cmid, 1, k, k]."""
+        cmid, cin = we.shape[0], we.shape[1]
+        assert x.C == cin and cin % 16 == 0 and cmid % 8 == 0 and stride == 1
+        out = self.new_act(out_hw[0], out_hw[1], cmid)
+        dev = self.device
+        wek = we.detach().float().reshape(cmid, cin).contiguous().to(torch.bfloat16).to(dev)          # [Cmid][Cin]
+        wdk = wd.detach().float().reshape(cmid, k, k).permute(1, 2, 0).contiguous().to(torch.bfloat16)   # [kh][kw][Cmid], bf16 like octseg_dwconv
+        blob = _lib.mbconv_blob(be, wdk, bd, k).to(dev)
+        self._keep += [wek, blob]
+        lib = self.lib
+
+        def op():   # `pool` starts zeroed (lower.py) and is re-zeroed by octseg_se_gate after each use
+            _lib.check(lib.octseg_mbconv_expand_dw(x.t.data_ptr(), x.N, x.H, x.W, cin, x.Cp, wek.data_ptr(), blob.data_ptr(),
+                                                   out.t.data_ptr(), cmid, k, stride, pad[0], pad[1], out_hw[0], out_hw[1],
+                                                   pool.data_ptr() if pool is not None else None, _lib.stream_ptr()), name)
+        exp_macs = x.N * x.H * x.W * cin * cmid
+        self.macs += exp_macs + x.N * out_hw[0] * out_hw[1] * cmid * k * k
+        self._add(name, lambda: op, [x], [out], kind='mbconv', extra_bytes=wek.numel() * 2 + blob.numel() * 4)
+        self.op_fused_macs[name] = exp_macs          # tensor-core MACs executed inside a non-conv_tc kernel
         return out
 
     def se_project(self, x: Act, pool: torch.Tensor, w1, b1, w2, b2, wp: torch.Tensor, bp: torch.Tensor, *,
@@ -358,7 +397,7 @@ class Builder:
             _lib.check(lib.octseg_se_scale_weights(gate.data_ptr(), base.data_ptr(), wn.t.data_ptr(), N, rows, Ktot,
                                                    C_mid, st), name + '.se_scale_weights')
         self.macs += N * 2 * C_mid * cr
-        self._add(name + '.se', lambda: gate_op, [], [wn], launches=3)
+        self._add(name + '.se', lambda: gate_op, [], [wn], launches=3, kind='se')
         self._add_conv(name, geom, lambda: ConvPlan(geom, wn.t, bias_rows, [x.t], out.t, act='none',
                                                     res=res.t if res is not None else None,
                                                     res_mode='before_act' if res is not None else 'none',

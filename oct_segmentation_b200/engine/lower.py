@@ -18,6 +18,12 @@ import torch
 from .builder import Builder, fold_bn
 from .conv import Act
 
+# Fused expand 1x1 + depthwise + SE sums (csrc/mbconv.cu) for the stride-1 MBConv blocks it fits.  It removes the
+# expanded tensor's HBM round trip (stage 2: 1.03 GB per launch instead of 2.9 GB for the pair it replaces) but on
+# B200 the pair is bound by CUDA-core issue / MUFU, not by HBM, and the fused kernel measured 7-50 % SLOWER than
+# the two launches (profiles/mbconv_fused_r2.md), so it is opt-in.  Set of stage input widths to fuse, or () for none.
+FUSE_MBCONV = ()
+
 
 # ----------------------------------------------------------------------------------- encoders
 def lower_resnet(b: Builder, enc, x: torch.Tensor, in_dtype: str, norm) -> List[Act]:
@@ -86,16 +92,23 @@ def lower_efficientnet(b: Builder, enc, x: torch.Tensor, in_dtype: str, norm) ->
         nm = f'encoder._blocks.{i}'
         inp = cur
         y = cur
-        if blk.expand != 1:
-            we, be = fold_bn(blk._expand_conv.weight, blk._bn0)
-            y = b.conv([(y, False)], we, be, name=nm + '._expand_conv', act='swish')
         wd, bd = fold_bn(blk._depthwise_conv.weight, blk._bn1)
         pt, pb = blk._depthwise_conv.pad
+        cmid = blk._depthwise_conv.weight.shape[0]
         oh = (y.H + pt + pb - blk.k) // blk.stride + 1
         ow = (y.W + pt + pb - blk.k) // blk.stride + 1
-        pool = torch.zeros(b.N, y.C, dtype=torch.float32, device=b.device)
-        y = b.dwconv(y, wd, bd, name=nm + '._depthwise_conv', k=blk.k, stride=blk.stride, pad=(pt, pt),
-                     out_hw=(oh, ow), act='swish', pool=pool)
+        pool = torch.zeros(b.N, cmid, dtype=torch.float32, device=b.device)
+        if blk.expand != 1 and cur.C in FUSE_MBCONV and blk.stride == 1 and cur.C % 16 == 0 and b.mbconv_fits(cur.C, blk.k, blk.stride):
+            # expand 1x1 -> depthwise in one launch: the 6x-wide tensor stays on chip (csrc/mbconv.cu)
+            we, be = fold_bn(blk._expand_conv.weight, blk._bn0)
+            y = b.mbconv_expand_dw(y, we, be, wd, bd, name=nm + '._depthwise_conv', k=blk.k, stride=blk.stride,
+                                   pad=(pt, pt), out_hw=(oh, ow), pool=pool)
+        else:
+            if blk.expand != 1:
+                we, be = fold_bn(blk._expand_conv.weight, blk._bn0)
+                y = b.conv([(y, False)], we, be, name=nm + '._expand_conv', act='swish')
+            y = b.dwconv(y, wd, bd, name=nm + '._depthwise_conv', k=blk.k, stride=blk.stride, pad=(pt, pt),
+                         out_hw=(oh, ow), act='swish', pool=pool)
         wp, bp = fold_bn(blk._project_conv.weight, blk._bn2)
         skip = inp if (blk.stride == 1 and blk.cin == blk.cout) else None
         cur = b.se_project(y, pool, blk._se_reduce.weight, blk._se_reduce.bias, blk._se_expand.weight,
