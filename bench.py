@@ -385,6 +385,92 @@ def ours_arm(args):
         dist.destroy_process_group()
 
 
+def files_arm(args):
+    """frames/s of the WHOLE entry point on files -- N synthetic PNGs on disk -> predict.main with
+    stream_chunk (decode + bicubic resize on host threads, GPU pipeline, overlay kernel, PNG encode of mask + overlay on
+    host threads, all overlapped) -> 2 PNGs per frame + quantities.json.  Each stage is also timed alone on the same
+    files, so the line shows what the overlap hides; the reference's own flow (oracle restatement of src/predict.py:
+    PIL decode, CPU networks, cv2 morphology, PNG encode, single thread of control) is timed on a small sample."""
+    import shutil
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    from PIL import Image
+    from oct_segmentation_b200 import config as cfgmod, predict as P, synthetic
+    n, chunk, B = args.e2e_files, args.stream_chunk, args.batch or 32
+    root = tempfile.mkdtemp(prefix='octseg_files_')
+    src, dst, mdir = os.path.join(root, 'in'), os.path.join(root, 'out'), os.path.join(root, 'models')
+    os.makedirs(src)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(8) as io:
+        list(io.map(lambda i: Image.fromarray(synthetic.synthetic_frame(30_000 + i, 512)).save(os.path.join(src, f'f{i:05d}.png')), range(n)))
+    gen_s = time.perf_counter() - t0
+    dev = torch.device('cuda:0')
+    models = synthetic.random_models(dev)
+    out_size = [1000, 1000]
+    workers = int(args.io_workers)
+    cfg = cfgmod.Config({'data_dir': src, 'models_dir': mdir, 'save_dir': dst, 'output_size': out_size, 'device': 'cuda',
+                         'classes': CLASSES, 'batch_size': B, 'stream_chunk': chunk, 'io_workers': workers, 'quantities': False})
+    orig_load = P.load_models
+    P.load_models = lambda *a, **k: models                     # seeded random-init checkpoints (no trained weights offline)
+    try:
+        P.main(cfgmod.Config(dict(cfg, data_dir=src, save_dir=os.path.join(root, 'warm'), stream_chunk=chunk)))   # warm-up: compile + graphs
+        shutil.rmtree(os.path.join(root, 'warm'), ignore_errors=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        P.main(cfg)
+        torch.cuda.synchronize()
+        total_s = time.perf_counter() - t0
+    finally:
+        P.load_models = orig_load
+    n_png = len([f for f in os.listdir(dst) if f.endswith('.png')])
+    # the three stages alone, on the same files
+    paths = P.list_images(src)
+    with ThreadPoolExecutor(workers) as io:
+        t0 = time.perf_counter()
+        images, masks, names = P.open_images(paths[:min(n, 4 * chunk)], out_size, pool=io)
+        decode_s = (time.perf_counter() - t0) * n / len(images)
+        pipe = P.make_pipeline(models, CLASSES, out_size, B, (out_size[1], out_size[0]), False)
+        P.segment(images, masks, out_size, CLASSES, '', 'cuda', batch_size=B, models=models, pipe=pipe)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        P.segment(images, masks, out_size, CLASSES, '', 'cuda', batch_size=B, models=models, pipe=pipe)
+        torch.cuda.synchronize()
+        gpu_s = (time.perf_counter() - t0) * n / len(images)
+        os.makedirs(os.path.join(root, 'enc'), exist_ok=True)
+        t0 = time.perf_counter()
+        P.save_results(images, masks, names, CLASSES, os.path.join(root, 'enc'), B, 'cuda', io)
+        encode_s = (time.perf_counter() - t0) * n / len(images)
+    # the reference flow (CPU oracle restatement), a small sample
+    ref_fps = None
+    if not args.no_cpu_baseline:
+        from oracle import model_ref, prepost_ref, synth
+        torch.set_num_threads(os.cpu_count() or 1)
+        rm = {k: (synth.make_model(k, calib_size=128, calib_frames=1), synth.MODEL_CONFIGS[k]) for k in ('LM', 'FC_LC', 'VV')}
+        k = max(1, args.cpu_frames)
+        t0 = time.perf_counter()
+        imgs = [Image.open(q_).resize(tuple(out_size)) for q_ in paths[:k]]
+        mks = [np.zeros((out_size[1], out_size[0], 4)) for _ in imgs]
+        model_ref.segment_with_models(imgs, mks, out_size, CLASSES, rm, 'cpu')
+        os.makedirs(os.path.join(root, 'ref'), exist_ok=True)
+        for im, mk, nm in zip(imgs, mks, names):
+            Image.fromarray(prepost_ref.overlay(np.asarray(im), (mk != 0).astype(np.uint8), CLASSES)).save(os.path.join(root, 'ref', nm + '_overlay.png'))
+            Image.fromarray(prepost_ref.color_mask(mk, CLASSES)).save(os.path.join(root, 'ref', nm + '_mask.png'))
+        ref_fps = k / (time.perf_counter() - t0)
+    shutil.rmtree(root, ignore_errors=True)
+    slowest = max(decode_s, gpu_s, encode_s)
+    emit({'metric': 'frames/s, PNG files in -> segmentation -> mask + overlay PNGs out (src/predict.py main, stream_chunk)',
+          'value': n / total_s, 'unit': 'frames/s', 'n_gpus': 1, 'frames': n, 'seconds': total_s, 'higher_is_better': True,
+          'config': {'workload': CONFIGS['ensemble']['workload'], 'files': f'{n} synthetic 512x512 PNGs', 'stream_chunk': chunk,
+                     'batch_size': B, 'io_workers': workers, 'host_cores': os.cpu_count(), 'pngs_written': n_png},
+          'stages_alone_s': {'decode+bicubic (host threads)': decode_s, 'gpu pipeline incl. copies': gpu_s,
+                             'overlay kernel + PNG encode (host threads)': encode_s, 'frame generation (not timed)': gen_s},
+          'overlap': {'sum_of_stages_s': decode_s + gpu_s + encode_s, 'slowest_stage_s': slowest,
+                      'total_over_slowest': total_s / slowest},
+          'cpu_baseline': None if ref_fps is None else {'value': ref_fps, 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                                        'sample': f'{max(1, args.cpu_frames)} files through the oracle restatement of the whole src/predict.py flow'},
+          'data': 'synthetic'})
+
+
 _RESULT_FD = None
 
 
@@ -415,11 +501,16 @@ def main():
     ap.add_argument('--config', default='ensemble', choices=sorted(CONFIGS),
                     help='ensemble = BASELINE config 4 (the metric); lm / fc_lc / ensemble1024 = configs 2 / 3 / 5')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--e2e-files', type=int, default=0, help='file-to-file mode: N synthetic PNGs -> predict.main(stream_chunk) -> PNGs')
+    ap.add_argument('--stream-chunk', type=int, default=64)
+    ap.add_argument('--io-workers', type=int, default=os.cpu_count() or 8)
     ap.add_argument('--cpu-frames', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     _claim_stdout()
-    if args.impl == 'reference':
+    if args.e2e_files > 0:
+        files_arm(args)
+    elif args.impl == 'reference':
         reference_arm(args)
     else:
         ours_arm(args)

@@ -69,6 +69,7 @@ struct __align__(64) ConvKParams {
   int bias_floats;    // n_tiles_n * BN + 64 bias values staged in shared memory (rounded up to 4)
   int b_stage_bytes;  // bytes of one B stage (kw weight tiles for wide segments)
   int a_stage_bytes;  // kABytes, kABytesWide, or the halo tile (rounded up to 1 KB) in halo mode
+  int own_spatial;    // 1: a CTA takes whole spatial tiles (all their channel tiles, back to back) -- see tile_at()
   int n_acc;          // accumulators in the TMEM ring (2 for BN = 256 ... 8 for BN <= 64)
   int halo;           // halo-tile mode: TH=16, TW=8, one halo box per channel chunk, resident weights
   int b_res_bytes;    // halo mode: bytes of one channel tile's weights (kh*kw*cchunks tiles of BN x 64)
@@ -235,8 +236,15 @@ constexpr int kTraceTiles = 256, kTraceEvents = 16;
 __device__ unsigned long long g_trace[kTraceEvents][kTraceTiles];
 #define OCTSEG_STAMP(ev, it) \
   do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it) < kTraceTiles) g_trace[ev][it] = clock64(); } while (0)
+// per-chunk phases of epilogue group 0's first warp: 0 start, 1 TMEM loaded, 2 math done, 3 staging buffer free,
+// 4 past barrier 1, 5 tile written + fenced + barrier 2, 6 store issued
+__device__ unsigned long long g_trace_chunk[8][kTraceTiles];
+__device__ int g_trace_chunk_n;
+#define OCTSEG_CSTAMP(ev, k) \
+  do { if (blockIdx.x == 0 && threadIdx.x == 64 && (k) < kTraceTiles) g_trace_chunk[ev][k] = clock64(); } while (0)
 #else
 #define OCTSEG_STAMP(ev, it) do { } while (0)
+#define OCTSEG_CSTAMP(ev, k) do { } while (0)
 #endif
 
 struct TileCoord {
@@ -275,6 +283,18 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   c.ph = c.phase >> 1;
   c.pw = c.phase & 1;
   return c;
+}
+
+// i-th tile of this CTA.  Default: tiles blockIdx, blockIdx + grid, ... (channel tile fastest, so CTAs running
+// together share the A tile in L2).  With several channel tiles of UNEQUAL width per spatial tile that deal gives
+// every CTA the same channel tile each time whenever grid % n_tiles_n == 0 (148 CTAs, 2 or 4 channel tiles): the
+// CTAs holding the wide tile set the pace (288 channels = 192 + 96: 25 % lost).  own_spatial deals whole spatial
+// tiles instead; the CTA runs their channel tiles back to back (its second A load is an L2 hit).
+__device__ __forceinline__ int tile_at(const ConvKParams& p, int i) {
+  if (!p.own_spatial) return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+  const uint32_t q = fd_div(static_cast<uint32_t>(i), p.fd_ntn);
+  const int r = i - static_cast<int>(q) * p.n_tiles_n;
+  return (static_cast<int>(blockIdx.x) + static_cast<int>(q) * static_cast<int>(gridDim.x)) * p.n_tiles_n + r;
 }
 
 template <int ACT, int RES>
@@ -353,8 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t s_asub = 128u * s_kc * 2u, s_bsub = static_cast<uint32_t>(p.BN) * s_kc * 2u;
       const uint32_t s_tx = static_cast<uint32_t>(p.TH * p.TW + p.BN) * s_kc * 2u;
       const CUtensorMap* s_mb = &p.tmB[kc_index(s_kc)];
-      [[maybe_unused]] int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int it = 0, tile; (tile = tile_at(p, it)) < p.total_tiles; ++it) {
         OCTSEG_STAMP(0, it);  // producer starts issuing this tile
         const TileCoord tc = decode_tile(p, tile);
         const int brow = tc.n_tile * p.BN;
@@ -510,8 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int s_kc = p.seg[0].kc, s_cch = p.seg[0].cchunks, s_subs = 64 / s_kc, s_steps = s_kc / 16;
       const uint32_t s_asub = 128u * s_kc * 2u, s_bsub = static_cast<uint32_t>(p.BN) * s_kc * 2u;
       const uint64_t s_desc = make_kmajor_desc(0, s_kc);
-      [[maybe_unused]] int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int it = 0, tile; (tile = tile_at(p, it)) < p.total_tiles; ++it) {
         OCTSEG_STAMP(1, it);  // MMA warp ready for this tile
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
@@ -670,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t sts_x = static_cast<uint32_t>(((half * 4) ^ (row & 7)) << 4);
     int acc = 0;
     uint32_t acc_phase = 0, chunk_ctr = 0;
-    [[maybe_unused]] int it = 0;
+    int it = 0;
     [[maybe_unused]] const bool tracer = (threadIdx.x == 64) || (threadIdx.x == 64 + 256);  // first thread of each group
     [[maybe_unused]] const int tev = 4 + 3 * group;
     // With one channel tile the chunk layout is the same for every tile, so a group knows from the chunk
@@ -684,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool rot = p.n_tiles_n == 1 && n_tma1 == 0 && nvalid1 <= 2 * kEpiPart;
     const int rot_np = nvalid1 <= kEpiPart ? 1 : 2, rot_sets = kEpiSplit / rot_np;
     const int rot_set = part / rot_np, rot_slice = part - rot_set * rot_np;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile; (tile = tile_at(p, it)) < p.total_tiles; ++it) {
       if (tracer) OCTSEG_STAMP(tev, it);  // epilogue group ready for this tile
       if ((can_skip && static_cast<int>((group ^ chunk_ctr) & 1u) >= n_tma1) || (rot && (it % rot_sets) != rot_set)) {
         mbar_wait(bar_tfull + 8 * acc, acc_phase);  // stay within the ring: arrivals must land in this tile's phase
@@ -727,8 +745,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (((chunk_ctr + ck) & 1) != static_cast<uint32_t>(group)) continue;  // warp-uniform
         const int cp = ck * 64 + half * 32;
         uint32_t v[32];
+        [[maybe_unused]] const int ckey = static_cast<int>((chunk_ctr + ck) >> 1);
+        OCTSEG_CSTAMP(0, ckey);
         tmem_ld32(taddr + cp, v);
         tmem_ld_wait();
+        OCTSEG_CSTAMP(1, ckey);
         uint4 ov[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -736,8 +757,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const __nv_bfloat16* r8 = (RES != OCTSEG_RES_NONE && rrow && cc < nvalid) ? rrow + cc : nullptr;
           ov[g] = epi8<ACT, RES>(v + 8 * g, bias + cc, r8);
         }
+        OCTSEG_CSTAMP(2, ckey);
         if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store left the buffer
+        OCTSEG_CSTAMP(3, ckey);
         group_bar_sync(group);
+        OCTSEG_CSTAMP(4, ckey);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sts_row + (sts_x ^ (g << 4))), "r"(ov[g].x), "r"(ov[g].y),
@@ -745,6 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                        : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         group_bar_sync(group);
+        OCTSEG_CSTAMP(5, ckey);
         if (gtid == 0) {
           const int cch = p.out_c_off + ch0 + ck * 64;
           if (p.out_grouped)
@@ -755,6 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_store_4d(&p.tmOut, sbuf, cch, tc.tw * p.TW, tc.th * p.TH, tc.n);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        OCTSEG_CSTAMP(6, ckey);
       }
       chunk_ctr += n_tma;
 
@@ -1090,6 +1116,11 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     return sms;
   }
   pl->grid = kp.total_tiles < sms ? kp.total_tiles : sms;
+  // unequal channel tiles + plenty of spatial tiles: deal whole spatial tiles (tile_at)
+  kp.own_spatial = (!kp.halo && d->n_tiles_n > 1 && d->Cout % d->cout_per_tile != 0 && pl->grid % d->n_tiles_n == 0 &&
+                    kp.total_tiles / d->n_tiles_n >= 4 * sms)
+                       ? 1
+                       : 0;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -1115,6 +1146,10 @@ extern "C" int octseg_conv_plan_destroy(octseg_conv_plan* plan) {
 #ifdef OCTSEG_TRACE
 extern "C" int octseg_debug_trace(unsigned long long* h_out) {
   OCTSEG_CUDA(cudaMemcpyFromSymbol(h_out, octseg::g_trace, sizeof(unsigned long long) * kTraceEvents * kTraceTiles));
+  return OCTSEG_OK;
+}
+extern "C" int octseg_debug_trace_chunks(unsigned long long* h_out) {
+  OCTSEG_CUDA(cudaMemcpyFromSymbol(h_out, octseg::g_trace_chunk, sizeof(unsigned long long) * 8 * kTraceTiles));
   return OCTSEG_OK;
 }
 #endif

@@ -71,13 +71,14 @@ def preprocess_images(images: List[Image.Image], input_size: int, device: str = 
 
 def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Sequence[int], classes: Sequence[str],
             models_dir: str, device: str, batch_size: int = 16, models: Dict = None,
-            quantities: List = None, pipe: EnsemblePipeline = None) -> List[np.ndarray]:
+            quantities: List = None, pipe: EnsemblePipeline = None, pool=None) -> List[np.ndarray]:
     """Perform segmentation for given images using specified models; fills and returns ``masks``
     (the caller's float64 HxWx4 arrays), channel CLASS_IDS[name]-1 per requested class.
 
     ``pipe``: an EnsemblePipeline from ``make_pipeline`` to reuse across calls (the streaming main() builds it
     once: networks are compiled for ``batch_size`` frames, staging buffers and streams are allocated once;
-    a short last batch is zero-filled, never recompiled)."""
+    a short last batch is zero-filled, never recompiled).  ``pool``: executor that spreads the uint8 -> float64 fill of
+    the caller's masks (32 MB per frame at 1000 x 1000, the reference's format) over host threads."""
     if device != 'cuda':
         raise RuntimeError('the B200 build of segment() runs on CUDA only (device resolved to %r)' % device)
     if not images:
@@ -96,14 +97,23 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
     spans = [(lo, min(lo + batch, n)) for lo in range(0, n, batch)]
     # copies of batch i+1 / i-1 overlap the compute of batch i (EnsemblePipeline.stream_host)
     for (lo, hi), (mask, label, counts, radii, *contours) in zip(spans, pipe.stream_host(frames[lo:hi] for lo, hi in spans)):
-        for i in range(lo, hi):
-            for class_name in classes:
-                idx = CLASS_IDS[class_name] - 1
-                masks[i][:, :, idx] = mask[i - lo, :, :, idx]
+        idxs = [CLASS_IDS[class_name] - 1 for class_name in classes]
+
+        def fill(i, lo=lo, mask=mask):
+            if len(idxs) == 4:
+                masks[i][...] = mask[i - lo]
+            else:
+                for idx in idxs:
+                    masks[i][:, :, idx] = mask[i - lo, :, :, idx]
+        if pool is not None:
+            list(pool.map(fill, range(lo, hi)))          # numpy copies release the GIL
+        else:
+            for i in range(lo, hi):
+                fill(i)
         if quantities is not None:
             ratio = P.dicom_ratio(pipe.Ho)
             quantities.extend(P.quantities_from_counts(counts, pipe.Ho, pipe.Wo, ratio, radii,
-                                                       contours[0] if contours else None))
+                                                       contours[0] if contours else None, masks=mask))
     return masks
 
 
@@ -249,7 +259,7 @@ def main(cfg) -> None:
                 quantities = [] if want_quantities else None
                 masks = segment(images=images, masks=masks, output_size=cfg.output_size, classes=cfg.classes,
                                 models_dir=models_dir, device=device, batch_size=batch_size, models=models,
-                                quantities=quantities, pipe=pipe)
+                                quantities=quantities, pipe=pipe, pool=io)
                 if want_quantities:
                     table.update(zip(names, quantities))
                 if saving is not None:

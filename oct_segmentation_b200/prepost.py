@@ -246,13 +246,15 @@ def dicom_ratio(h: int) -> int:
 
 
 def quantities_from_counts(counts: np.ndarray, H: int, W: int, ratio: int, radii: Optional[np.ndarray] = None,
-                           contours=None) -> List[Dict]:
+                           contours=None, masks: Optional[np.ndarray] = None) -> List[Dict]:
     """Per-frame, per-class table from the device reductions (host side, cheap):
     present <=> 0 < nnz < H*W (== np.unique(ch).shape[0] == 2, analysis.py:189);
     area = sqrt(nnz // ratio) (analysis.py:199-200); radial thickness median/min over rays that hit;
     with ``contours`` (host (sums, nverts, verts) of ``contour_largest``) also the reference table's
     thickness_mean = contour median / ratio and thickness_min = contour min / ratio (analysis.py:202-207), under the
-    keys contour_thickness_mean / contour_thickness_min, for present classes."""
+    keys contour_thickness_mean / contour_thickness_min, for present classes.  A border longer than the device
+    buffer (CONTOUR_CAP points; only ragged, noise-like masks get there) is walked again on the GPU with a buffer of
+    the reported length when the host copy ``masks`` (uint8 (N, H, W, 4)) is given; without it that raises."""
     rows = []
     for n in range(counts.shape[0]):
         row = {}
@@ -268,7 +270,11 @@ def quantities_from_counts(counts: np.ndarray, H: int, W: int, ratio: int, radii
                 q['thickness_min'] = int(r.min()) if r.size else 0
                 q['thickness_max'] = int(r.max()) if r.size else 0
             if contours is not None and q['present']:
-                t = thickness_from_contour(contours[0][n, c], int(contours[1][n, c]), contours[2][n, c])
+                sums_nc, nv, verts_nc = contours[0][n, c], int(contours[1][n, c]), contours[2][n, c]
+                if nv > verts_nc.shape[0] and masks is not None:
+                    redo = contour_largest(torch.from_numpy(np.ascontiguousarray(masks[n:n + 1])).cuda(), cap=-(-nv // 1024) * 1024)
+                    sums_nc, nv, verts_nc = (redo[0][0, c].cpu().numpy(), int(redo[1][0, c]), redo[2][0, c].cpu().numpy())
+                t = thickness_from_contour(sums_nc, nv, verts_nc)
                 q['contour_thickness_mean'] = t['median'] / ratio
                 q['contour_thickness_min'] = t['min'] / ratio
             row[name] = q

@@ -35,6 +35,9 @@ if __name__ == '__main__':
         'head': ('linknet head 32->2 @896 (packed f=2)', [(64, 896, 448)], 4, 1, 16, 'none'),
         'vvstem': ('regnet stem s2d 16->32 @448 2x2', [(16, 448, 448)], 32, 2, 16, 'relu'),
         'expand': ('effnet expand 48->288 @224', [(48, 224, 224)], 288, 1, 16, 'swish'),
+        'expand_relu': ('effnet expand 48->288 @224 relu', [(48, 224, 224)], 288, 1, 16, 'relu'),
+        'e32': ('1x1 32->192 @448 relu', [(32, 448, 448)], 192, 1, 16, 'relu'),
+        'e80': ('1x1 80->480 @112 relu', [(80, 112, 112)], 480, 1, 16, 'relu'),
         'proj': ('effnet project 32->32 @448', [(32, 448, 448)], 32, 1, 16, 'none'),
         'c3': ('3x3 64->64 @256', [(64, 256, 256)], 64, 3, 32, 'relu'),
     }
@@ -62,5 +65,16 @@ if __name__ == '__main__':
     for i in range(100, 108):
         r = [int(t[e, i] - t0) for e in range(16)]
         print(f'{i:4d} {r[0]:7d} {r[10]-r[0]:5d} {r[11]-r[10]:5d} {r[12]-r[11]:5d} | {r[1]:7d} {r[2]-r[1]:5d} {r[13]-r[2]:5d} {r[14]-r[13]:5d} {r[15]-r[14]:5d} {r[3]-r[15]:5d}')
+    lib.octseg_debug_trace_chunks.argtypes = [C.c_void_p]
+    cb = np.zeros((8, 256), dtype=np.uint64)
+    _lib.check(lib.octseg_debug_trace_chunks(cb.ctypes.data), 'trace chunks')
+    c = cb.astype(np.int64)
+    print('group 0 chunks: start | tmem_ld  math  wait_store  bar1  sts+fence+bar2  issue | gap to next start')
+    for k in range(8, 24):
+        r = c[:, k]
+        if r[0] == 0:
+            break
+        print(f'{k:4d} {int(r[0] - t0):8d} | {int(r[1]-r[0]):6d} {int(r[2]-r[1]):6d} {int(r[3]-r[2]):6d} {int(r[4]-r[3]):6d} {int(r[5]-r[4]):6d} '
+              f'{int(r[6]-r[5]):6d} | {int(c[0, k + 1] - r[6]):6d}')
     d = np.diff(t[3, 50:200])
     print('steady-state cycles per tile (MMA commit to commit):', float(d.mean()))
