@@ -43,7 +43,9 @@ constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter -> 4 wa
 constexpr int kEpiSplit = kEpiWarps / 4;      // column parts per 64-channel chunk
 constexpr int kEpiPart = 64 / kEpiSplit;      // columns per warp per chunk (16)
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kStoreWarp = 2 + kEpiWarps;     // warp 18: issues the epilogue's TMA stores (off the math warps' critical path)
+constexpr int kThreads = 64 + kEpiThreads + 32;
+constexpr int kOutBufs = 4;                   // staging buffers: 2 per epilogue group
 constexpr uint32_t kTmemCols = 512;
 constexpr int kOutBytes = 128 * 128;  // one 128-row x 64-channel bf16 staging buffer
 
@@ -308,12 +310,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t smemB = smem0 + nst * a_bytes;
   // 2 x 16 KB epilogue staging (1 KB aligned: its 128B swizzle is address based)
   const uint32_t smemOut = smemB + (p.halo ? ((static_cast<uint32_t>(p.b_res_bytes) + 1023u) & ~1023u) : nst * b_bytes);
-  const uint32_t smemBias = smemOut + 2 * kOutBytes;     // fp32 bias of every channel tile
+  const uint32_t smemBias = smemOut + kOutBufs * kOutBytes;  // fp32 bias of every channel tile
   const uint32_t bars = smemBias + p.bias_floats * 4;    // full[8] empty[8] tfull[2] tempty[2] tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
   const uint32_t bar_tfull = bars + 16 * kMaxStages, bar_tempty = bar_tfull + 8 * kMaxAcc;
   const uint32_t bar_bres = bar_tempty + 8 * kMaxAcc;  // halo mode: resident weights landed
-  const uint32_t tmem_slot = bar_bres + 8;
+  const uint32_t bar_sfull = bar_bres + 8;              // [4] staging buffer written (256 arrivals of its group)
+  const uint32_t bar_sfree = bar_sfull + 8 * kOutBufs;  // [4] its TMA store has read it (store warp)
+  const uint32_t tmem_slot = bar_sfree + 8 * kOutBufs;
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -328,6 +332,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
     mbar_init(bar_bres, 1);
+    for (int b = 0; b < kOutBufs; ++b) {
+      mbar_init(bar_sfull + 8 * b, kEpiThreads / 2);
+      mbar_init(bar_sfree + 8 * b, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -673,6 +681,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     }
+  } else if (warp == kStoreWarp) {
+    // ------------------------------------------------------------------ TMA-store issuer (one lane)
+    // Replays the epilogue's (tile, chunk) sequence: waits until a group has written a staging buffer, stores it,
+    // and hands the buffer back once the store has read it.  Issuing a tensor store costs its thread ~300 cycles
+    // (measured, tools/trace_conv.py); on a math warp that sat on the critical path of every 64-channel chunk.
+    if (lane == 0 && p.use_tma_store) {
+      uint32_t chunk_ctr = 0, cnt[2] = {0u, 0u};
+      int pending = -1;  // buffer whose store was issued last (its read may still be in flight)
+      for (int it = 0, tile; (tile = tile_at(p, it)) < p.total_tiles; ++it) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int ch0 = tc.n_tile * p.cout_per_tile;
+        const int nvalid = min(p.cout_per_tile, p.Cout - ch0);
+        const int n_tma = p.out_grouped ? 1 : ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0));
+        for (int ck = 0; ck < n_tma; ++ck) {
+          const uint32_t g = (chunk_ctr + ck) & 1u;
+          const uint32_t kg = cnt[g]++;
+          const int buf = static_cast<int>(g * 2 + (kg & 1u));
+          mbar_wait(bar_sfull + 8 * buf, (kg >> 1) & 1u);
+          const uint32_t sbuf = smemOut + buf * kOutBytes;
+          const int cch = p.out_c_off + ch0 + ck * 64;
+          if (p.out_grouped)
+            tma_store_5d(&p.tmOut, sbuf, 0, tc.n_tile, tc.tw * p.TW, tc.th * p.TH, tc.n);
+          else if (p.phases == 4)
+            tma_store_5d(&p.tmOut, sbuf, cch, tc.pw, tc.tw * p.TW, tc.ph, tc.n * p.Hq + tc.th * p.TH);
+          else
+            tma_store_4d(&p.tmOut, sbuf, cch, tc.tw * p.TW, tc.th * p.TH, tc.n);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (pending >= 0) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // every store but the newest has read its buffer
+            mbar_arrive(bar_sfree + 8 * pending);
+          }
+          pending = buf;
+        }
+        chunk_ctr += n_tma;
+      }
+      if (pending >= 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(bar_sfree + 8 * pending);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores landed before exit
+    }
   } else {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware: warp id % 4)
@@ -682,9 +731,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int gtid = (static_cast<int>(threadIdx.x) - 64) & 255;
     const int row = q * 32 + lane;
     const int th_l = static_cast<int>(fd_div(static_cast<uint32_t>(row), p.fd_TW)), tw_l = row - th_l * p.TW;
-    const uint32_t sbuf = smemOut + group * kOutBytes;
     // this thread's staging row; its four 16-byte slots are chunk (half*4 + g) ^ (row & 7) (128B swizzle)
-    const uint32_t sts_row = sbuf + row * 128;
+    const uint32_t sts_row0 = smemOut + group * 2 * kOutBytes + row * 128;
+    uint32_t grp_chunks = 0;  // chunks this group has staged so far (buffer = grp_chunks & 1)
     const uint32_t sts_x = static_cast<uint32_t>(((half * 4) ^ (row & 7)) << 4);
     int acc = 0;
     uint32_t acc_phase = 0, chunk_ctr = 0;
@@ -758,29 +807,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           ov[g] = epi8<ACT, RES>(v + 8 * g, bias + cc, r8);
         }
         OCTSEG_CSTAMP(2, ckey);
-        if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store left the buffer
+        const uint32_t sbi = static_cast<uint32_t>(group * 2) + (grp_chunks & 1u);
+        mbar_wait(bar_sfree + 8 * sbi, ((grp_chunks >> 1) & 1u) ^ 1u);  // the store of this buffer's previous chunk has read it
         OCTSEG_CSTAMP(3, ckey);
-        group_bar_sync(group);
-        OCTSEG_CSTAMP(4, ckey);
+        const uint32_t sts_row = sts_row0 + (grp_chunks & 1u) * kOutBytes;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sts_row + (sts_x ^ (g << 4))), "r"(ov[g].x), "r"(ov[g].y),
                        "r"(ov[g].z), "r"(ov[g].w)
                        : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        group_bar_sync(group);
-        OCTSEG_CSTAMP(5, ckey);
-        if (gtid == 0) {
-          const int cch = p.out_c_off + ch0 + ck * 64;
-          if (p.out_grouped)
-            tma_store_5d(&p.tmOut, sbuf, 0, tc.n_tile, tc.tw * p.TW, tc.th * p.TH, tc.n);
-          else if (p.phases == 4)
-            tma_store_5d(&p.tmOut, sbuf, cch, tc.pw, tc.tw * p.TW, tc.ph, tc.n * p.Hq + tc.th * p.TH);
-          else
-            tma_store_4d(&p.tmOut, sbuf, cch, tc.tw * p.TW, tc.th * p.TH, tc.n);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        OCTSEG_CSTAMP(6, ckey);
+        mbar_arrive(bar_sfull + 8 * sbi);  // 256 arrivals: the store warp issues the TMA store
+        ++grp_chunks;
+        OCTSEG_CSTAMP(4, ckey);
       }
       chunk_ctr += n_tma;
 
@@ -841,7 +880,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         acc_phase ^= 1;
       }
     }
-    if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores landed before exit
   }
 
   tc_fence_before();
@@ -1101,7 +1139,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   const int stage_bytes = kp.a_stage_bytes + kp.b_stage_bytes;
   kp.bias_floats = (d->n_tiles_n * d->BN + 64 + 3) & ~3;
   const int b_res_region = (kp.b_res_bytes + 1023) & ~1023;
-  const int budget = 227 * 1024 - 1024 - 512 - 2 * kOutBytes - kp.bias_floats * 4 - b_res_region;
+  const int budget = 227 * 1024 - 1024 - 512 - kOutBufs * kOutBytes - kp.bias_floats * 4 - b_res_region;
   int nst = budget / stage_bytes;
   if (nst > kMaxStages) nst = kMaxStages;
   if (nst < 2) {
@@ -1109,7 +1147,7 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     return fail(OCTSEG_EINVAL, "tile does not fit shared memory");
   }
   kp.nstages = nst;
-  pl->smem = static_cast<size_t>(nst) * stage_bytes + b_res_region + 2 * kOutBytes + kp.bias_floats * 4 + 1024 + 512;
+  pl->smem = static_cast<size_t>(nst) * stage_bytes + b_res_region + kOutBufs * kOutBytes + kp.bias_floats * 4 + 1024 + 512;
   int sms = octseg_sm_count();
   if (sms <= 0) {
     delete pl;

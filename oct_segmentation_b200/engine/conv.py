@@ -25,11 +25,13 @@ HALO_TILES = True  # allow halo-tile mode (ConvGeom.halo)
 HALO_B_BYTES = 80 * 1024   # resident-weight budget of halo mode (shared memory)
 
 
-def choose_kc(c_eff: int) -> int:
+def choose_kc(c_eff: int, taps: int = 9) -> int:
     """Channel-chunk width of a K-segment: 64 (128B swizzle), 32 (64B) or 16 (32B).  Narrow sources
     use narrow chunks so neither TMA nor the MMAs spend time on zero padding; 64/kc consecutive
-    (tap, chunk) sub-blocks share one pipeline stage."""
-    if c_eff > 48:
+    (tap, chunk) sub-blocks share one pipeline stage.  A 1x1 conv over 33..48 channels is output-bound: one
+    zero-padded 64-channel chunk (one TMA box of 128-byte rows) beats three 16-channel boxes of 32-byte rows
+    (measured 48 -> 288 @224^2: 0.23 ms vs 0.34 ms, tools/bench_expand.py)."""
+    if c_eff > 48 or (taps == 1 and c_eff > 32):
         return 64
     if c_eff > 32:
         return 16
@@ -243,7 +245,7 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
         else:
             kh, kw = w.shape[2], w.shape[3]
             cg = sC // groups
-            kc = choose_kc(cg if groups > 1 else sC)
+            kc = choose_kc(cg if groups > 1 else sC, kh * kw)
             seg = SegSpec(N, sH, sW, sC, ldc, kh, kw, stride, (-pad[0], -pad[0]), (-pad[1], -pad[1]),
                           cg if groups > 1 else 0, -(-(cg if groups > 1 else sC) // kc), kc)
         segs.append(seg)
