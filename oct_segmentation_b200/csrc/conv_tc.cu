@@ -55,6 +55,7 @@ struct SegK {
   int c_per_tile, cchunks;
   int kc;  // chunk width (16/32/64 channels): swizzle 32B/64B/128B, 64/kc sub-blocks per stage
   int wide;  // 1: one (TW + kw - 1)-pixel box per tap ROW; the kw taps are shifted views of it
+  int last_steps;  // K = 16 MMA steps of the LAST chunk that hold real channels (the rest of it is zero padding: skipped)
 };
 
 struct __align__(64) ConvKParams {
@@ -71,6 +72,7 @@ struct __align__(64) ConvKParams {
   int bias_floats;    // n_tiles_n * BN + 64 bias values staged in shared memory (rounded up to 4)
   int b_stage_bytes;  // bytes of one B stage (kw weight tiles for wide segments)
   int a_stage_bytes;  // kABytes, kABytesWide, or the halo tile (rounded up to 1 KB) in halo mode
+  int d2s_tma;        // depth-to-space output through TMA: 64 % d2s == 0, one store per 2x2 sub-pixel of a 64-column chunk
   int own_spatial;    // 1: a CTA takes whole spatial tiles (all their channel tiles, back to back) -- see tile_at()
   int n_acc;          // accumulators in the TMEM ring (2 for BN = 256 ... 8 for BN <= 64)
   int halo;           // halo-tile mode: TH=16, TW=8, one halo box per channel chunk, resident weights
@@ -428,9 +430,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int cbase = sg.c_per_tile * tc.n_tile;
           const uint32_t tx_bytes = static_cast<uint32_t>((p.TH + sg.kh - 1) * (p.TW + sg.kw - 1) * sg.kc * 2);
           for (int cc = 0; cc < sg.cchunks; ++cc) {
+            OCTSEG_STAMP(10, it);
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            OCTSEG_STAMP(11, it);
             mbar_arrive_expect_tx_if(leader, bar_full + 8 * stage, tx_bytes);
             tma_load_4d_if(leader, smemA + stage * a_bytes, &p.tmA[0], bar_full + 8 * stage, cbase + cc * sg.kc, w0, h0, tc.n);
+            OCTSEG_STAMP(12, it);
             if (++stage == nst) {
               stage = 0;
               phase ^= 1;
@@ -534,9 +539,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int halo_nt = -1;
       uint32_t bres_phase = 0;
       const bool simple = p.nseg == 1 && !p.halo && !p.seg[0].wide && p.seg[0].kh == 1 && p.seg[0].kw == 1 && p.phases == 1;
-      const int s_kc = p.seg[0].kc, s_cch = p.seg[0].cchunks, s_subs = 64 / s_kc, s_steps = s_kc / 16;
+      const int s_kc = p.seg[0].kc, s_cch = p.seg[0].cchunks, s_subs = 64 / s_kc, s_steps = s_kc / 16, s_last = p.seg[0].last_steps;
       const uint32_t s_asub = 128u * s_kc * 2u, s_bsub = static_cast<uint32_t>(p.BN) * s_kc * 2u;
       const uint64_t s_desc = make_kmajor_desc(0, s_kc);
+      // halo mode: loop-invariant geometry of the single segment, hoisted out of the tile loop
+      const uint32_t h_kh = p.seg[0].kh, h_kw = p.seg[0].kw, h_cch = p.seg[0].cchunks, h_pw = p.TW + p.seg[0].kw - 1;
+      const uint32_t h_rb = p.seg[0].kc * 2;  // bytes per pixel of a chunk = the swizzle span (32 / 64 / 128)
+      const uint32_t h_tile_bytes = static_cast<uint32_t>(p.BN) * h_rb;
+      const int h_full = p.seg[0].kc / 16, h_last = p.seg[0].last_steps;
+      // A: 8-pixel tile rows are the 8-row groups; group stride = one halo row (h_pw * h_rb bytes)
+      const uint64_t h_desc_b = make_kmajor_desc(0, p.seg[0].kc);
+      const uint64_t h_desc_a = (h_desc_b & ~(0x3FFFull << 32)) | (static_cast<uint64_t>((h_pw * h_rb) >> 4) << 32);
       for (int it = 0, tile; (tile = tile_at(p, it)) < p.total_tiles; ++it) {
         OCTSEG_STAMP(1, it);  // MMA warp ready for this tile
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -552,7 +565,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int j = 0; j < n; ++j) {
               const uint64_t adesc = s_desc | ((smemA + stage * a_bytes + j * s_asub) >> 4);
               const uint64_t bdesc = s_desc | ((smemB + stage * b_bytes + j * s_bsub) >> 4);
-              for (int t = 0; t < s_steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
+              const int nsteps = cc + j == s_cch - 1 ? s_last : s_steps;
+              for (int t = 0; t < nsteps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
                 tc_mma_bf16(leader, d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
                 accum = 1;
               }
@@ -571,29 +585,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(bar_bres, bres_phase);
             bres_phase ^= 1;
           }
-          const int pw = p.TW + sg.kw - 1;  // halo row pitch in pixels
-          const int rb = sg.kc * 2;         // bytes per pixel of a chunk = the swizzle span (32 / 64 / 128)
-          // A: 8-pixel tile rows are the 8-row groups; group stride = one halo row (pw * rb bytes)
-          uint64_t desc_a = make_kmajor_desc(0, sg.kc);
-          desc_a = (desc_a & ~(0x3FFFull << 32)) | (static_cast<uint64_t>((pw * rb) >> 4) << 32);
-          const uint64_t desc_b = make_kmajor_desc(0, sg.kc);
-          const uint32_t tile_bytes = static_cast<uint32_t>(p.BN * rb);
-          const int steps = sg.kc / 16;
-          for (int cc = 0; cc < sg.cchunks; ++cc) {
+          // Per-tap descriptors advance by ADDITIONS of loop-invariant strides kept in registers: with one K = 16 step
+          // per tap (16-channel sources) the issue loop itself was the bottleneck (~240 cycles per tap with the
+          // multiplies, parameter loads and vector->uniform moves of the first version; tools/trace_conv.py d2s16).
+          const uint32_t a_tap = h_rb, a_row = (h_pw - h_kw) * h_rb, b_tap = h_cch * h_tile_bytes;
+          for (int cc = 0; cc < h_cch; ++cc) {
+            const int steps = cc == h_cch - 1 ? h_last : h_full;
+            OCTSEG_STAMP(13, it);
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
-            const uint32_t a0 = smemA + stage * a_bytes;
-            for (int ty = 0; ty < sg.kh; ++ty)
-              for (int tx = 0; tx < sg.kw; ++tx) {
-                const uint64_t adesc = desc_a | ((a0 + static_cast<uint32_t>((ty * pw + tx) * rb)) >> 4);
-                const uint64_t bdesc =
-                    desc_b | ((smemB + static_cast<uint32_t>((ty * sg.kw + tx) * sg.cchunks + cc) * tile_bytes) >> 4);
+            OCTSEG_STAMP(14, it);
+            uint32_t a_addr = smemA + stage * a_bytes;
+            uint32_t b_addr = smemB + static_cast<uint32_t>(cc) * h_tile_bytes;
+            for (int ty = 0; ty < h_kh; ++ty) {
+              for (int tx = 0; tx < h_kw; ++tx) {
+                const uint64_t adesc = h_desc_a | (a_addr >> 4);
+                const uint64_t bdesc = h_desc_b | (b_addr >> 4);
                 for (int t = 0; t < steps; ++t) {  // K=16 per MMA: +32 B inside the swizzle span
                   tc_mma_bf16(leader, d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
                   accum = 1;
                 }
+                a_addr += a_tap;
+                b_addr += b_tap;
               }
+              a_addr += a_row;
+            }
             tc_commit(leader, bar_empty + 8 * stage);
+            OCTSEG_STAMP(15, it);
             if (++stage == nst) {
               stage = 0;
               phase ^= 1;
@@ -610,17 +628,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             // so a start address that is only 128-byte aligned still decodes what TMA wrote.
             const int kw = p.seg[s].kw;
             const uint32_t tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
-            for (int st = p.seg[s].kh * p.seg[s].cchunks; st > 0; --st) {
+            const int cch = p.seg[s].cchunks, lsteps = p.seg[s].last_steps;
+            int ccw = 0;  // chunk index of the current stage (stages run tap row major, chunk fastest)
+            for (int st = p.seg[s].kh * cch; st > 0; --st) {
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
+              const int nsteps = ccw == cch - 1 ? lsteps : 4;
+              if (++ccw == cch) ccw = 0;
               for (int tx = 0; tx < kw; ++tx) {
                 const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes + tx * 128u) >> 4);
                 const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes + tx * tile_bytes) >> 4);
-                tc_mma_bf16(leader, d_tmem, adesc, bdesc, idesc, accum);
-                tc_mma_bf16(leader, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                tc_mma_bf16(leader, d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                tc_mma_bf16(leader, d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-                accum = 1;
+                for (int t = 0; t < nsteps; ++t) {
+                  tc_mma_bf16(leader, d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, accum);
+                  accum = 1;
+                }
               }
               tc_commit(leader, bar_empty + 8 * stage);
               if (++stage == nst) {
@@ -630,6 +651,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
           } else if (kc == 64) {
             // hot path: one 64-channel sub-block per stage, four back-to-back MMAs
+            const int cch = p.seg[s].cchunks, lsteps = p.seg[s].last_steps;
+            int cck = 0;  // chunk index of the current sub-block (chunk fastest within a tap)
             for (; nsub > 0; --nsub) {
               OCTSEG_STAMP(13, it);
               mbar_wait(bar_full + 8 * stage, phase);
@@ -637,10 +660,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               OCTSEG_STAMP(14, it);  // operands landed
               const uint64_t adesc = desc_hi | ((smemA + stage * a_bytes) >> 4);
               const uint64_t bdesc = desc_hi | ((smemB + stage * b_bytes) >> 4);
-              tc_mma_bf16(leader, d_tmem, adesc, bdesc, idesc, accum);
-              tc_mma_bf16(leader, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-              tc_mma_bf16(leader, d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-              tc_mma_bf16(leader, d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              const bool full_chunk = lsteps == 4 || cck != cch - 1;
+              if (++cck == cch) cck = 0;
+              if (full_chunk) {
+                tc_mma_bf16(leader, d_tmem, adesc, bdesc, idesc, accum);
+                tc_mma_bf16(leader, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                tc_mma_bf16(leader, d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                tc_mma_bf16(leader, d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              } else {  // the last chunk's K = 16 steps that are all zero padding are skipped
+                for (int t = 0; t < lsteps; ++t) tc_mma_bf16(leader, d_tmem, adesc + 2 * t, bdesc + 2 * t, idesc, t ? 1u : accum);
+              }
               accum = 1;
               tc_commit(leader, bar_empty + 8 * stage);
               OCTSEG_STAMP(15, it);  // MMAs issued, stage committed
@@ -701,7 +730,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_wait(bar_sfull + 8 * buf, (kg >> 1) & 1u);
           const uint32_t sbuf = smemOut + buf * kOutBytes;
           const int cch = p.out_c_off + ch0 + ck * 64;
-          if (p.out_grouped)
+          if (p.d2s_tma) {  // one box per 2x2 sub-pixel held by this chunk: (channels, pw, j, ph, n*Hq + i)
+            const int nsub = 64 / p.d2s;
+            for (int sl = 0; sl < nsub; ++sl) {
+              const int sub = ck * nsub + sl;
+              tma_store_5d(&p.tmOut, sbuf + static_cast<uint32_t>(sl * 128 * p.d2s * 2), 0, sub & 1, tc.tw * p.TW, sub >> 1,
+                           tc.n * p.Hq + tc.th * p.TH);
+            }
+          } else if (p.out_grouped)
             tma_store_5d(&p.tmOut, sbuf, 0, tc.n_tile, tc.tw * p.TW, tc.th * p.TH, tc.n);
           else if (p.phases == 4)
             tma_store_5d(&p.tmOut, sbuf, cch, tc.pw, tc.tw * p.TW, tc.ph, tc.n * p.Hq + tc.th * p.TH);
@@ -732,9 +768,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int row = q * 32 + lane;
     const int th_l = static_cast<int>(fd_div(static_cast<uint32_t>(row), p.fd_TW)), tw_l = row - th_l * p.TW;
     // this thread's staging row; its four 16-byte slots are chunk (half*4 + g) ^ (row & 7) (128B swizzle)
-    const uint32_t sts_row0 = smemOut + group * 2 * kOutBytes + row * 128;
+    // (depth-to-space through TMA: a chunk holds 64 / d2s sub-pixels, each its own [128 rows][d2s channels] region
+    //  with the 32 / 64 / 128-byte swizzle of its row length)
+    const uint32_t sts_base0 = smemOut + group * 2 * kOutBytes;
     uint32_t grp_chunks = 0;  // chunks this group has staged so far (buffer = grp_chunks & 1)
-    const uint32_t sts_x = static_cast<uint32_t>(((half * 4) ^ (row & 7)) << 4);
+    uint32_t sts_off[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (p.d2s_tma) {
+        const int cs = p.d2s, cl = half * 32 + g * 8, sl = cl / cs, co = cl - sl * cs;
+        const int swz = cs == 64 ? (row & 7) : (cs == 32 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+        sts_off[g] = static_cast<uint32_t>(sl * 128 * cs * 2 + row * cs * 2 + (((co >> 3) ^ swz) << 4));
+      } else {
+        sts_off[g] = static_cast<uint32_t>(row * 128 + (((half * 4 + g) ^ (row & 7)) << 4));
+      }
+    }
     int acc = 0;
     uint32_t acc_phase = 0, chunk_ctr = 0;
     int it = 0;
@@ -810,10 +858,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t sbi = static_cast<uint32_t>(group * 2) + (grp_chunks & 1u);
         mbar_wait(bar_sfree + 8 * sbi, ((grp_chunks >> 1) & 1u) ^ 1u);  // the store of this buffer's previous chunk has read it
         OCTSEG_CSTAMP(3, ckey);
-        const uint32_t sts_row = sts_row0 + (grp_chunks & 1u) * kOutBytes;
+        const uint32_t sts_base = sts_base0 + (grp_chunks & 1u) * kOutBytes;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sts_row + (sts_x ^ (g << 4))), "r"(ov[g].x), "r"(ov[g].y),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sts_base + sts_off[g]), "r"(ov[g].x), "r"(ov[g].y),
                        "r"(ov[g].z), "r"(ov[g].w)
                        : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -990,6 +1038,12 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     k.cchunks = sg.cchunks;
     k.kc = sg.kc;
     k.wide = sg.wide ? 1 : 0;
+    {
+      const int c_eff = sg.c_per_tile > 0 ? sg.c_per_tile : sg.C;
+      const int rem = c_eff - (sg.cchunks - 1) * sg.kc;
+      const int ls = (rem + 15) / 16;
+      k.last_steps = ls < 1 ? 1 : (ls > sg.kc / 16 ? sg.kc / 16 : ls);
+    }
     if (sg.wide && sg.kw > b_tiles) b_tiles = sg.kw;
     if (sg.wide) any_wide = true;
     const int nsub = sg.kh * sg.kw * sg.cchunks, subs = 64 / sg.kc;
@@ -1082,8 +1136,12 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
                     d->d2s == 0 && d->Cout == d->n_tiles_n * d->cout_per_tile && (d->cout_per_tile * 2) % 16 == 0)
                        ? 1
                        : 0;
+  kp.d2s_tma = (d->d2s && 64 % d->d2s == 0 && d->Hq % d->TH == 0 && d->BN == 4 * d->d2s && d->n_tiles_n == 1 && d->out_c_off == 0 &&
+                d->out_ldc == d->d2s && d->Cout == 4 * d->d2s)
+                   ? 1
+                   : 0;
   kp.use_tma_store = (d->out_mode == OCTSEG_OUT_BF16_NHWC &&
-                      (d->cout_per_tile >= 64 || d->n_tiles_n == 1 || kp.out_grouped) && d->d2s == 0 &&
+                      (d->cout_per_tile >= 64 || d->n_tiles_n == 1 || kp.out_grouped) && (d->d2s == 0 || kp.d2s_tma) &&
                       (d->phases == 1 || (d->Hq % d->TH == 0 && d->out_H == 2 * d->Hq && d->out_W == 2 * d->Wq)))
                          ? 1
                          : 0;
@@ -1096,6 +1154,18 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     const uint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
     const int rc = encode_map(&kp.tmOut, static_cast<const __nv_bfloat16*>(d->out) + d->out_c_off, 5, dims, strides, box, estr,
                               "out(grouped)");
+    if (rc) {
+      delete pl;
+      return rc;
+    }
+  } else if (kp.d2s_tma) {
+    // low-res pixel (i, j) of image n, sub-pixel (ph, pw): dims (c, pw, j, ph, n*Hq + i) of the 2x larger output
+    const uint64_t ld = static_cast<uint64_t>(d->out_ldc) * 2, wout = 2ull * d->Wq;
+    const uint64_t dims[5] = {static_cast<uint64_t>(d->d2s), 2u, static_cast<uint64_t>(d->Wq), 2u, static_cast<uint64_t>(d->N) * d->Hq};
+    const uint64_t strides[4] = {ld, 2 * ld, ld * wout, 2 * ld * wout};
+    const uint32_t box[5] = {static_cast<uint32_t>(d->d2s), 1u, static_cast<uint32_t>(d->TW), 1u, static_cast<uint32_t>(d->TH)};
+    const uint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    const int rc = encode_map(&kp.tmOut, d->out, 5, dims, strides, box, estr, "out(d2s)", d->d2s);
     if (rc) {
       delete pl;
       return rc;

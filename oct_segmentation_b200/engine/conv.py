@@ -19,6 +19,8 @@ import torch
 
 from .. import _lib
 
+import os as _os
+KC64_ALWAYS = _os.environ.get('OCTSEG_KC64', '0') == '1'   # experiment: zero-padded 64-channel chunks for every source
 KC = 64  # K elements per pipeline stage (one 128-byte swizzle atom of bf16)
 WIDE_BOXES = True  # allow shifted-view tap reuse (SegSpec.wide)
 HALO_TILES = True  # allow halo-tile mode (ConvGeom.halo)
@@ -31,7 +33,7 @@ def choose_kc(c_eff: int, taps: int = 9) -> int:
     (tap, chunk) sub-blocks share one pipeline stage.  A 1x1 conv over 33..48 channels is output-bound: one
     zero-padded 64-channel chunk (one TMA box of 128-byte rows) beats three 16-channel boxes of 32-byte rows
     (measured 48 -> 288 @224^2: 0.23 ms vs 0.34 ms, tools/bench_expand.py)."""
-    if c_eff > 48 or (taps == 1 and c_eff > 32):
+    if c_eff > 48 or (taps == 1 and c_eff > 32) or KC64_ALWAYS:
         return 64
     if c_eff > 32:
         return 16

@@ -41,14 +41,31 @@ if __name__ == '__main__':
         'proj': ('effnet project 32->32 @448', [(32, 448, 448)], 32, 1, 16, 'none'),
         'c3': ('3x3 64->64 @256', [(64, 256, 256)], 64, 3, 32, 'relu'),
     }
+    LAYERS['d2s16'] = ('linknet convT 16->16 @448 (depth-to-space)', [(16, 448, 448)], 16, 4, 16, 'relu')
+    LAYERS['vvhead'] = ('unet head 16->1 3x3 @896 (packed f=4, u8 planes)', [(64, 896, 224)], 4, 3, 16, 'none')
     name, srcs, cout, k, n, act = LAYERS[sys.argv[1]]
     spec = [((n, s[1], s[2], s[0], CV.pad8(s[0])), False) for s in srcs]
-    w = torch.randn(cout, sum(s[0] for s in srcs), k, k) * 0.05
-    geom, packed = CV.plan_conv(spec, w, pad=(k // 2, k // 2), out_hw=(srcs[0][1], srcs[0][2]))
-    bias = CV.pad_bias(torch.zeros(cout), geom, cout)
     seg_t = [torch.randn(n, s[1], s[2], CV.pad8(s[0]), device='cuda').to(torch.bfloat16) for s in srcs]
-    out = torch.empty(n, geom.out_H, geom.out_W, geom.Cout, dtype=torch.bfloat16, device='cuda')
-    plan = CV.ConvPlan(geom, packed, bias, seg_t, out, act=act, name=name)
+    if sys.argv[1] == 'd2s16':
+        cs = CV.pad8(cout)
+        wp, bp = CV.d2s_weights(torch.randn(srcs[0][0], cout, 4, 4) * 0.05, torch.zeros(cout), True, cs)
+        geom, packed = CV.plan_conv(spec, wp, pad=(1, 1))
+        bias = CV.pad_bias(bp, geom, 4 * cs)
+        out = torch.empty(n, 2 * srcs[0][1], 2 * srcs[0][2], cs, dtype=torch.bfloat16, device='cuda')
+        plan = CV.ConvPlan(geom, packed, bias, seg_t, out, act=act, name=name, out_ldc=cs, d2s=cs)
+    elif sys.argv[1] == 'vvhead':
+        w16 = torch.randn(1, 16, 3, 3) * 0.05
+        wp, bp = CV.pack_conv_weights(w16, torch.zeros(1), [16], [16], 4, 1, 1)
+        geom, packed = CV.plan_conv(spec, wp, stride=1, pad=(1, 1), out_bf16=False)
+        bias = CV.pad_bias(bp, geom, 4)
+        out = torch.empty(n, 1, 896, 896, dtype=torch.uint8, device='cuda')
+        plan = CV.ConvPlan(geom, packed, bias, seg_t, out, out_mode='u8_nchw', act=act, name=name, out_pack=4, out_ldc=1)
+    else:
+        w = torch.randn(cout, sum(s[0] for s in srcs), k, k) * 0.05
+        geom, packed = CV.plan_conv(spec, w, pad=(k // 2, k // 2), out_hw=(srcs[0][1], srcs[0][2]))
+        bias = CV.pad_bias(torch.zeros(cout), geom, cout)
+        out = torch.empty(n, geom.out_H, geom.out_W, geom.Cout, dtype=torch.bfloat16, device='cuda')
+        plan = CV.ConvPlan(geom, packed, bias, seg_t, out, act=act, name=name)
     for _ in range(3):
         plan.run()
     torch.cuda.synchronize()
@@ -56,13 +73,13 @@ if __name__ == '__main__':
     _lib.check(lib.octseg_debug_trace(buf.ctypes.data), 'trace')
     t = buf.astype(np.int64)
     t0 = t[0, 0]
-    print(name, 'tile', (geom.TH, geom.TW), 'BN', geom.BN, 'ntn', geom.n_tiles_n, 'kc', [s.kc for s in geom.segs])
+    print(name, 'tile', (geom.TH, geom.TW), 'BN', geom.BN, 'ntn', geom.n_tiles_n, 'kc', [s.kc for s in geom.segs], 'halo', geom.halo, 'Ktot', geom.Ktot)
     print('tile  prod  | mma_rdy acc_free commit | g0_rdy g0_full g0_rel | g1_rdy g1_full g1_rel')
     for i in list(range(0, 12)) + list(range(100, 112)):
         r = [int(t[e, i] - t0) for e in range(10)]
         print(f'{i:4d} {r[0]:6d} | {r[1]:6d} {r[2]:6d} {r[3]:6d} | {r[4]:6d} {r[5]:6d} {r[6]:6d} | {r[7]:6d} {r[8]:6d} {r[9]:6d}')
     print('tile  prod: start setup stage_free issued | mma: rdy acc_free k_wait landed issued commit')
-    for i in range(100, 108):
+    for i in range(20, 28):
         r = [int(t[e, i] - t0) for e in range(16)]
         print(f'{i:4d} {r[0]:7d} {r[10]-r[0]:5d} {r[11]-r[10]:5d} {r[12]-r[11]:5d} | {r[1]:7d} {r[2]-r[1]:5d} {r[13]-r[2]:5d} {r[14]-r[13]:5d} {r[15]-r[14]:5d} {r[3]-r[15]:5d}')
     lib.octseg_debug_trace_chunks.argtypes = [C.c_void_p]
