@@ -141,12 +141,15 @@ int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t H, int32_t
                         int32_t Ho, int32_t Wo, void* stream);
 
 /* Depthwise kxk conv (efficientnet_pytorch MBConvBlock._depthwise_conv with static "same"
-   padding, k in {3,5}, stride in {1,2}) + folded BN + swish; optionally accumulates the squeeze-excite channel sums
-   (adaptive_avg_pool2d numerator) into `pool_sum` fp32 [N][C] (must be zeroed by caller). */
+   padding, k in {3,5}, stride in {1,2}) + folded BN + swish; optionally writes the squeeze-excite channel sums
+   (adaptive_avg_pool2d numerator) as partial sums `pool_sum` fp32 [N][pool_slots][C]: one slot per row group of
+   tiles, each written exactly once (plain stores: no zeroing, no atomics, bit-reproducible);
+   pool_slots = octseg_dwconv_pool_slots(C, Ho, Wo); octseg_se_hidden adds the slots in order. */
 int octseg_dwconv(const void* in, const void* weight /* bf16 [kh][kw][C] */, const float* bias,
                   void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
                   int32_t pad_t, int32_t pad_l, int32_t Ho, int32_t Wo, int32_t act,
-                  float* pool_sum, void* stream);
+                  float* pool_sum, int32_t pool_slots, void* stream);
+int octseg_dwconv_pool_slots(int32_t C, int32_t Ho, int32_t Wo);
 
 /* Fused front half of an MBConv block (efficientnet_pytorch MBConvBlock: _expand_conv -> _bn0 -> swish ->
    _depthwise_conv (static "same" padding) -> _bn1 -> swish, plus the squeeze-excite channel sums), BatchNorms folded.
@@ -154,32 +157,38 @@ int octseg_dwconv(const void* in, const void* weight /* bf16 [kh][kw][C] */, con
    x: bf16 NHWC [N][H][W][ldc_in] (Cin real channels, Cin % 16 == 0); w_exp: bf16 [Cmid][Cin];
    blob: fp32 [ceil(Cmid/64)][2 + k*k][64], per 64-channel block c0: row 0 = b_exp[c0..]/2, row 1 = b_dw[c0..]/2,
    row 2 + ky*k + kx = w_dw[ky][kx][c0..]/2 (zero beyond Cmid; the halving is the swish form h*tanh(h)+h, h = x/2);
-   out: bf16 NHWC [N][Ho][Wo][Cmid]; k in {3,5}, stride 1; pool_sum: fp32 [N][Cmid] accumulated (zeroed by the
-   caller) or NULL.  EINVAL if the tile does not fit shared memory (octseg_mbconv_smem_bytes(Cin, k, stride) >
+   out: bf16 NHWC [N][Ho][Wo][Cmid]; k in {3,5}, stride 1; pool_sum: fp32 [N][slots][Cmid] per-tile partial sums
+   (slots = octseg_mbconv_pool_slots(k, Ho, Wo), each written once) or NULL.  EINVAL if the tile does not fit shared memory (octseg_mbconv_smem_bytes(Cin, k, stride) >
    227 KB, or < 0 for unsupported shapes).  octseg_mbconv_blob_floats(Cmid, k) = number of floats in `blob`. */
 int octseg_mbconv_expand_dw(const void* x, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ldc_in,
                             const void* w_exp, const float* blob, void* out, int32_t Cmid, int32_t k, int32_t stride,
                             int32_t pad_t, int32_t pad_l, int32_t Ho, int32_t Wo, float* pool_sum, void* stream);
 int octseg_mbconv_smem_bytes(int32_t Cin, int32_t k, int32_t stride);
 int octseg_mbconv_blob_floats(int32_t Cmid, int32_t k);
+int octseg_mbconv_pool_slots(int32_t k, int32_t Ho, int32_t Wo);
 
 /* Squeeze-excite (efficientnet_pytorch MBConvBlock: adaptive_avg_pool2d -> _se_reduce -> swish ->
    _se_expand -> sigmoid -> gate * x), folded into the projection 1x1 conv's weights:
-   hidden[n][r] = swish(w1[r,:] . (pool_sum[n,:] * inv_hw) + b1[r])                 fp32 [N][Cr]     */
-int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1 /* [Cr][C] */, const float* b1,
-                     float* hidden, int32_t N, int32_t C, int32_t Cr, void* stream);
+   hidden[n][r] = swish(w1[r,:] . (sum_s pool_sum[n,s,:] * inv_hw) + b1[r])          fp32 [N][Cr]
+   pool_sum: fp32 [N][slots][C] partial sums (octseg_dwconv / octseg_mbconv_expand_dw), added in slot order into
+   sums_scratch fp32 [N][C] first (a second tiny launch; may be NULL when slots == 1). */
+int octseg_se_hidden(const float* pool_sum, int32_t slots, float* sums_scratch, float inv_hw,
+                     const float* w1 /* [Cr][C] */, const float* b1, float* hidden, int32_t N, int32_t C, int32_t Cr,
+                     void* stream);
 
 /* gate[n][k] = sigmoid(w2[k,:] . hidden[n,:] + b2[k])                               fp32 [N][C]
-   `pool_clear` (may be NULL): fp32 [N][C] buffer set to zero on the way -- the pool_sum that octseg_se_hidden
-   just consumed, so the next octseg_dwconv call finds it zeroed without a separate memset. */
+   `pool_clear` (may be NULL): fp32 [N][C] buffer set to zero on the way (unused since the pool sums became
+   write-once slots; kept for callers that accumulate into a buffer of their own). */
 int octseg_se_gate(const float* hidden, const float* w2t /* fp32 [Cr][C] */, const float* b2, float* gate,
                    float* pool_clear, int32_t N, int32_t C, int32_t Cr, void* stream);
 
-/* out[n][row][k] = bf16(w[row][k] * gate[n][k]) for k < C and 0 for the K padding: per-image weights of the
-   projection conv (B tensor map z = n), i.e. `gate * x` folded into `_project_conv`. */
+/* out[n][row][k] = bf16(w[row][k] * gate[n][k % gate_period]) for k < C and 0 for the K padding: per-image weights
+   of the projection conv (B tensor map z = n), i.e. `gate * x` folded into `_project_conv`.  gate: fp32
+   [N][gate_period]; gate_period = C for a plain conv (0 means C), the channel count of one pixel when the conv runs on
+   a pixel-packed view (K = packed pixels x channels). */
 int octseg_se_scale_weights(const float* gate, const float* w /* fp32 [rows][Ktot] */,
                             void* out /* bf16 [N][rows][Ktot] */, int32_t N, int32_t rows, int32_t Ktot,
-                            int32_t C, void* stream);
+                            int32_t C, int32_t gate_period, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pre-processing: preprocessing_img (src/data/utils.py:159-166): RGB->BGR + cv2.resize

@@ -127,6 +127,30 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 // rescale of the projection weights.  All three steps are latency-bound, so each kernel is laid out for
 // many independent loads in flight rather than for FLOPs.
 //
+// Step 0 (maps with more than one slot): sums[n][c] = sum_s pool[n][s][c] in slot order.  pool holds the depthwise
+// kernel's write-once partial sums (one slot per row group of tiles, up to 56 for a 448 x 448 map); adding them in a
+// fixed order makes the pooled mean bit-reproducible (the first version accumulated with fp32 atomics).  One thread
+// per (image, 4 channels): slots independent 16-byte loads in flight.
+__global__ void __launch_bounds__(256) se_pool_reduce_kernel(const float* __restrict__ pool, float* __restrict__ sums,
+                                                             int N, int slots, int C4) {
+  const size_t total = static_cast<size_t>(N) * C4;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = idx / C4, c4 = idx - n * C4;
+    const float4* p = reinterpret_cast<const float4*>(pool) + n * slots * C4 + c4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int sl = 0; sl < slots; ++sl) {
+      const float4 v = __ldg(p + static_cast<size_t>(sl) * C4);
+      a.x += v.x;
+      a.y += v.y;
+      a.z += v.z;
+      a.w += v.w;
+    }
+    reinterpret_cast<float4*>(sums)[idx] = a;
+  }
+}
+
 // hidden[n][r] = swish(W1[r,:] . mean[n,:] + b1[r]): one block per hidden unit r computes it for ALL images,
 // so W1's row is read once and every thread has up to 1 + N independent loads per step.
 constexpr int kSeMaxN = 8;  // images per block of se_hidden_kernel (blockIdx.y = image group)
@@ -201,7 +225,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) se_scale_weights_kernel(const float* __restrict__ gate,
                                                                const float* __restrict__ w,  // [rows][Ktot]
                                                                __nv_bfloat16* __restrict__ out, int N, int rows,
-                                                               int Ktot, int C) {
+                                                               int Ktot, int C, int period) {
   const int k8n = Ktot >> 3;
   const size_t per_image = static_cast<size_t>(rows) * k8n;
   const size_t total = per_image * N;
@@ -214,8 +238,9 @@ __global__ void __launch_bounds__(256) se_scale_weights_kernel(const float* __re
     if (k < C) {  // C and Ktot are multiples of 8: a group is entirely real or entirely padding
       const float4 a0 = __ldg(reinterpret_cast<const float4*>(w + rem * 8));
       const float4 a1 = __ldg(reinterpret_cast<const float4*>(w + rem * 8 + 4));
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * C + k));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * C + k + 4));
+      const int kg = k % period;  // pixel-packed problems repeat the channel block `period` along K
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * period + kg));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * period + kg + 4));
       f[0] = a0.x * g0.x;
       f[1] = a0.y * g0.y;
       f[2] = a0.z * g0.z;
@@ -278,10 +303,21 @@ extern "C" int octseg_maxpool3x3s2(const void* in, void* out, int32_t N, int32_t
   return check_launch("maxpool3x3s2_kernel");
 }
 
-extern "C" int octseg_se_hidden(const float* pool_sum, float inv_hw, const float* w1, const float* b1, float* hidden,
-                                int32_t N, int32_t C, int32_t Cr, void* stream) {
+extern "C" int octseg_se_hidden(const float* pool_sum, int32_t slots, float* sums_scratch, float inv_hw, const float* w1,
+                                const float* b1, float* hidden, int32_t N, int32_t C, int32_t Cr, void* stream) {
+  if (slots < 1) return fail(OCTSEG_EINVAL, "se_hidden: slots must be >= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* sums = pool_sum;
+  if (slots > 1) {
+    if (!sums_scratch || C % 4 || (reinterpret_cast<uintptr_t>(pool_sum) & 15) || (reinterpret_cast<uintptr_t>(sums_scratch) & 15))
+      return fail(OCTSEG_EINVAL, "se_hidden: slots > 1 needs a 16-byte aligned fp32 [N][C] scratch buffer and C %% 4 == 0");
+    se_pool_reduce_kernel<<<grid_for(static_cast<size_t>(N) * (C / 4), 256), 256, 0, st>>>(pool_sum, sums_scratch, N, slots, C / 4);
+    const int rc = check_launch("se_pool_reduce_kernel");
+    if (rc) return rc;
+    sums = sums_scratch;
+  }
   dim3 grid(Cr, cdiv(N, kSeMaxN));
-  se_hidden_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pool_sum, inv_hw, w1, b1, hidden, N, C, Cr);
+  se_hidden_kernel<<<grid, 256, 0, st>>>(sums, inv_hw, w1, b1, hidden, N, C, Cr);
   return check_launch("se_hidden_kernel");
 }
 
@@ -295,13 +331,15 @@ extern "C" int octseg_se_gate(const float* hidden, const float* w2t, const float
 }
 
 extern "C" int octseg_se_scale_weights(const float* gate, const float* w, void* out, int32_t N, int32_t rows,
-                                       int32_t Ktot, int32_t C, void* stream) {
+                                       int32_t Ktot, int32_t C, int32_t gate_period, void* stream) {
   if (Ktot % 8 || C % 8 || C > Ktot) return fail(OCTSEG_EINVAL, "se_scale_weights: C and Ktot must be multiples of 8, C <= Ktot");
+  if (gate_period <= 0) gate_period = C;
+  if (gate_period % 8 || C % gate_period) return fail(OCTSEG_EINVAL, "se_scale_weights: gate_period must be a multiple of 8 dividing C");
   if ((reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
       (reinterpret_cast<uintptr_t>(gate) & 15))
     return fail(OCTSEG_EINVAL, "se_scale_weights: pointers must be 16-byte aligned");
   const size_t total = static_cast<size_t>(N) * rows * (Ktot / 8);
   se_scale_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      gate, w, static_cast<__nv_bfloat16*>(out), N, rows, Ktot, C);
+      gate, w, static_cast<__nv_bfloat16*>(out), N, rows, Ktot, C, gate_period);
   return check_launch("se_scale_weights_kernel");
 }

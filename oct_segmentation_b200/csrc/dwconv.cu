@@ -14,6 +14,8 @@
 //   * fp32 filters of the CTA's channel block sit in shared memory, reloaded only when the block changes;
 //   * squeeze-excite sums (of the fp32 activation, before the bf16 rounding) stay in registers across tiles and leave the CTA as one global atomic per
 //     channel when the (image, channel block) changes.
+//   (round 2: the sums leave as plain stores into one slot per (image, row group of tiles) -- summed in a fixed
+//    order by octseg_se_hidden -- instead of fp32 atomics: bit-reproducible, and no buffer to re-zero.)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -31,7 +33,8 @@ struct DwParams {
   const __nv_bfloat16* weight;  // [K*K][C]
   const float* bias;            // [C]
   __nv_bfloat16* out;           // [N][Ho][Wo][C]
-  float* pool_sum;              // [N][C] or null
+  float* pool_sum;              // [N][pool_slots][C] partial sums (slot = row group of tiles) or null
+  int pool_slots;
   int C, Ho, Wo, pad_t, pad_l, act;
   // Work order.  A chunk = `chunk_tiles` consecutive tiles of one (image, channel block): one row of
   // tiles, or the whole plane on small maps.  Chunks are dealt round-robin to the persistent CTAs with
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kDwThreads, DwCfg<K, S, CB, SH, SW>::CTAS)
   }
   __syncthreads();
 
-  auto decode = [&](int i, int& cb, int& n, int& th, int& tw) {  // i = local tile index
+  auto decode = [&](int i, int& cb, int& n, int& th, int& tw, int& rg) {  // i = local tile index
     const uint32_t ci = fd_div(static_cast<uint32_t>(i), p.fd_chunk_tiles);
     const uint32_t j = static_cast<uint32_t>(i) - ci * p.fd_chunk_tiles.d;
     const uint32_t chunk = blockIdx.x + ci * gridDim.x;
@@ -98,12 +101,13 @@ __global__ void __launch_bounds__(kDwThreads, DwCfg<K, S, CB, SH, SW>::CTAS)
     uint32_t q = fd_div(chunk, p.fd_cb);
     cb = static_cast<int>(chunk - q * p.fd_cb.d);
     const uint32_t nn = fd_div(q, p.fd_rg);
-    th = static_cast<int>((q - nn * p.fd_rg.d) * p.chunk_rows + jr);
+    rg = static_cast<int>(q - nn * p.fd_rg.d);
+    th = rg * p.chunk_rows + static_cast<int>(jr);
     n = static_cast<int>(nn);
   };
   auto issue = [&](int t, int stage) {  // one elected thread
-    int cb, n, th, tw;
-    decode(t, cb, n, th, tw);
+    int cb, n, th, tw, rg;
+    decode(t, cb, n, th, tw, rg);
     const uint32_t bar = s_bar + 8 * stage;
     mbar_arrive_expect_tx(bar, static_cast<uint32_t>(Cfg::IH * IW * PIX));
     tma_load_4d(s_stage + stage * Cfg::STAGE, &tm_in, bar, cb * CB, tw * Cfg::TW * S - p.pad_l,
@@ -117,13 +121,14 @@ __global__ void __launch_bounds__(kDwThreads, DwCfg<K, S, CB, SH, SW>::CTAS)
   const float wscale = p.act == OCTSEG_ACT_SWISH ? 0.5f : 1.f;
   const uint32_t pix_bytes = static_cast<uint32_t>(p.C) * 2u;
   const size_t row_bytes = static_cast<size_t>(p.Wo) * pix_bytes;
-  int cur_cb = -1, cur_n = -1;
+  int cur_cb = -1, cur_n = -1, cur_rg = -1;
   float2 bias2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   float2 ps[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   bool cvalid = false;
 
-  // SE sums of the finished (image, channel block): registers -> warp shuffle -> shared -> one atomic per channel
-  auto flush_pool = [&](int n, int cb) {
+  // SE sums of the finished chunk (image, row group, channel block): registers -> warp shuffle -> shared -> ONE plain
+  // store per channel into the chunk's own slot (every slot is written exactly once per launch)
+  auto flush_pool = [&](int n, int rg, int cb) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
 #pragma unroll
@@ -144,17 +149,17 @@ __global__ void __launch_bounds__(kDwThreads, DwCfg<K, S, CB, SH, SW>::CTAS)
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < kDwThreads / 32; ++w) s += part[w * CB + tid];
-      atomicAdd(p.pool_sum + static_cast<size_t>(n) * p.C + cb * CB + tid, s);
+      p.pool_sum[(static_cast<size_t>(n) * p.pool_slots + rg) * p.C + cb * CB + tid] = s;
     }
     __syncthreads();
     ps[0] = ps[1] = make_float2(0.f, 0.f);
   };
 
   for (int it = 0; it < n_local; ++it) {
-    int cb, n, th, tw;
-    decode(it, cb, n, th, tw);
+    int cb, n, th, tw, rg;
+    decode(it, cb, n, th, tw, rg);
     if (tid == 0 && it + NST - 1 < n_local) issue(it + NST - 1, (it + NST - 1) % NST);
-    if (p.pool_sum && cur_cb >= 0 && (cb != cur_cb || n != cur_n)) flush_pool(cur_n, cur_cb);
+    if (p.pool_sum && cur_cb >= 0 && (cb != cur_cb || n != cur_n || rg != cur_rg)) flush_pool(cur_n, cur_rg, cur_cb);
     if (cb != cur_cb) {
       // the previous iteration ended with __syncthreads(): nobody still reads the old filters
       for (int i = tid; i < K * K * CB; i += kDwThreads) {
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(kDwThreads, DwCfg<K, S, CB, SH, SW>::CTAS)
       cur_cb = cb;
     }
     cur_n = n;
+    cur_rg = rg;
 
     const int stage = it % NST;
     mbar_wait(s_bar + 8 * stage, static_cast<uint32_t>((it / NST) & 1));
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(kDwThreads, DwCfg<K, S, CB, SH, SW>::CTAS)
     }
     __syncthreads();  // every thread is done with this stage (and with `part`) before it is refilled
   }
-  if (p.pool_sum) flush_pool(cur_n, cur_cb);
+  if (p.pool_sum) flush_pool(cur_n, cur_rg, cur_cb);
 }
 
 template <int K, int S, int CB, int SH, int SW>
@@ -223,6 +229,8 @@ static int launch_dw(const CUtensorMap& tm, DwParams p, int N, int cblocks, cuda
   p.chunk_rows = tiles_w >= 4 ? 1 : tiles_h;          // a row of tiles, or the whole plane on small maps
   p.chunk_tiles = p.chunk_rows * tiles_w;
   const int row_groups = tiles_h / p.chunk_rows;
+  if (p.pool_sum && p.pool_slots != row_groups)
+    return fail(OCTSEG_EINVAL, "dwconv: pool_slots=%d but this shape writes %d slots (octseg_dwconv_pool_slots)", p.pool_slots, row_groups);
   const long long chunks = static_cast<long long>(row_groups) * N * cblocks;
   if (chunks * p.chunk_tiles >= (1ll << 24)) return fail(OCTSEG_EINVAL, "dwconv: too many tiles (%lld)", chunks * p.chunk_tiles);
   p.n_chunks = static_cast<int>(chunks);
@@ -248,9 +256,26 @@ static int launch_dw(const CUtensorMap& tm, DwParams p, int N, int cblocks, cuda
 
 using namespace octseg;
 
+// tile geometry of octseg_dwconv for a shape: channel block, small-map flag, tile extent
+static void dw_tile_config(int C, int Ho, int Wo, int& cb, bool& small, int& TH, int& TW) {
+  cb = C <= 32 ? 32 : 64;
+  small = cb == 64 && Ho <= 32 && Wo <= 32;  // 4 x 32 tiles waste less of 28 x 28 maps than 8 x 16
+  const int sh = cb == 32 ? 4 : (small ? 2 : 4), sw = cb == 32 ? 8 : (small ? 8 : 4);
+  TH = sh * kDwR;
+  TW = sw * kDwP;
+}
+
+extern "C" int octseg_dwconv_pool_slots(int32_t C, int32_t Ho, int32_t Wo) {
+  int cb, TH, TW;
+  bool small;
+  dw_tile_config(C, Ho, Wo, cb, small, TH, TW);
+  const int tiles_w = cdiv(Wo, TW), tiles_h = cdiv(Ho, TH);
+  return tiles_w >= 4 ? tiles_h : 1;
+}
+
 extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bias, void* out, int32_t N, int32_t H,
                              int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad_t, int32_t pad_l,
-                             int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, void* stream) {
+                             int32_t Ho, int32_t Wo, int32_t act, float* pool_sum, int32_t pool_slots, void* stream) {
   if (C % 8) return fail(OCTSEG_EINVAL, "dwconv: C must be a multiple of 8 (C=%d)", C);
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
       (reinterpret_cast<uintptr_t>(bias) & 15))
@@ -279,6 +304,7 @@ extern "C" int octseg_dwconv(const void* in, const void* weight, const float* bi
   p.bias = bias;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.pool_sum = pool_sum;
+  p.pool_slots = pool_slots;
   p.C = C;
   p.Ho = Ho;
   p.Wo = Wo;

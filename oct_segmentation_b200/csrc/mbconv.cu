@@ -55,7 +55,7 @@ struct MbCfg {
 struct MbParams {
   const float* blob;            // [ncb][2 + K*K][64] fp32: b_exp/2, b_dw/2, w_dw/2 per 64-channel block (zero padded)
   __nv_bfloat16* out;           // [N][Ho][Wo][Cmid]
-  float* pool_sum;              // [N][Cmid] or null
+  float* pool_sum;              // [N][tiles_h * tiles_w][Cmid] per-tile partial sums (summed by octseg_se_hidden) or null
   int H, W, Cmid, Ho, Wo, pad_t, pad_l;
   int kch;                      // Cin / 16
   int ncb;                      // ceil(Cmid / 64)
@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(kMbThreads, MbCfg<K, S>::CTAS)
             }
           }
         }
-        // SE sums of this (tile, block): registers -> warp shuffle -> shared -> one atomic per channel
+        // SE sums of this (tile, block): registers -> warp shuffle -> shared -> one plain store per channel into the
+        // tile's own slot (bit-reproducible: octseg_se_hidden adds the slots in order)
         if (p.pool_sum) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(kMbThreads, MbCfg<K, S>::CTAS)
           float sum = 0.f;
 #pragma unroll
           for (int w = 0; w < 8; ++w) sum += part[w * CB + tid];
-          atomicAdd(p.pool_sum + static_cast<size_t>(n) * p.Cmid + cb * CB + tid, sum);
+          p.pool_sum[(static_cast<size_t>(n) * (p.tiles_h * p.tiles_w) + th * p.tiles_w + tw) * p.Cmid + cb * CB + tid] = sum;
         }
       }
     }
@@ -405,6 +406,10 @@ using namespace octseg;
 extern "C" int octseg_mbconv_smem_bytes(int32_t Cin, int32_t k, int32_t stride) {
   if (Cin % 16 || Cin < 16 || (k != 3 && k != 5) || stride != 1) return -1;
   return static_cast<int>(k == 3 ? mb_smem_bytes<3, 1>(Cin / 16) : mb_smem_bytes<5, 1>(Cin / 16));
+}
+
+extern "C" int octseg_mbconv_pool_slots(int32_t k, int32_t Ho, int32_t Wo) {
+  return k == 3 ? cdiv(Ho, MbCfg<3, 1>::TH) * cdiv(Wo, MbCfg<3, 1>::TW) : cdiv(Ho, MbCfg<5, 1>::TH) * cdiv(Wo, MbCfg<5, 1>::TW);
 }
 
 extern "C" int octseg_mbconv_blob_floats(int32_t Cmid, int32_t k) { return cdiv(Cmid, kMbCB) * (2 + k * k) * kMbCB; }

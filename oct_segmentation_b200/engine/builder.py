@@ -318,6 +318,13 @@ class Builder:
         self._add(name, lambda: op, [x], [out], kind='maxpool')
         return out
 
+    def new_pool(self, C: int, k: int, out_hw: Tuple[int, int], fused: bool) -> torch.Tensor:
+        """Squeeze-excite partial-sum buffer fp32 [N][slots][C] for a depthwise (or fused MBConv) launch of this shape:
+        every slot is written exactly once per launch and octseg_se_hidden adds them in order (no atomics)."""
+        slots = (self.lib.octseg_mbconv_pool_slots(k, out_hw[0], out_hw[1]) if fused
+                 else self.lib.octseg_dwconv_pool_slots(C, out_hw[0], out_hw[1]))
+        return torch.zeros(self.N, slots, C, dtype=torch.float32, device=self.device)
+
     def dwconv(self, x: Act, w: torch.Tensor, b: torch.Tensor, *, name: str, k: int, stride: int,
                pad: Tuple[int, int], out_hw: Tuple[int, int], act: str, pool: Optional[torch.Tensor]) -> Act:
         assert x.C % 8 == 0
@@ -327,10 +334,11 @@ class Builder:
         self._keep += [wk, bk]
         lib, a = self.lib, _lib.ACT[act]
 
-        def op():   # `pool` starts zeroed (lower.py) and is re-zeroed by octseg_se_gate after each use
+        def op():   # `pool` (new_pool): write-once slots, summed by octseg_se_hidden
             _lib.check(lib.octseg_dwconv(x.t.data_ptr(), wk.data_ptr(), bk.data_ptr(), out.t.data_ptr(), x.N, x.H,
                                          x.W, x.C, k, stride, pad[0], pad[1], out_hw[0], out_hw[1], a,
-                                         pool.data_ptr() if pool is not None else None, _lib.stream_ptr()), name)
+                                         pool.data_ptr() if pool is not None else None,
+                                         pool.shape[1] if pool is not None else 0, _lib.stream_ptr()), name)
         self.macs += x.N * out_hw[0] * out_hw[1] * x.C * k * k
         self._add(name, lambda: op, [x], [out], kind='dwconv')
         return out
@@ -355,7 +363,7 @@ class Builder:
         self._keep += [wek, blob]
         lib = self.lib
 
-        def op():   # `pool` starts zeroed (lower.py) and is re-zeroed by octseg_se_gate after each use
+        def op():   # `pool` (new_pool): write-once per-tile slots, summed by octseg_se_hidden
             _lib.check(lib.octseg_mbconv_expand_dw(x.t.data_ptr(), x.N, x.H, x.W, cin, x.Cp, wek.data_ptr(), blob.data_ptr(),
                                                    out.t.data_ptr(), cmid, k, stride, pad[0], pad[1], out_hw[0], out_hw[1],
                                                    pool.data_ptr() if pool is not None else None, _lib.stream_ptr()), name)
@@ -377,29 +385,43 @@ class Builder:
         b2d = b2.detach().float().contiguous().to(dev)
         hidden = torch.empty(N, cr, dtype=torch.float32, device=dev)
         gate = torch.empty(N, C_mid, dtype=torch.float32, device=dev)
-        spec = [((N, x.H, x.W, x.C, x.Cp), False)]
-        geom, packed32 = plan_conv(spec, wp, out_hw=(x.H, x.W), packed_dtype=torch.float32)
+        cout = wp.shape[0]
+        cs = pad8(cout)
+        # narrow projections (<= 32 output channels, the 448 x 448 stage): two adjacent pixels per GEMM row, so the
+        # output rows are 128 bytes and K is a whole 64-channel chunk (same memory, wider view; block-diagonal weights)
+        f = 2 if (cs <= 32 and x.Cp <= 64 and x.C == x.Cp and x.W % 2 == 0 and (res is None or res.Cp == cs)) else 1
+        if f > 1:
+            wpk, bpk = pack_conv_weights(wp, bp, [x.C], [x.Cp], f, 0, cs)
+            spec = [((N, x.H, x.W // f, f * x.Cp, f * x.Cp), False)]
+            geom, packed32 = plan_conv(spec, wpk, out_hw=(x.H, x.W // f), packed_dtype=torch.float32)
+            geom.macs = N * x.H * x.W * cout * C_mid                                # dense count of the real op
+            bias_rows = pad_bias(bpk, geom, f * cs)
+        else:
+            spec = [((N, x.H, x.W, x.C, x.Cp), False)]
+            geom, packed32 = plan_conv(spec, wp, out_hw=(x.H, x.W), packed_dtype=torch.float32)
+            bias_rows = pad_bias(bp, geom, cout)
         rows, Ktot = packed32.shape[1], packed32.shape[2]
         base = packed32[0].contiguous().to(dev)                                    # fp32 [rows][Ktot]
         wn = self.new_scratch((N, rows, Ktot), torch.bfloat16)                     # per-image weights: dead after the conv
-        cout = wp.shape[0]
         out = self.new_act(x.H, x.W, cout)
-        bias_rows = pad_bias(bp, geom, cout)
         self._keep += [w1d, b1d, w2d, b2d, hidden, gate, base]
         lib, inv_hw = self.lib, 1.0 / float(x.H * x.W)
 
         def gate_op():
             st = _lib.stream_ptr()
-            _lib.check(lib.octseg_se_hidden(pool.data_ptr(), inv_hw, w1d.data_ptr(), b1d.data_ptr(), hidden.data_ptr(),
-                                            N, C_mid, cr, st), name + '.se_hidden')
+            _lib.check(lib.octseg_se_hidden(pool.data_ptr(), pool.shape[1], gate.data_ptr(), inv_hw, w1d.data_ptr(), b1d.data_ptr(),
+                                            hidden.data_ptr(), N, C_mid, cr, st), name + '.se_hidden')   # `gate` doubles as the [N][C] sums scratch
             _lib.check(lib.octseg_se_gate(hidden.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gate.data_ptr(),
-                                          pool.data_ptr(), N, C_mid, cr, st), name + '.se_gate')
+                                          None, N, C_mid, cr, st), name + '.se_gate')
             _lib.check(lib.octseg_se_scale_weights(gate.data_ptr(), base.data_ptr(), wn.t.data_ptr(), N, rows, Ktot,
-                                                   C_mid, st), name + '.se_scale_weights')
+                                                   f * C_mid, C_mid, st), name + '.se_scale_weights')
         self.macs += N * 2 * C_mid * cr
-        self._add(name + '.se', lambda: gate_op, [], [wn], launches=3, kind='se')
-        self._add_conv(name, geom, lambda: ConvPlan(geom, wn.t, bias_rows, [x.t], out.t, act='none',
-                                                    res=res.t if res is not None else None,
-                                                    res_mode='before_act' if res is not None else 'none',
-                                                    per_image_weights=True, name=name), [x, res, wn], [out])
+        self._add(name + '.se', lambda: gate_op, [], [wn], launches=3 + int(pool.shape[1] > 1), kind='se')
+        def make_plan():
+            def pk(t):      # the pixel-packed view of an NHWC tensor
+                return t.view(t.shape[0], t.shape[1], t.shape[2] // f, f * t.shape[3]) if f > 1 else t
+            return ConvPlan(geom, wn.t, bias_rows, [pk(x.t)], pk(out.t), act='none',
+                            res=pk(res.t) if res is not None else None,
+                            res_mode='before_act' if res is not None else 'none', per_image_weights=True, name=name)
+        self._add_conv(name, geom, make_plan, [x, res, wn], [out])
         return out

@@ -97,8 +97,10 @@ def lower_efficientnet(b: Builder, enc, x: torch.Tensor, in_dtype: str, norm) ->
         cmid = blk._depthwise_conv.weight.shape[0]
         oh = (y.H + pt + pb - blk.k) // blk.stride + 1
         ow = (y.W + pt + pb - blk.k) // blk.stride + 1
-        pool = torch.zeros(b.N, cmid, dtype=torch.float32, device=b.device)
-        if blk.expand != 1 and cur.C in FUSE_MBCONV and blk.stride == 1 and cur.C % 16 == 0 and b.mbconv_fits(cur.C, blk.k, blk.stride):
+        fuse = (blk.expand != 1 and cur.C in FUSE_MBCONV and blk.stride == 1 and cur.C % 16 == 0
+                and b.mbconv_fits(cur.C, blk.k, blk.stride))
+        pool = b.new_pool(cmid, blk.k, (oh, ow), fuse)          # fp32 [N][slots][C] partial sums for the SE mean
+        if fuse:
             # expand 1x1 -> depthwise in one launch: the 6x-wide tensor stays on chip (csrc/mbconv.cu)
             we, be = fold_bn(blk._expand_conv.weight, blk._bn0)
             y = b.mbconv_expand_dw(y, we, be, wd, bd, name=nm + '._depthwise_conv', k=blk.k, stride=blk.stride,

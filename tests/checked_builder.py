@@ -20,7 +20,7 @@ class CheckedBuilder(Builder):
         super().__init__(device, N, reuse=False)     # the references re-read inputs that would otherwise be dead
         self.ref = Bf16Builder(N, device)
         self.checks = []
-        self._pools = {}        # '<name>.se' -> live SE pool tensor (the gate kernel zeroes it after use)
+        self._pools = {}        # '<name>.se' -> SE partial-sum buffer [N][slots][C] of that block
         self._pool_snap = {}    # '<name>' -> its contents just before the SE launches
 
     def stem(self, x, in_dtype, w, b, **k):
@@ -60,7 +60,7 @@ class CheckedBuilder(Builder):
             kk = dict(k)
             kk['pool'] = torch.zeros_like(pool)
             r = _nchw(self.ref.dwconv(x, w, b, **kk))
-            self._last_pool_err = _rel(pool, kk['pool'])
+            self._last_pool_err = _rel(pool.sum(1), kk['pool'].sum(1))
             return r
         self.checks.append((k['name'], ref_fn, lambda: _nchw(out)))
         return out
@@ -73,7 +73,7 @@ class CheckedBuilder(Builder):
             kk = dict(k)
             kk['pool'] = torch.zeros_like(pool)
             r = _nchw(self.ref.mbconv_expand_dw(x, we, be, wd, bd, **kk))
-            self._last_pool_err = _rel(pool, kk['pool'])
+            self._last_pool_err = _rel(pool.sum(1), kk['pool'].sum(1))
             return r
         self.checks.append((k['name'], ref_fn, lambda: _nchw(out)))
         return out

@@ -67,8 +67,12 @@ class CpuBuilder:
         pb = (out_hw[0] - 1) * stride + k - H - pad[0]
         pr = (out_hw[1] - 1) * stride + k - W - pad[1]
         y = act_fn(F.conv2d(F.pad(xin, (pad[1], max(pr, 0), pad[0], max(pb, 0))), w, b, stride=stride, groups=x.C), act)
-        pool.copy_(y.sum(dim=(2, 3)))
+        pool.zero_()
+        pool[:, 0].copy_(y.sum(dim=(2, 3)))
         return _act(y)
+
+    def new_pool(self, C, k, out_hw, fused):
+        return torch.zeros(self.N, 1, C, device=self.device)
 
     def mbconv_fits(self, cin, k, stride):
         return stride == 1 and cin % 16 == 0 and cin <= 160
@@ -81,7 +85,7 @@ class CpuBuilder:
     def se_project(self, x, pool, w1, b1, w2, b2, wp, bp, *, name, res):
         xin = _nchw(x)
         w1, b1, w2, b2, wp, bp = (self._d(t) for t in (w1, b1, w2, b2, wp, bp))
-        mean = pool / float(x.H * x.W)
+        mean = pool.sum(1) / float(x.H * x.W)
         h = F.linear(mean, w1.flatten(1), b1)
         h = h * torch.sigmoid(h)
         gate = torch.sigmoid(F.linear(h, w2.flatten(1), b2))
@@ -115,13 +119,14 @@ class Bf16Builder(CpuBuilder):
     def dwconv(self, x, w, b, **k):
         a = super().dwconv(x, _r16(w.detach().float()), b, **k)        # the kernel keeps dw weights in bf16
         a.t = _r16(a.t)
-        k['pool'].copy_(a.t[..., :a.C].sum(dim=(1, 2)))     # the kernel pools the rounded values
+        k['pool'].zero_()
+        k['pool'][:, 0].copy_(a.t[..., :a.C].sum(dim=(1, 2)))
         return a
 
     def se_project(self, x, pool, w1, b1, w2, b2, wp, bp, **k):
         xin = _nchw(x)
         w1, b1, w2, b2, wp, bp = (self._d(t) for t in (w1, b1, w2, b2, wp, bp))
-        mean = pool / float(x.H * x.W)
+        mean = pool.sum(1) / float(x.H * x.W)
         h = F.linear(mean, w1.flatten(1), b1)
         h = h * torch.sigmoid(h)
         gate = torch.sigmoid(F.linear(h, w2.flatten(1), b2))

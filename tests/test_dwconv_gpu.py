@@ -32,9 +32,11 @@ def test_dwconv_matches_torch(case, act):
     ph, pw = max((Ho - 1) * s + k - H, 0), max((Wo - 1) * s + k - W, 0)
     pt, pl = ph // 2, pw // 2
     out = torch.full((N, Ho, Wo, C), float('nan'), dtype=torch.bfloat16, device='cuda')
-    pool = torch.zeros(N, C, device='cuda')
+    slots = lib.octseg_dwconv_pool_slots(C, Ho, Wo)
+    pool3 = torch.full((N, slots, C), float('nan'), device='cuda')       # every slot must be written (no zeroing contract)
     _lib.check(lib.octseg_dwconv(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), N, H, W, C, k, s, pt, pl,
-                                 Ho, Wo, _lib.ACT[act], pool.data_ptr(), torch.cuda.current_stream().cuda_stream), 'dw')
+                                 Ho, Wo, _lib.ACT[act], pool3.data_ptr(), slots, torch.cuda.current_stream().cuda_stream), 'dw')
+    pool = pool3.sum(1)
     torch.cuda.synchronize()
     xin = F.pad(x.float().permute(0, 3, 1, 2), (pl, pw - pl, pt, ph - pt))
     ref = F.conv2d(xin, w.float().permute(2, 0, 1).unsqueeze(1), b, stride=s, groups=C)
@@ -58,9 +60,33 @@ def test_dwconv_without_pool_and_repeatable():
     for _ in range(2):
         out = torch.empty(2, 24, 24, 96, dtype=torch.bfloat16, device='cuda')
         _lib.check(lib.octseg_dwconv(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), 2, 24, 24, 96, 3, 1, 1, 1,
-                                     24, 24, _lib.ACT['relu'], None, torch.cuda.current_stream().cuda_stream), 'dw')
+                                     24, 24, _lib.ACT['relu'], None, 0, torch.cuda.current_stream().cuda_stream), 'dw')
         outs.append(out)
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1])
     ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(2, 0, 1).unsqueeze(1), b, padding=1, groups=96))
     assert ((outs[0].float().permute(0, 3, 1, 2) - ref).norm() / ref.norm()).item() <= 4e-3
+
+
+def test_dwconv_pool_sums_are_bit_reproducible():
+    """The squeeze-excite sums leave the kernel as write-once slots added in a fixed order (no fp32 atomics): two runs
+    on a map with many row groups give identical bits, and a slot count other than the kernel's own is refused."""
+    lib = _lib.load()
+    N, H, C = 3, 112, 480
+    x = torch.randn(N, H, H, C).to(torch.bfloat16).cuda()
+    w = (torch.randn(5, 5, C) * 0.2).to(torch.bfloat16).cuda()
+    b = torch.randn(C).cuda()
+    out = torch.empty(N, H, H, C, dtype=torch.bfloat16, device='cuda')
+    slots = lib.octseg_dwconv_pool_slots(C, H, H)
+    assert slots == 14
+    pools = []
+    for _ in range(2):
+        pool = torch.full((N, slots, C), float('nan'), device='cuda')
+        _lib.check(lib.octseg_dwconv(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), N, H, H, C, 5, 1, 2, 2, H, H,
+                                     _lib.ACT['swish'], pool.data_ptr(), slots, torch.cuda.current_stream().cuda_stream), 'dw')
+        pools.append(pool)
+    torch.cuda.synchronize()
+    assert torch.isfinite(pools[0]).all() and torch.equal(pools[0], pools[1])
+    rc = lib.octseg_dwconv(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), N, H, H, C, 5, 1, 2, 2, H, H,
+                           _lib.ACT['swish'], pools[0].data_ptr(), slots + 1, torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b'pool_slots' in lib.octseg_last_error()

@@ -40,12 +40,14 @@ def test_mbconv_expand_dw_matches_torch(case):
     bd = (torch.randn(cmid, generator=g) * 0.5).cuda()
     p = (k - 1) // 2
     out = torch.full((N, H, W, cmid), float('nan'), dtype=torch.bfloat16, device='cuda')
-    pool = torch.zeros(N, cmid, device='cuda')
+    slots = lib.octseg_mbconv_pool_slots(k, H, W)
+    pool3 = torch.full((N, slots, cmid), float('nan'), device='cuda')   # every slot must be written (no zeroing contract)
     blob = _lib.mbconv_blob(be, wd, bd, k).cuda()
     assert blob.numel() == lib.octseg_mbconv_blob_floats(cmid, k)
     _lib.check(lib.octseg_mbconv_expand_dw(x.data_ptr(), N, H, W, cin, ldc, we.data_ptr(), blob.data_ptr(), out.data_ptr(),
-                                           cmid, k, 1, p, p, H, W, pool.data_ptr(), torch.cuda.current_stream().cuda_stream), 'mbconv')
+                                           cmid, k, 1, p, p, H, W, pool3.data_ptr(), torch.cuda.current_stream().cuda_stream), 'mbconv')
     torch.cuda.synchronize()
+    pool = pool3.sum(1)
     xin = x[..., :cin].float().permute(0, 3, 1, 2)
     e = swish(F.conv2d(xin, we.float()[:, :, None, None], be)).to(torch.bfloat16).float()      # stored as bf16 when unfused
     ref = swish(F.conv2d(e, wd.float().permute(2, 0, 1).unsqueeze(1), bd, padding=p, groups=cmid))

@@ -116,6 +116,30 @@ def test_network_matches_oracle(key):
     assert agree >= 0.9995, f'{key}: confident-pixel mask agreement {agree:.5f}'
 
 
+@pytest.mark.parametrize('key', ['LM', 'VV', 'FC_LC'])
+def test_logits_are_bit_reproducible_and_independent_of_buffer_reuse(key):
+    """(1) Two replays on the same input give identical bits -- including FC_LC, whose squeeze-excite sums are
+    write-once slots added in a fixed order (round 1 accumulated them with fp32 atomics).  (2) The activation arena
+    (buffers recycled by liveness, engine/builder.py) changes nothing: a plan whose every activation owns its bytes
+    produces the same logits bit for bit."""
+    ref, ours = build_pair(key)
+    size = 192
+    x = torch.from_numpy(frames_bgr(2, size)).cuda()
+    outs = []
+    for reuse in (True, False):
+        net = CompiledNet(ours.model, 2, size, size, x.device, 'u8', 'f32_nchw', use_graph=reuse, reuse=reuse)
+        net.x_nhwc.copy_(x)
+        a = net.run().clone()
+        net.x_nhwc.copy_(x)
+        b = net.run().clone()
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), f'{key}: two runs differ (reuse={reuse})'
+        outs.append(a)
+        if reuse:
+            assert net.arena_bytes < 0.5 * net.act_bytes
+    assert torch.equal(outs[0], outs[1]), f'{key}: logits depend on activation-buffer reuse'
+
+
 def test_forward_normalises_like_reference():
     """OCTSegmentationModel.forward = (x - mean)/std then net (model.py:65-71)."""
     ref, ours = build_pair('LM')

@@ -24,13 +24,14 @@ def main():
         b = torch.zeros(C, device='cuda')
         Ho = H // s
         out = torch.empty(N, Ho, Ho, C, dtype=torch.bfloat16, device='cuda')
-        pool = torch.zeros(N, C, device='cuda')
+        slots = lib.octseg_dwconv_pool_slots(C, Ho, Ho)
+        pool = torch.zeros(N, slots, C, device='cuda')
         pad = max((Ho - 1) * s + k - H, 0) // 2
         st = torch.cuda.current_stream().cuda_stream
 
         def run():
             _lib.check(lib.octseg_dwconv(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), N, H, H, C, k, s, pad, pad,
-                                         Ho, Ho, 2, pool.data_ptr(), st), 'dw')
+                                         Ho, Ho, 2, pool.data_ptr(), slots, st), 'dw')
         for _ in range(3):
             run()
         torch.cuda.synchronize()

@@ -42,7 +42,7 @@ def main():
         wd = (torch.randn(k, k, cmid) * 0.3).to(torch.bfloat16).cuda()
         bd = torch.randn(cmid, device='cuda') * 0.1
         out = torch.empty(N, H, H, cmid, dtype=torch.bfloat16, device='cuda')
-        pool = torch.zeros(N, cmid, device='cuda')
+        pool = torch.zeros(N, max(lib.octseg_mbconv_pool_slots(k, H, H), lib.octseg_dwconv_pool_slots(cmid, H, H)), cmid, device='cuda')
         row = dict(case=nm, batch=N, cin=cin, cmid=cmid, k=k, H=H, out_MB=round(out.numel() * 2 / 1e6, 1))
         if lib.octseg_mbconv_smem_bytes(cin, k, 1) <= 227 * 1024:
             blob = _lib.mbconv_blob(be, wd, bd, k).cuda()
@@ -60,7 +60,7 @@ def main():
             def unfused():
                 plan.run()
                 _lib.check(lib.octseg_dwconv(e.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), N, H, H, cmid, k, 1, p, p,
-                                             H, H, _lib.ACT['swish'], pool.data_ptr(), st), 'dw')
+                                             H, H, _lib.ACT['swish'], pool.data_ptr(), lib.octseg_dwconv_pool_slots(cmid, H, H), st), 'dw')
             row['unfused_ms'] = round(timed(unfused), 4)
         print(json.dumps(row), flush=True)
 
