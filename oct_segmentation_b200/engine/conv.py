@@ -292,6 +292,22 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
         if (sg.mul == 1 and sg.kh * sg.kw >= 4 and sg.kh <= 7 and sg.kw <= 7 and b_bytes <= HALO_B_BYTES
                 and Hq * Wq >= 0.75 * cover):
             halo, TH, TW = 1, 16, 8
+    if (TH != 1 and WIDE_BOXES and not halo and phases == 1 and not transposed and BN <= 128
+            and all(sg.kc == 64 and sg.mul == 1 and sg.kw >= 2 and (sg.c_per_tile == 0 or sg.cchunks == 1) for sg in segs)):
+        # k x k conv over wide sources with few output channels and no resident-weight (halo) form: L2 -> shared-memory
+        # traffic bounds it (every tap re-reads its A tile).  A ROW tile lets the kw taps of a tap row share one box
+        # (wide boxes below: 3x less A traffic), which pays even when the row does not fill the 128 MMA rows:
+        # 168 -> 64 @224^2 (U-Net decoder skip conv): 0.86 ms with 4 x 32 tiles, 0.43 ms with 1 x 112 (tools/ab/tile_test.py)
+        kw_max = max(sg.kw for sg in segs)
+        best_tw, best_eff = 0, 0.0
+        for tw in range(16, min(Wq, 128) + 1):
+            if tw + kw_max - 1 > 136:
+                break
+            eff = Wq / (-(-Wq // tw) * tw) * tw / 128.0
+            if eff >= best_eff:
+                best_tw, best_eff = tw, eff
+        if best_eff >= 0.8:
+            TH, TW = 1, best_tw
     if TH == 1 and WIDE_BOXES and not halo:
         # activation-traffic saver for L2-bound shapes: the B stage then holds kw weight tiles
         for sg in segs:
