@@ -1,6 +1,8 @@
 """Turn ncu outputs under gpurun_out/ into the small text/JSON summaries committed under profiles/.
 
-  python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv profiles/launches_r1_summary.md 32   (32 = bench batch)
+  python tools/summarize_ncu.py launches gpurun_out/launches_r2.csv profiles/launches_r2_summary.md 32 [config]   (32 = bench batch)
+      also writes profiles/launches_r2_traffic.json (dram bytes per conv_tc_kernel launch), stamped with the sha1 of the
+      liboctseg.so it was measured on: bench.py only quotes it as roofline.traffic when the library is the same build
   python tools/summarize_ncu.py full gpurun_out/prof_x.ncu-rep profiles/prof_x_r1.txt
 """
 import collections
@@ -17,7 +19,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__cycles_elapsed.max', 'smsp__inst_executed.sum', 'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct']
 
 
-def launches(src, dst, batch=None):
+def launches(src, dst, batch=None, config='ensemble'):
     rows = list(csv.reader(open(src)))
     hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
     h = rows[hi]
@@ -50,8 +52,13 @@ def launches(src, dst, batch=None):
     open(dst, 'w').write('\n'.join(out) + '\n')
     tc = next((v for k, v in agg.items() if k.split('::')[-1] == 'conv_tc_kernel'), None)
     if tc:
+        import hashlib
+        import os
+        lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oct_segmentation_b200', 'liboctseg.so')
+        sha = hashlib.sha1(open(lib, 'rb').read()).hexdigest()[:16] if os.path.exists(lib) else ''
         json.dump({'kernel': 'conv_tc_kernel', 'launches': tc[0], 'dram_bytes_per_launch': tc[2] / tc[0],
-                   'share_of_kernel_time': tc[1] / tot, 'source': src, 'batch': int(batch) if batch else None}, open(dst.replace('_summary.md', '_traffic.json'), 'w'))
+                   'share_of_kernel_time': tc[1] / tot, 'source': src, 'batch': int(batch) if batch else None, 'config': config,
+                   'lib_sha16': sha}, open(dst.replace('_summary.md', '_traffic.json'), 'w'))
     print('\n'.join(out))
 
 
