@@ -71,7 +71,7 @@ def preprocess_images(images: List[Image.Image], input_size: int, device: str = 
 
 def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Sequence[int], classes: Sequence[str],
             models_dir: str, device: str, batch_size: int = 16, models: Dict = None,
-            quantities: List = None, pipe: EnsemblePipeline = None, pool=None) -> List[np.ndarray]:
+            quantities: List = None, pipe: EnsemblePipeline = None, pool=None, ratio: int = None) -> List[np.ndarray]:
     """Perform segmentation for given images using specified models; fills and returns ``masks``
     (the caller's float64 HxWx4 arrays), channel CLASS_IDS[name]-1 per requested class.
 
@@ -111,7 +111,7 @@ def segment(images: List[Image.Image], masks: List[np.ndarray], output_size: Seq
             for i in range(lo, hi):
                 fill(i)
         if quantities is not None:
-            ratio = P.dicom_ratio(pipe.Ho)
+            ratio = P.dicom_ratio(pipe.Ho) if ratio is None else ratio      # analysis.py:155 (the DICOM's height when known)
             quantities.extend(P.quantities_from_counts(counts, pipe.Ho, pipe.Wo, ratio, radii,
                                                        contours[0] if contours else None, masks=mask))
     return masks

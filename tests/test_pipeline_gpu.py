@@ -3,6 +3,8 @@ the oracle restatement of /root/reference/src/predict.py on the same synthetic c
 import json
 import os
 
+import cv2
+
 import numpy as np
 import pytest
 import torch
@@ -238,3 +240,47 @@ def test_pipeline_contour_quantities(model_pairs):
                     assert row[name]['contour_thickness_min'] == t['min'] / ratio
                 else:
                     assert 'contour_thickness_mean' not in row[name]
+
+
+def test_dicom_volume_analysis_matches_reference_formulas():
+    """analysis.analyse_volume = get_analysis's data path (src/app/tools/analysis.py:139-213) with its
+    `TODO: run inference` filled in by the GPU ensemble.  A synthetic 16-bit grayscale volume (a gap of empty slices
+    in the middle) -> per-slice cv2 min-max normalise + BGR2RGB (the reference's two calls) -> segment() -> objects
+    table.  Checked against the oracle's restatement of the same formulas applied to the masks the pipeline produced:
+    slices, object ids, area = sqrt(nnz // ratio) with the DICOM's ratio, contour thickness,
+    and the base64 PNG of every present class mask."""
+    import base64
+    from io import BytesIO
+    from PIL import Image
+    from oct_segmentation_b200 import analysis, predict as PR, synthetic
+    from oracle import prepost_ref as R
+    dev = torch.device('cuda')
+    models = synthetic.random_models(dev, input_size=128)
+    n, S = 6, 160
+    vol = np.stack([synthetic.synthetic_frame(900 + i, S)[..., 0].astype(np.uint16) * 200 for i in range(n)])
+    vol[2:4] = 0                                                     # empty slices: every class absent there
+    out = [250, 250]
+    data = analysis.analyse_volume(vol, models, output_size=out, batch_size=4)
+    assert data['ratio'] == int(S * 150 // 1000) and data['images'] == [f'{i + 1:03d}' for i in range(n)]
+    # the masks, recomputed through the same public call on the same normalised frames
+    images = [Image.fromarray(analysis.normalise_slice(vol[i])).resize(tuple(out)) for i in range(n)]
+    assert np.array_equal(np.asarray(analysis.normalise_slice(vol[0]))[..., 0],
+                          cv2.normalize(vol[0], None, alpha=0, beta=255, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_8U))
+    masks = [np.zeros((out[1], out[0], 4)) for _ in range(n)]
+    PR.segment(images, masks, out, analysis.CLASS_NAMES, '', 'cuda', batch_size=4, models=models)
+    m8 = [(m != 0).astype(np.uint8) * 255 for m in masks]
+    some = False
+    for c, name in enumerate(analysis.CLASS_NAMES):
+        present = [R.class_present(np.ascontiguousarray(m[:, :, c])) for m in m8]
+        obj = data['objects'][name]
+        assert obj['slice'] == [i for i, p in enumerate(present) if p]
+        assert obj['object_id'] == R.object_ids(present)
+        want = [R.frame_quantities(m, data['ratio'])[name] for m, p in zip(m8, present) if p]
+        assert obj['area'] == [w['area'] for w in want]
+        assert obj['thickness_mean'] == [w['thickness_mean'] for w in want]
+        assert obj['thickness_min'] == [w['thickness_min'] for w in want]
+        assert obj['img_name'] == [f'{i + 1:03d}' for i, p in enumerate(present) if p]
+        for b64, idx in zip(obj['masks'], obj['slice']):
+            assert np.array_equal(np.asarray(Image.open(BytesIO(base64.b64decode(b64)))), m8[idx][:, :, c])
+        some |= len(obj['slice']) > 0
+    assert some, 'no class present in any slice: the test volume is degenerate'
