@@ -335,7 +335,7 @@ def ours_arm(args):
 
     # ---------------------------------------------------------------- rooflines (rank 0, after the timed regions)
     roof = kernels = per_net = prepost = None
-    if rank == 0:
+    if rank == 0 and not args.no_rooflines:
         peak_tf, peak_hbm, peak_src = peaks()
         kernels, per_net = kernel_rooflines(pipe, B, peak_tf, peak_hbm)
         prepost = prepost_rooflines(pipe, dev_batches[0], B, peak_hbm)
@@ -506,6 +506,8 @@ def main():
     ap.add_argument('--io-workers', type=int, default=os.cpu_count() or 8)
     ap.add_argument('--cpu-frames', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-rooflines', action='store_true',
+                    help='skip the instrumented per-launch passes (for the ncu launch list: only the timed steps run)')
     args = ap.parse_args()
     _claim_stdout()
     if args.e2e_files > 0:

@@ -302,3 +302,27 @@ def test_activation_arena_of_a_lowered_network_reuses_dead_buffers():
             b0, b1, blo, bhi = spans[j]
             if not (ahi < blo or bhi < alo):
                 assert a1 <= b0 or b1 <= a0
+
+
+def test_dicom_front_end_normalises_like_the_reference_and_needs_pydicom_only_for_files():
+    """analysis.normalise_slice = the reference's two cv2 calls (src/app/tools/analysis.py:166-177); a file path needs
+    pydicom (absent offline: a clear ImportError), an in-memory pixel array does not."""
+    import cv2
+    from oct_segmentation_b200 import analysis
+    rng = np.random.default_rng(0)
+    g16 = rng.integers(100, 4000, (40, 48), dtype=np.uint16)
+    want = cv2.cvtColor(cv2.cvtColor(cv2.normalize(g16, None, alpha=0, beta=255, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_8U),
+                                     cv2.COLOR_GRAY2BGR), cv2.COLOR_BGR2RGB)
+    got = analysis.normalise_slice(g16)
+    assert got.dtype == np.uint8 and got.shape == (40, 48, 3) and np.array_equal(got, want)
+    assert got.min() == 0 and got.max() == 255
+    c8 = rng.integers(0, 200, (32, 32, 3), dtype=np.uint8)
+    want = cv2.cvtColor(cv2.normalize(c8, None, alpha=0, beta=255, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_8U), cv2.COLOR_BGR2RGB)
+    assert np.array_equal(analysis.normalise_slice(c8), want)
+    try:
+        import pydicom  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match='pydicom'):
+            analysis.analyse_volume('/nonexistent/study.dcm', models={})
+    with pytest.raises(ValueError):
+        analysis.analyse_volume(np.zeros((4, 4), np.uint8), models={})
