@@ -239,8 +239,8 @@ def prepost_rooflines(pipe, frames_dev, B, peak_hbm):
     for d in pipe.model_dirs:
         S = pipe.sizes[d]
         net = pipe.nets[d]
-        pre_ms += timed(lambda: P.preprocess(frames_dev, S, out=net.x_nhwc))
-        pre_bytes += B * (3.0 * Hs * Ws + 3.0 * S * S)
+        pre_ms += timed(lambda: P.preprocess_s2d(frames_dev, S, out=net.x_s2d))     # resize + BGR + stem packing, one pass
+        pre_bytes += B * (3.0 * Hs * Ws + 6.0 * S * S)                              # uint8 source in, bf16 NHWC out
     out['preprocess'] = {'ms_per_batch': pre_ms, 'gbs_algorithmic': pre_bytes / pre_ms / 1e6, 'frac_of_hbm_peak': pre_bytes / pre_ms / 1e6 / peak_hbm}
     planes = {}
     from oct_segmentation_b200.pipeline import MODELS_META

@@ -203,6 +203,15 @@ int octseg_preprocess_resize_bgr(const uint8_t* src /* [N][Hs][Ws][3] RGB */, in
                                  const int32_t* xofs, const int16_t* xalpha, const int32_t* yofs,
                                  const int16_t* ybeta, int32_t area_fast_2x, void* stream);
 
+/* The same resize written straight into the stem's input format (what octseg_stem_pack produces for a uint8 frame
+   without normalisation): dst = bf16 [N][S/2][S/2][16], channel (dy*2 + dx)*3 + c = pixel (2y+dy, 2x+dx), channel c of
+   the BGR frame preprocessing_img returns (src/data/utils.py:159-166), channels 12..15 zero.  uint8 -> bf16 is exact, so
+   this is octseg_preprocess_resize_bgr + octseg_stem_pack in one pass over the frame (predict path, model.py:192).
+   channels: 3 (RGB source) or 1 (grayscale, replicated).  S even, dst 16-byte aligned. */
+int octseg_preprocess_resize_s2d(const uint8_t* src, int32_t channels, int32_t N, int32_t Hs, int32_t Ws, void* dst,
+                                 int32_t S, const int32_t* xofs, const int16_t* xalpha, const int32_t* yofs,
+                                 const int16_t* ybeta, int32_t area_fast_2x, void* stream);
+
 /* Grayscale extension ("grayscale-to-3ch"; the reference replicates channels only in
    dataset prep, src/data/utils.py:111): src is uint8 [N][Hs][Ws] and the resized plane is written to all three
    channels of dst -- identical to octseg_preprocess_resize_bgr on the channel-replicated frame. */

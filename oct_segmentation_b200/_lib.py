@@ -24,7 +24,7 @@ EXPORTS = [
     'octseg_stem_pack', 'octseg_maxpool3x3s2', 'octseg_dwconv', 'octseg_se_hidden',
     'octseg_se_gate', 'octseg_se_scale_weights', 'octseg_preprocess_resize_bgr', 'octseg_postprocess',
     'octseg_radial_thickness', 'octseg_overlay', 'octseg_preprocess_resize_gray',
-    'octseg_fold_average_threshold', 'octseg_contour_largest', 'octseg_mbconv_expand_dw', 'octseg_mbconv_smem_bytes', 'octseg_mbconv_blob_floats', 'octseg_mbconv_pool_slots', 'octseg_dwconv_pool_slots',
+    'octseg_fold_average_threshold', 'octseg_contour_largest', 'octseg_mbconv_expand_dw', 'octseg_mbconv_smem_bytes', 'octseg_mbconv_blob_floats', 'octseg_mbconv_pool_slots', 'octseg_dwconv_pool_slots', 'octseg_preprocess_resize_s2d',
 ]
 
 
@@ -91,6 +91,9 @@ def load() -> C.CDLL:
                                    C.c_int32, C.c_void_p]
     lib.octseg_se_scale_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_int32, C.c_int32, C.c_void_p]
+    lib.octseg_preprocess_resize_s2d.argtypes = [
+        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.octseg_preprocess_resize_bgr.argtypes = [
         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]

@@ -54,7 +54,7 @@ struct DwCfg {
   static constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;  // input tile incl. halo
   static constexpr int PIX = CB * 2;                           // bytes per pixel in the tile
   static constexpr int STAGE = (IH * IW * PIX + 127) / 128 * 128;
-  static constexpr int CTAS = S == 1 ? (K == 3 ? 3 : 2) : 1;  // resident CTAs per SM (registers + shared memory)
+  static constexpr int CTAS = S == 1 ? 2 : 1;  // resident CTAs per SM (registers + shared memory; 3 for k = 3 fits in 80 registers but measured 2 % slower)
   static constexpr int NST = S == 1 ? 3 : 2;
   static constexpr int WSM = K * K * CB * 4;                   // fp32 filters
   static constexpr int PART = (kDwThreads / 32) * CB * 4;      // per-warp SE partial sums

@@ -21,43 +21,12 @@ __device__ __forceinline__ void stage_row(uint8_t* dst, const uint8_t* __restric
   }
 }
 
-// cv2's uint8 bilinear: horizontal pass in int32 with 11-bit coefficients, vertical pass
-//   dst = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
-// One block per destination row: its two source rows are staged in shared memory with 16-byte loads,
-// a thread produces 4 destination pixels (12 bytes, written as three 32-bit words, BGR order) from
-// byte reads of the staged rows and one 16-byte read of each coefficient table.
-// CS = source channels: 3 (RGB, swapped to BGR) or 1 (grayscale, replicated into the three output channels: the
-// documented extension of SURVEY.md section 8a -- resizing a replicated frame == replicating the resized plane).
-constexpr int kPreThreads = 256;
+// Four consecutive destination pixels (4q .. 4q+3, clamped at S-1) of one destination row from its two staged source
+// rows: 12 bytes in BGR order.  cv2's uint8 bilinear arithmetic (see the kernel below), or its 2x2 area fast path.
 template <int CS>
-__global__ void __launch_bounds__(kPreThreads) preprocess_resize_bgr_kernel(
-    const uint8_t* __restrict__ src, int Hs, int Ws, uint8_t* __restrict__ dst, int S, const int* __restrict__ xofs,
-    const short* __restrict__ xalpha, const int* __restrict__ yofs, const short* __restrict__ ybeta, int area2x) {
-  extern __shared__ __align__(16) uint8_t rows[];  // [2][row_pitch]
-  const int dy = blockIdx.x, n = blockIdx.y;
-  const int row_bytes = Ws * CS, pitch = (row_bytes + 15) & ~15;
-  const uint8_t* img = src + static_cast<size_t>(n) * Hs * row_bytes;
-  int y0, y1, b0 = 0, b1 = 0;
-  if (area2x) {  // cv2 switches INTER_LINEAR to the fast 2x2 area average when both scales are exactly 2
-    y0 = 2 * dy;
-    y1 = 2 * dy + 1;
-  } else {
-    const int sy = yofs[dy];
-    y0 = min(max(sy, 0), Hs - 1);
-    y1 = min(max(sy + 1, 0), Hs - 1);
-    b0 = ybeta[2 * dy];
-    b1 = ybeta[2 * dy + 1];
-  }
-  stage_row(rows, img + static_cast<size_t>(y0) * row_bytes, row_bytes);
-  stage_row(rows + pitch, img + static_cast<size_t>(y1) * row_bytes, row_bytes);
-  __syncthreads();
-  const uint8_t* r0 = rows;
-  const uint8_t* r1 = rows + pitch;
-  uint8_t* drow = dst + (static_cast<size_t>(n) * S + dy) * S * 3;
-  const bool vec = (S & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(xofs) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(xalpha) & 15) == 0;
-  for (int q = threadIdx.x; q < (S + 3) / 4; q += kPreThreads) {
-    uint8_t o[12];
+__device__ __forceinline__ void resize_quad(const uint8_t* r0, const uint8_t* r1, int Ws, int S, const int* __restrict__ xofs,
+                                            const short* __restrict__ xalpha, int b0, int b1, int area2x, bool vec, int q,
+                                            uint8_t (&o)[12]) {
     int sx[4] = {0, 0, 0, 0}, al[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (!area2x) {
       if (vec) {
@@ -103,6 +72,46 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_resize_bgr_kernel(
       o[3 * p + 1] = v[CS / 2];
       o[3 * p + 2] = v[0];
     }
+}
+
+// cv2's uint8 bilinear: horizontal pass in int32 with 11-bit coefficients, vertical pass
+//   dst = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
+// One block per destination row: its two source rows are staged in shared memory with 16-byte loads,
+// a thread produces 4 destination pixels (12 bytes, written as three 32-bit words, BGR order) from
+// byte reads of the staged rows and one 16-byte read of each coefficient table.
+// CS = source channels: 3 (RGB, swapped to BGR) or 1 (grayscale, replicated into the three output channels: the
+// documented extension of SURVEY.md section 8a -- resizing a replicated frame == replicating the resized plane).
+constexpr int kPreThreads = 256;
+template <int CS>
+__global__ void __launch_bounds__(kPreThreads) preprocess_resize_bgr_kernel(
+    const uint8_t* __restrict__ src, int Hs, int Ws, uint8_t* __restrict__ dst, int S, const int* __restrict__ xofs,
+    const short* __restrict__ xalpha, const int* __restrict__ yofs, const short* __restrict__ ybeta, int area2x) {
+  extern __shared__ __align__(16) uint8_t rows[];  // [2][row_pitch]
+  const int dy = blockIdx.x, n = blockIdx.y;
+  const int row_bytes = Ws * CS, pitch = (row_bytes + 15) & ~15;
+  const uint8_t* img = src + static_cast<size_t>(n) * Hs * row_bytes;
+  int y0, y1, b0 = 0, b1 = 0;
+  if (area2x) {  // cv2 switches INTER_LINEAR to the fast 2x2 area average when both scales are exactly 2
+    y0 = 2 * dy;
+    y1 = 2 * dy + 1;
+  } else {
+    const int sy = yofs[dy];
+    y0 = min(max(sy, 0), Hs - 1);
+    y1 = min(max(sy + 1, 0), Hs - 1);
+    b0 = ybeta[2 * dy];
+    b1 = ybeta[2 * dy + 1];
+  }
+  stage_row(rows, img + static_cast<size_t>(y0) * row_bytes, row_bytes);
+  stage_row(rows + pitch, img + static_cast<size_t>(y1) * row_bytes, row_bytes);
+  __syncthreads();
+  const uint8_t* r0 = rows;
+  const uint8_t* r1 = rows + pitch;
+  uint8_t* drow = dst + (static_cast<size_t>(n) * S + dy) * S * 3;
+  const bool vec = (S & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(xofs) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(xalpha) & 15) == 0;
+  for (int q = threadIdx.x; q < (S + 3) / 4; q += kPreThreads) {
+    uint8_t o[12];
+    resize_quad<CS>(r0, r1, Ws, S, xofs, xalpha, b0, b1, area2x, vec, q, o);
     if (vec) {
       uint32_t* d32 = reinterpret_cast<uint32_t*>(drow) + 3 * q;
 #pragma unroll
@@ -111,6 +120,64 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_resize_bgr_kernel(
     } else {
       for (int p = 0; p < 4 && 4 * q + p < S; ++p)
         for (int c = 0; c < 3; ++c) drow[(4 * q + p) * 3 + c] = o[3 * p + c];
+    }
+  }
+}
+
+// The same resize written straight into the network stem's input format (csrc/direct.cu: stem_pack_s2d_kernel): bf16
+// [N][S/2][S/2][16], channel (dy*2 + dx)*3 + c = pixel (2y+dy, 2x+dx) of the BGR frame, channels 12..15 zero.  One
+// block per PAIR of destination rows (four staged source rows); a thread turns its two 4-pixel quads into two whole
+// 32-byte pixels of the packed tensor (two 16-byte stores each).  uint8 -> bf16 is exact.  Saves the uint8 frame's
+// write + read and the separate pack launch of the predict path (no normalisation there, model.py:192).
+template <int CS>
+__global__ void __launch_bounds__(kPreThreads) preprocess_resize_s2d_kernel(
+    const uint8_t* __restrict__ src, int Hs, int Ws, uint4* __restrict__ dst, int S, const int* __restrict__ xofs,
+    const short* __restrict__ xalpha, const int* __restrict__ yofs, const short* __restrict__ ybeta, int area2x) {
+  extern __shared__ __align__(16) uint8_t rows[];  // [4][row_pitch]
+  const int r = blockIdx.x, n = blockIdx.y;
+  const int row_bytes = Ws * CS, pitch = (row_bytes + 15) & ~15;
+  const uint8_t* img = src + static_cast<size_t>(n) * Hs * row_bytes;
+  int b[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int dy = 2 * r + h;
+    int y0, y1;
+    if (area2x) {
+      y0 = 2 * dy;
+      y1 = 2 * dy + 1;
+    } else {
+      const int sy = yofs[dy];
+      y0 = min(max(sy, 0), Hs - 1);
+      y1 = min(max(sy + 1, 0), Hs - 1);
+      b[h][0] = ybeta[2 * dy];
+      b[h][1] = ybeta[2 * dy + 1];
+    }
+    stage_row(rows + (2 * h) * pitch, img + static_cast<size_t>(y0) * row_bytes, row_bytes);
+    stage_row(rows + (2 * h + 1) * pitch, img + static_cast<size_t>(y1) * row_bytes, row_bytes);
+  }
+  __syncthreads();
+  const bool vec = (S & 3) == 0 && (reinterpret_cast<uintptr_t>(xofs) & 15) == 0 && (reinterpret_cast<uintptr_t>(xalpha) & 15) == 0;
+  uint4* drow = dst + (static_cast<size_t>(n) * (S / 2) + r) * (S / 2) * 2;  // 2 x uint4 per packed pixel
+  for (int q = threadIdx.x; q < (S + 3) / 4; q += kPreThreads) {
+    uint8_t o0[12], o1[12];
+    resize_quad<CS>(rows, rows + pitch, Ws, S, xofs, xalpha, b[0][0], b[0][1], area2x, vec, q, o0);
+    resize_quad<CS>(rows + 2 * pitch, rows + 3 * pitch, Ws, S, xofs, xalpha, b[1][0], b[1][1], area2x, vec, q, o1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {          // packed pixel 2q + h = destination pixels 4q + 2h, 4q + 2h + 1 of both rows
+      if (2 * q + h >= S / 2) break;
+      uint32_t w[8];                       // 16 bf16: row 0 (2 px x 3 ch), row 1 (2 px x 3 ch), 4 zeros
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const uint32_t lo0 = __float_as_uint(static_cast<float>(o0[6 * h + 2 * e])) >> 16;
+        const uint32_t hi0 = __float_as_uint(static_cast<float>(o0[6 * h + 2 * e + 1])) & 0xffff0000u;
+        const uint32_t lo1 = __float_as_uint(static_cast<float>(o1[6 * h + 2 * e])) >> 16;
+        const uint32_t hi1 = __float_as_uint(static_cast<float>(o1[6 * h + 2 * e + 1])) & 0xffff0000u;
+        w[e] = lo0 | hi0;
+        w[3 + e] = lo1 | hi1;
+      }
+      w[6] = w[7] = 0u;
+      drow[2 * (2 * q + h)] = make_uint4(w[0], w[1], w[2], w[3]);
+      drow[2 * (2 * q + h) + 1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
   }
 }
@@ -299,6 +366,31 @@ static int launch_preprocess(const uint8_t* src, int32_t N, int32_t Hs, int32_t 
   preprocess_resize_bgr_kernel<CS><<<grid, kPreThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       src, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x);
   return check_launch("preprocess_resize_bgr_kernel");
+}
+
+template <int CS>
+static int launch_preprocess_s2d(const uint8_t* src, int32_t N, int32_t Hs, int32_t Ws, void* dst, int32_t S,
+                                 const int32_t* xofs, const int16_t* xalpha, const int32_t* yofs, const int16_t* ybeta,
+                                 int32_t area_fast_2x, void* stream) {
+  if (!src || !dst) return fail(OCTSEG_EINVAL, "preprocess_s2d: null buffer");
+  if (!area_fast_2x && (!xofs || !xalpha || !yofs || !ybeta)) return fail(OCTSEG_EINVAL, "preprocess_s2d: null LUT");
+  if (S % 2 || (reinterpret_cast<uintptr_t>(dst) & 15)) return fail(OCTSEG_EINVAL, "preprocess_s2d: S must be even and dst 16-byte aligned");
+  if (N <= 0 || S <= 0) return OCTSEG_OK;
+  if (N > 65535) return fail(OCTSEG_EINVAL, "preprocess_s2d: at most 65535 frames per call");
+  const size_t smem = 4 * static_cast<size_t>((Ws * CS + 15) & ~15);
+  if (smem > 48 * 1024) return fail(OCTSEG_EINVAL, "preprocess_s2d: source rows of %d pixels do not fit shared memory", Ws);
+  dim3 grid(S / 2, N);
+  preprocess_resize_s2d_kernel<CS><<<grid, kPreThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      src, Hs, Ws, static_cast<uint4*>(dst), S, xofs, xalpha, yofs, ybeta, area_fast_2x);
+  return check_launch("preprocess_resize_s2d_kernel");
+}
+
+extern "C" int octseg_preprocess_resize_s2d(const uint8_t* src, int32_t channels, int32_t N, int32_t Hs, int32_t Ws, void* dst,
+                                            int32_t S, const int32_t* xofs, const int16_t* xalpha, const int32_t* yofs,
+                                            const int16_t* ybeta, int32_t area_fast_2x, void* stream) {
+  if (channels == 3) return launch_preprocess_s2d<3>(src, N, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x, stream);
+  if (channels == 1) return launch_preprocess_s2d<1>(src, N, Hs, Ws, dst, S, xofs, xalpha, yofs, ybeta, area_fast_2x, stream);
+  return fail(OCTSEG_EINVAL, "preprocess_s2d: frames must have 1 or 3 channels");
 }
 
 extern "C" int octseg_preprocess_resize_bgr(const uint8_t* src, int32_t N, int32_t Hs, int32_t Ws, uint8_t* dst,

@@ -284,20 +284,31 @@ class Builder:
 
         in[2(oy+qy)+dy] with ky = 2qy + dy + pad: the k taps of a row fold into ceil-ish k/2 taps qy of the
         2x2-packed tensor (12 channels, padded to 16); weights move to w2[co][(dy*2+dx)*3+c][qy-q0][qx-q0]."""
-        assert stride == 2 and x.shape[1] == 3
-        N, _, H, W = x.shape
+        assert stride == 2
+        if in_dtype == 's2d':
+            N, H, W = x.shape[0], 2 * x.shape[1], 2 * x.shape[2]
+        else:
+            assert x.shape[1] == 3
+            N, _, H, W = x.shape
         cout = w.shape[0]
-        x2 = self.new_act(H // 2, W // 2, 12)
-        sn, sc, sh, sw = x.stride()
-        mean_a = (C.c_float * 3)(*mean) if mean is not None else None
-        istd_a = (C.c_float * 3)(*[1.0 / s for s in std]) if std is not None else None
-        self._keep += [x]
-        lib, dt = self.lib, {'f32': 0, 'u8': 1}[in_dtype]
+        if in_dtype == 's2d':
+            # the caller (pipeline: octseg_preprocess_resize_s2d) writes the packed input itself: `x` IS the
+            # (N, H/2, W/2, 16) bf16 tensor, an external buffer that never enters the arena
+            assert x.dtype == torch.bfloat16 and tuple(x.shape) == (N, H // 2, W // 2, 16) and (mean is None and std is None)
+            x2 = Act(x, 12)
+            self._keep += [x]
+        else:
+            x2 = self.new_act(H // 2, W // 2, 12)
+            sn, sc, sh, sw = x.stride()
+            mean_a = (C.c_float * 3)(*mean) if mean is not None else None
+            istd_a = (C.c_float * 3)(*[1.0 / s for s in std]) if std is not None else None
+            self._keep += [x]
+            lib, dt = self.lib, {'f32': 0, 'u8': 1}[in_dtype]
 
-        def pack_op():
-            _lib.check(lib.octseg_stem_pack(x.data_ptr(), dt, sn, sc, sh, sw, N, H, W, mean_a, istd_a,
-                                            x2.t.data_ptr(), _lib.stream_ptr()), name + '.pack')
-        self._add(name + '.pack', lambda: pack_op, [], [x2], kind='pack', extra_bytes=N * H * W * 3 * (1 if in_dtype == 'u8' else 4))
+            def pack_op():
+                _lib.check(lib.octseg_stem_pack(x.data_ptr(), dt, sn, sc, sh, sw, N, H, W, mean_a, istd_a,
+                                                x2.t.data_ptr(), _lib.stream_ptr()), name + '.pack')
+            self._add(name + '.pack', lambda: pack_op, [], [x2], kind='pack', extra_bytes=N * H * W * 3 * (1 if in_dtype == 'u8' else 4))
         w2, q0 = stem_s2d_weights(w, k, pad)
         assert q0[0] <= 0 and q0[1] <= 0
         out = self.conv([(x2, False)], w2, b, name=name, pad=(-q0[0], -q0[1]), out_hw=out_hw, act=act)

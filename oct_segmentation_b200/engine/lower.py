@@ -29,7 +29,7 @@ FUSE_MBCONV = ()
 def lower_resnet(b: Builder, enc, x: torch.Tensor, in_dtype: str, norm) -> List[Act]:
     """torchvision ResNet (Bottleneck, stride on the 3x3): feature taps at strides 2,4,8,16,32."""
     w, bias = fold_bn(enc.conv1.weight, enc.bn1)
-    H, W = x.shape[2], x.shape[3]
+    H, W = (2 * x.shape[1], 2 * x.shape[2]) if in_dtype == 's2d' else (x.shape[2], x.shape[3])
     f1 = b.stem(x, in_dtype, w, bias, name='encoder.conv1', k=7, stride=2, pad=(3, 3),
                 out_hw=((H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1), act='relu', mean=norm and norm[0], std=norm and norm[1])
     feats = [f1]
@@ -56,7 +56,7 @@ def lower_resnet(b: Builder, enc, x: torch.Tensor, in_dtype: str, norm) -> List[
 def lower_regnet(b: Builder, enc, x: torch.Tensor, in_dtype: str, norm) -> List[Act]:
     """timm RegNetX: stem 3x3 s2, four stages of 1x1 -> grouped 3x3 (stride) -> 1x1 (+shortcut) -> ReLU."""
     w, bias = fold_bn(enc.stem.conv.weight, enc.stem.bn)
-    H, W = x.shape[2], x.shape[3]
+    H, W = (2 * x.shape[1], 2 * x.shape[2]) if in_dtype == 's2d' else (x.shape[2], x.shape[3])
     cur = b.stem(x, in_dtype, w, bias, name='encoder.stem', k=3, stride=2, pad=(1, 1),
                  out_hw=((H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1), act='relu', mean=norm and norm[0], std=norm and norm[1])
     feats = [cur]
@@ -81,7 +81,7 @@ def lower_regnet(b: Builder, enc, x: torch.Tensor, in_dtype: str, norm) -> List[
 
 def lower_efficientnet(b: Builder, enc, x: torch.Tensor, in_dtype: str, norm) -> List[Act]:
     """efficientnet_pytorch MBConv stack with static 'same' padding; taps after blocks 11/18/38/55."""
-    H, W = x.shape[2], x.shape[3]
+    H, W = (2 * x.shape[1], 2 * x.shape[2]) if in_dtype == 's2d' else (x.shape[2], x.shape[3])
     w, bias = fold_bn(enc._conv_stem.weight, enc._bn0)
     pt, pb = enc._conv_stem.pad
     oh, ow = (H + pt + pb - 3) // 2 + 1, (W + pt + pb - 3) // 2 + 1

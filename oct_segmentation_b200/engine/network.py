@@ -29,9 +29,15 @@ class CompiledNet:
         classes = model.segmentation_head[0].out_channels
         with torch.cuda.device(self.device):
             # static input, stored NHWC; the stem reads it through a logical NCHW view
-            dt = torch.float32 if in_dtype == 'f32' else torch.uint8
-            self.x_nhwc = torch.zeros(N, H, W, 3, dtype=dt, device=self.device)
-            x_view = self.x_nhwc.permute(0, 3, 1, 2)
+            if in_dtype == 's2d':
+                # stem-packed input written by the caller (prepost.preprocess_s2d): bf16 (N, H/2, W/2, 16)
+                self.x_nhwc = None
+                self.x_s2d = torch.zeros(N, H // 2, W // 2, 16, dtype=torch.bfloat16, device=self.device)
+                x_view = self.x_s2d
+            else:
+                dt = torch.float32 if in_dtype == 'f32' else torch.uint8
+                self.x_nhwc = torch.zeros(N, H, W, 3, dtype=dt, device=self.device)
+                x_view = self.x_nhwc.permute(0, 3, 1, 2)
             odt = torch.float32 if out_mode == 'f32_nchw' else torch.uint8
             self.out = torch.zeros(N, classes, H, W, dtype=odt, device=self.device)
             b = builder_cls(self.device, N, **builder_kw)
@@ -74,5 +80,7 @@ class CompiledNet:
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """x: logical NCHW (any strides) of the compiled shape/dtype."""
+        if self.x_nhwc is None:
+            raise RuntimeError("a net compiled for in_dtype='s2d' takes its input through x_s2d (prepost.preprocess_s2d)")
         self.x_nhwc.copy_(x.permute(0, 2, 3, 1), non_blocking=True)
         return self.run()

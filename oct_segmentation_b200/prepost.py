@@ -91,6 +91,34 @@ def preprocess(frames_rgb: torch.Tensor, S: int, out: Optional[torch.Tensor] = N
     return out
 
 
+def preprocess_s2d(frames_rgb: torch.Tensor, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`preprocess` written straight into the network stem's input format: bf16 CUDA (N, S/2, S/2, 16), channel
+    (dy*2 + dx)*3 + c = BGR pixel (2y+dy, 2x+dx), channels 12..15 zero -- what the stem-pack launch would make of
+    `preprocess(frames, S)`; one pass over the frame instead of two plus a uint8 round trip.  `unpack_s2d` inverts it."""
+    assert frames_rgb.is_cuda and frames_rgb.dtype == torch.uint8 and frames_rgb.is_contiguous() and S % 2 == 0
+    gray = frames_rgb.dim() == 3 or frames_rgb.shape[3] == 1
+    assert gray or (frames_rgb.dim() == 4 and frames_rgb.shape[3] == 3), 'frames must have 1 or 3 channels'
+    N, Hs, Ws = frames_rgb.shape[:3]
+    if out is None:
+        out = torch.empty(N, S // 2, S // 2, 16, dtype=torch.bfloat16, device=frames_rgb.device)
+    assert out.is_contiguous() and tuple(out.shape) == (N, S // 2, S // 2, 16) and out.dtype == torch.bfloat16
+    lib = _lib.load()
+    area2x = int(Hs == 2 * S and Ws == 2 * S)
+    xo, xa, yo, yb = _resize_luts(Hs, Ws, S, str(frames_rgb.device))
+    with torch.cuda.device(frames_rgb.device):
+        _lib.check(lib.octseg_preprocess_resize_s2d(frames_rgb.data_ptr(), 1 if gray else 3, N, Hs, Ws, out.data_ptr(), S,
+                                                    xo.data_ptr(), xa.data_ptr(), yo.data_ptr(), yb.data_ptr(), area2x,
+                                                    _lib.stream_ptr()), 'preprocess_resize_s2d')
+    return out
+
+
+def unpack_s2d(x2: torch.Tensor) -> torch.Tensor:
+    """(N, H/2, W/2, 16) stem-packed tensor -> (N, H, W, 3) frame (same dtype): inverse of the space-to-depth packing."""
+    N, H2, W2, _ = x2.shape
+    v = x2[..., :12].reshape(N, H2, W2, 2, 2, 3)                 # (n, y, x, dy, dx, c)
+    return v.permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * H2, 2 * W2, 3)
+
+
 def postprocess(planes: Dict[int, torch.Tensor], order: Sequence[int], Ho: int, Wo: int, N: int, device,
                 mask: Optional[torch.Tensor] = None, label: Optional[torch.Tensor] = None,
                 counts: Optional[torch.Tensor] = None):

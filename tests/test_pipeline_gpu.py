@@ -80,11 +80,13 @@ def test_pipeline_postprocessing_is_exact_given_the_same_planes(model_pairs):
         assert np.array_equal(counts[n], [R.area_count(want[:, :, c]) for c in range(4)])
         for c in range(4):
             assert np.array_equal(radii[n, c], R.radial_radii((want[:, :, c] * 255).astype(np.uint8)))
-    # input of each network == cv2 preprocessing of the frames
+    # input of each network == cv2 preprocessing of the frames (the pipeline writes it stem-packed: bf16, 2x2 blocks)
     for d in pipe.model_dirs:
         S = pipe.sizes[d]
         want_in = np.stack([R.preprocess_frame(f, S) for f in frames])
-        assert np.array_equal(pipe.nets[d].x_nhwc.cpu().numpy(), want_in)
+        x2 = pipe.nets[d].x_s2d
+        assert x2.dtype == torch.bfloat16 and (x2[..., 12:] == 0).all()
+        assert np.array_equal(P.unpack_s2d(x2).float().cpu().numpy(), want_in.astype(np.float32))
 
 
 def test_stream_host_equals_run_host(model_pairs):

@@ -275,3 +275,31 @@ def test_contour_thickness_full_size():
     assert n2[0, 1] > 64
     with pytest.raises(RuntimeError):
         P.thickness_from_contour(s2[0, 1], int(n2[0, 1]), v2[0, 1])
+
+
+@pytest.mark.parametrize('Hs,Ws,S', [(1000, 1000, 512), (1000, 1000, 896), (512, 512, 896), (1024, 1024, 512), (250, 300, 128), (64, 64, 32)])
+def test_preprocess_s2d_equals_cv2_then_stem_pack(Hs, Ws, S):
+    """octseg_preprocess_resize_s2d = preprocessing_img (cv2 bilinear + BGR, bit for bit) followed by the exact uint8 ->
+    bf16 space-to-depth packing the network stems read: unpacking it gives cv2's frame, and it equals what the separate
+    stem-pack launch makes of the uint8 result (so the fused path feeds the networks identical bits)."""
+    import ctypes as C
+    from oct_segmentation_b200 import _lib
+    rng = np.random.default_rng(Hs + S)
+    frames = rng.integers(0, 256, (2, Hs, Ws, 3), dtype=np.uint8)
+    dev = torch.device('cuda')
+    x2 = P.preprocess_s2d(torch.from_numpy(frames).to(dev), S)
+    assert x2.shape == (2, S // 2, S // 2, 16) and x2.dtype == torch.bfloat16 and (x2[..., 12:] == 0).all()
+    want = np.stack([R.preprocess_frame(f, S) for f in frames])
+    assert np.array_equal(P.unpack_s2d(x2).float().cpu().numpy(), want.astype(np.float32))
+    # the two-launch path: uint8 resize, then octseg_stem_pack
+    u8 = P.preprocess(torch.from_numpy(frames).to(dev), S)
+    ref = torch.empty_like(x2)
+    xv = u8.permute(0, 3, 1, 2)
+    sn, sc, sh, sw = xv.stride()
+    _lib.check(_lib.load().octseg_stem_pack(u8.data_ptr(), 1, sn, sc, sh, sw, 2, S, S, None, None, ref.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), 'stem_pack')
+    assert torch.equal(x2, ref)
+    # grayscale frames are replicated
+    g = P.preprocess_s2d(torch.from_numpy(np.ascontiguousarray(frames[..., 0])).to(dev), S)
+    want_g = np.stack([R.preprocess_frame(np.repeat(f[..., :1], 3, -1), S) for f in frames])
+    assert np.array_equal(P.unpack_s2d(g).float().cpu().numpy(), want_g.astype(np.float32))
