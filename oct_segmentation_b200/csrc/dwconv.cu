@@ -55,7 +55,7 @@ struct DwCfg {
   static constexpr int PIX = CB * 2;                           // bytes per pixel in the tile
   static constexpr int STAGE = (IH * IW * PIX + 127) / 128 * 128;
   static constexpr int CTAS = S == 1 ? 2 : 1;  // resident CTAs per SM (registers + shared memory; 3 for k = 3 fits in 80 registers but measured 2 % slower)
-  static constexpr int NST = S == 1 ? 3 : 2;
+  static constexpr int NST = S == 1 ? 3 : 2;   // (a 4-stage ring for k = 3 measured the same 4.0 TB/s)
   static constexpr int WSM = K * K * CB * 4;                   // fp32 filters
   static constexpr int PART = (kDwThreads / 32) * CB * 4;      // per-warp SE partial sums
   static constexpr int SMEM = NST * STAGE + WSM + PART + 64 + 128;  // + barriers + alignment slack
