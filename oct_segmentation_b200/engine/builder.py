@@ -404,12 +404,12 @@ class Builder:
         if f > 1:
             wpk, bpk = pack_conv_weights(wp, bp, [x.C], [x.Cp], f, 0, cs)
             spec = [((N, x.H, x.W // f, f * x.Cp, f * x.Cp), False)]
-            geom, packed32 = plan_conv(spec, wpk, out_hw=(x.H, x.W // f), packed_dtype=torch.float32)
+            geom, packed32 = plan_conv(spec, wpk, out_hw=(x.H, x.W // f), packed_dtype=torch.float32, allow_resident=False)
             geom.macs = N * x.H * x.W * cout * C_mid                                # dense count of the real op
             bias_rows = pad_bias(bpk, geom, f * cs)
         else:
             spec = [((N, x.H, x.W, x.C, x.Cp), False)]
-            geom, packed32 = plan_conv(spec, wp, out_hw=(x.H, x.W), packed_dtype=torch.float32)
+            geom, packed32 = plan_conv(spec, wp, out_hw=(x.H, x.W), packed_dtype=torch.float32, allow_resident=False)
             bias_rows = pad_bias(bp, geom, cout)
         rows, Ktot = packed32.shape[1], packed32.shape[2]
         base = packed32[0].contiguous().to(dev)                                    # fp32 [rows][Ktot]

@@ -25,6 +25,8 @@ KC = 64  # K elements per pipeline stage (one 128-byte swizzle atom of bf16)
 WIDE_BOXES = True  # allow shifted-view tap reuse (SegSpec.wide)
 HALO_TILES = True  # allow halo-tile mode (ConvGeom.halo)
 HALO_B_BYTES = 80 * 1024   # resident-weight budget of halo mode (shared memory)
+RES1X1_B_BYTES = 100 * 1024   # ... and of its 1x1 form (three 16 KB A stages remain)
+RESIDENT_1X1 = _os.environ.get('OCTSEG_RES1X1', '0') == '1'   # experiment: resident weights for mid-size 1x1 convs
 
 
 def choose_kc(c_eff: int, taps: int = 9) -> int:
@@ -170,7 +172,7 @@ def _phase_tap_groups(ph: int, a: int) -> List[int]:
 def plan_conv(srcs: Sequence[Tuple[Tuple[int, int, int, int, int], bool]], weight: torch.Tensor,
               out_hw: Optional[Tuple[int, int]] = None, stride: int = 1, pad: Tuple[int, int] = (0, 0),
               groups: int = 1, transposed: bool = False, out_bf16: bool = True,
-              packed_dtype: torch.dtype = torch.bfloat16) -> Tuple[ConvGeom, torch.Tensor]:
+              packed_dtype: torch.dtype = torch.bfloat16, allow_resident: bool = True) -> Tuple[ConvGeom, torch.Tensor]:
     """Plan one conv.
 
     srcs: [((N, H, W, C, ldc), upsampled)] in concat order; ``upsampled`` sources are at half the
@@ -209,11 +211,11 @@ def plan_conv(srcs: Sequence[Tuple[Tuple[int, int, int, int, int], bool]], weigh
             phases, Hq, Wq = 1, out_H, out_W
         macs = N * out_H * out_W * cout * cin_g * kh * kw
     return _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, tuple(pad), groups, transposed, out_bf16, macs,
-                 packed_dtype)
+                 packed_dtype, allow_resident and packed_dtype == torch.bfloat16)
 
 
 def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transposed, out_bf16, macs,
-          packed_dtype=torch.bfloat16):
+          packed_dtype=torch.bfloat16, allow_resident=True):
     cout = w.shape[1] if transposed else w.shape[0]
     cout_w = pad8(cout) if out_bf16 else cout          # channels the kernel writes
     TH, TW = choose_tile(Hq, Wq)
@@ -226,6 +228,19 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
         k_est = sum((2 * 2 if (transposed or up) else (3 * 3 if phases == 4 else w.shape[2] * w.shape[3])) * sC
                     for (_, _, _, sC, _), up in srcs)
         n_tiles_n, BN = choose_bn(max(cout_w, 16), k_est)
+        res1x1 = False
+        if (RESIDENT_1X1 and allow_resident and out_bf16 and len(srcs) == 1 and phases == 1 and not transposed and stride == 1
+                and tuple(w.shape[2:]) == (1, 1) and srcs[0][0][3] >= 128 and cout_w >= 128
+                and Hq * Wq >= 0.75 * (-(-Hq // 16) * 16) * (-(-Wq // 8) * 8)):
+            # mid-size 1x1 conv: every tile re-reads its BN x K weight slice from L2 (stages 4-5 expands of EfficientNet are
+            # bound by that).  Halo-tile mode with a 1x1 "halo" keeps the slice resident in shared memory instead; BN is
+            # the widest whole number of 64-channel chunks whose slice fits.
+            cch = -(-srcs[0][0][3] // 64)
+            bn_max = min(256, RES1X1_B_BYTES // (cch * 128) // 64 * 64)
+            if bn_max >= 128:
+                n_tiles_n = -(-cout_w // bn_max)
+                BN = -(-(-(-cout_w // n_tiles_n)) // 64) * 64
+                res1x1 = True
         cout_per_tile = BN
     rows = n_tiles_n * BN
 
@@ -291,6 +306,8 @@ def _plan(srcs, w, phases, N, Hq, Wq, out_H, out_W, stride, pad, groups, transpo
         cover = (-(-Hq // 16) * 16) * (-(-Wq // 8) * 8)
         if (sg.mul == 1 and sg.kh * sg.kw >= 4 and sg.kh <= 7 and sg.kw <= 7 and b_bytes <= HALO_B_BYTES
                 and Hq * Wq >= 0.75 * cover):
+            halo, TH, TW = 1, 16, 8
+        elif groups == 1 and res1x1 and sg.kc == 64 and b_bytes <= RES1X1_B_BYTES:
             halo, TH, TW = 1, 16, 8
     if (TH != 1 and WIDE_BOXES and not halo and phases == 1 and not transposed and BN <= 128
             and all(sg.kc == 64 and sg.mul == 1 and sg.kw >= 2 and (sg.c_per_tile == 0 or sg.cchunks == 1) for sg in segs)):
