@@ -50,6 +50,12 @@ CONFIGS = {
                      workload='hybrid ensemble LM(UnetPlusPlus/resnet101@512)+FC_LC(LinkNet/efficientnet-b7@896)+'
                               'VV(Unet/timm-regnetx_064@896), routing+label map+pixel counts+radial thickness at 1000x1000, '
                               'synthetic 512x512 RGB frames'),
+    # config 1 (the reference's CPU-runnable case; `--impl reference --config unet` times exactly that): plain U-Net on
+    # resnet101, single-class lumen, 512 x 512
+    'unet': dict(classes=['Lumen'], src=512, out=[1000, 1000], input_size=None, batch=32, keys=('LM',),
+                 arch={'LM': dict(architecture='Unet', encoder='resnet101', model_name='Unet_resnet101')},
+                 workload='LM only: Unet/resnet101@512 single-class (BASELINE configs[0] on the GPU), threshold+nearest '
+                          'resize+pixel counts at 1000x1000, synthetic 512x512 RGB frames'),
     # config 2: U-Net++ LM single class, batch 32
     'lm': dict(classes=['Lumen'], src=512, out=[1000, 1000], input_size=None, batch=32, keys=('LM',),
                workload='LM only: UnetPlusPlus/resnet101@512 single-class, threshold+nearest resize+pixel counts at 1000x1000, '
@@ -123,8 +129,9 @@ def cpu_oracle_frames_per_s(n_frames: int, warmup: int, cfg: dict):
     torch.set_num_threads(os.cpu_count() or 1)
     models = {}
     for key in cfg['keys']:
-        m = synth.make_model(key, calib_size=128, calib_frames=1)
-        mc = dict(synth.MODEL_CONFIGS[key])
+        over = cfg.get('arch', {}).get(key)
+        m = synth.make_model('U_LM' if over else key, calib_size=128, calib_frames=1)
+        mc = dict(synth.MODEL_CONFIGS[key], **(over or {}))
         if cfg['input_size']:
             mc['input_size'] = cfg['input_size']
         models[key] = (m, mc)
@@ -275,7 +282,7 @@ def ours_arm(args):
     B, K, W = args.batch or cfg['batch'], args.steps, args.warmup
     SRC, OUT_SIZE = cfg['src'], cfg['out']
 
-    models = synthetic.random_models(dev, keys=cfg['keys'], input_size=cfg['input_size'])
+    models = synthetic.random_models(dev, keys=cfg['keys'], input_size=cfg['input_size'], arch=cfg.get('arch'))
     pipe = EnsemblePipeline(models, cfg['classes'], OUT_SIZE, dev, B, src_hw=(SRC, SRC), thickness=True)
 
     # this rank's slice of the global synthetic frame list (weak scaling: B*(K+W) frames per rank)

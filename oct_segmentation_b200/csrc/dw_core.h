@@ -12,6 +12,21 @@ namespace octseg {
 
 constexpr int kDwR = 2, kDwP = 4;  // output rows x pixels per thread
 
+// Packed FFMA2 or two scalar FFMAs per channel pair.  Measured on B200 (tools/ab/ffma_rate.cu): FFMA2 with three
+// register-pair operands sustains 43-56 FMA lanes/clk/SM, scalar three-register FFMA 73-83, so FFMA2 only pays where the
+// kernel is bound by issue slots (k = 3), not by the FMA pipe (k = 5).
+#ifndef OCTSEG_DW_PACKED_K3
+#define OCTSEG_DW_PACKED_K3 1
+#endif
+#ifndef OCTSEG_DW_PACKED_K5
+#define OCTSEG_DW_PACKED_K5 0
+#endif
+template <bool PACKED>
+__device__ __forceinline__ float2 dw_fma2(float2 a, float2 b, float2 c) {
+  if (PACKED) return __ffma2_rn(a, b, c);
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+}
+
 // bf16 pair -> fp32 pair on the ALU pipe only (PRMT + LOP3): the compiler would turn `w << 16` into
 // IMAD.U32, which competes with the FFMA2s for the FMA pipe this kernel is bound by
 __device__ __forceinline__ float2 dw_bf16x2_to_f32x2(uint32_t w) {
@@ -40,6 +55,7 @@ template <int K, int S, int CB, int IW, int PIX>
 __device__ __forceinline__ void dw_patch(uint32_t base, uint32_t w_off, const float2 (&bias2)[2], int act,
                                          float2 (&acc)[kDwR][kDwP][2]) {
   constexpr int R = kDwR, P = kDwP;
+  constexpr bool PK = K == 3 ? (OCTSEG_DW_PACKED_K3 != 0) : (OCTSEG_DW_PACKED_K5 != 0);
   constexpr int RH = (R - 1) * S + K, RW = (P - 1) * S + K;  // a thread's input window
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -81,8 +97,15 @@ __device__ __forceinline__ void dw_patch(uint32_t base, uint32_t w_off, const fl
           for (int q = 0; q < P; ++q) {
             const int kx = dx - q * S;
             if (kx >= 0 && kx < K) {
-              acc[r][q][0] = __ffma2_rn(f0, w[r][kx][0], acc[r][q][0]);
-              acc[r][q][1] = __ffma2_rn(f1, w[r][kx][1], acc[r][q][1]);
+              // K5 == 2: packed on every other input column (balances FMA-pipe time against issue slots)
+              constexpr bool MIX = K == 5 && OCTSEG_DW_PACKED_K5 == 2;
+              if (MIX ? (dx & 1) == 0 : PK) {
+                acc[r][q][0] = dw_fma2<true>(f0, w[r][kx][0], acc[r][q][0]);
+                acc[r][q][1] = dw_fma2<true>(f1, w[r][kx][1], acc[r][q][1]);
+              } else {
+                acc[r][q][0] = dw_fma2<false>(f0, w[r][kx][0], acc[r][q][0]);
+                acc[r][q][1] = dw_fma2<false>(f1, w[r][kx][1], acc[r][q][1]);
+              }
             }
           }
         }

@@ -68,13 +68,13 @@ def synthetic_frames(start: int, count: int, size: int = 512) -> np.ndarray:
 
 
 
-def random_models(device, keys=('LM', 'FC_LC', 'VV'), input_size=None) -> Dict[str, Tuple[object, Dict]]:
+def random_models(device, keys=('LM', 'FC_LC', 'VV'), input_size=None, arch=None) -> Dict[str, Tuple[object, Dict]]:
     """Seeded random-init models of the shipped architectures (library-default init, unit BatchNorm
     statistics, damped residual gammas) keyed by model_dir, ready for EnsemblePipeline."""
     from .model import OCTSegmentationModel
     out = {}
     for key in keys:
-        cfg = dict(MODEL_CONFIGS[key])
+        cfg = dict(MODEL_CONFIGS[key], **((arch or {}).get(key) or {}))      # arch: per-key architecture / encoder override
         if input_size is not None:
             cfg['input_size'] = input_size
         torch.manual_seed(MODEL_SEEDS[key])

@@ -30,6 +30,21 @@ MODEL_CONFIGS = {
            'input_size': 896, 'classes': ['Vasa vasorum']},
 }
 MODEL_SEEDS = {'LM': 1000, 'FC_LC': 1001, 'VV': 1002}
+# Parity-only cases beside the shipped trio: BASELINE.json configs[0] (plain U-Net on resnet101, the reference's best
+# U-Net for the lumen) and two cross pairings of the shipped decoders / encoders (the factory accepts any pairing).
+EXTRA_CONFIGS = {
+    'U_LM': {'model_name': 'Unet_resnet101', 'architecture': 'Unet', 'encoder': 'resnet101', 'input_size': 512,
+             'classes': ['Lumen']},
+    'LINK_R101': {'model_name': 'LinkNet_resnet101', 'architecture': 'LinkNet', 'encoder': 'resnet101', 'input_size': 512,
+                  'classes': ['Fibrous cap', 'Lipid core']},
+    'UPP_REGNET': {'model_name': 'UnetPlusPlus_timm-regnetx_064', 'architecture': 'UnetPlusPlus',
+                   'encoder': 'timm-regnetx_064', 'input_size': 512, 'classes': ['Lumen']},
+}
+EXTRA_SEEDS = {'U_LM': 1010, 'LINK_R101': 1011, 'UPP_REGNET': 1012}
+
+
+def model_config(key: str) -> dict:
+    return MODEL_CONFIGS[key] if key in MODEL_CONFIGS else EXTRA_CONFIGS[key]
 
 
 def _randomize_bn(model: nn.Module, gen: torch.Generator) -> None:
@@ -77,12 +92,13 @@ def calibrate_bn(model: nn.Module, x: torch.Tensor) -> None:
 def make_model(key: str, calib_size: int = 128, calib_frames: int = 2, logit_gain: float = 1.0) -> model_ref.OCTSegmentationModelRef:
     """Seeded synthetic checkpoint for 'LM' | 'FC_LC' | 'VV': library-default init, randomised BN
     affine, BN statistics calibrated on synthetic frames (BGR, 0..255, un-normalised like predict())."""
-    cfg = MODEL_CONFIGS[key]
-    torch.manual_seed(MODEL_SEEDS[key])
+    cfg = model_config(key)
+    seed = MODEL_SEEDS[key] if key in MODEL_SEEDS else EXTRA_SEEDS[key]
+    torch.manual_seed(seed)
     m = model_ref.OCTSegmentationModelRef(arch=cfg['architecture'], encoder_name=cfg['encoder'],
                                           model_name=cfg['model_name'], in_channels=3, classes=cfg['classes'],
                                           encoder_weights=None)
-    gen = torch.Generator().manual_seed(MODEL_SEEDS[key] + 7)
+    gen = torch.Generator().manual_seed(seed + 7)
     _randomize_bn(m.model, gen)
     frames = synthetic_frames(0, calib_frames, calib_size)[..., ::-1].copy()       # RGB -> BGR
     x = torch.from_numpy(frames).permute(0, 3, 1, 2).float()

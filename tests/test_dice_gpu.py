@@ -29,7 +29,7 @@ from oracle import model_ref, synth
 pytestmark = pytest.mark.gpu
 
 # (fit resolution = shipped input size, batch, steps): sized so that all three fits take ~1-2 minutes on a B200
-FIT = {'LM': (512, 2, 300), 'VV': (896, 1, 300), 'FC_LC': (896, 1, 400)}
+FIT = {'LM': (512, 2, 300), 'VV': (896, 1, 300), 'FC_LC': (896, 1, 400), 'U_LM': (512, 2, 300)}   # U_LM: BASELINE configs[0]
 _CACHE = {}
 
 
@@ -45,7 +45,7 @@ def fitted(key):
         size, batch, steps = FIT[key]
         ref = synth.make_model(key, calib_size=128, calib_frames=2)
         loss = synth.fit_model(ref, 'cuda', steps=steps, size=size, batch=batch)
-        cfg = synth.MODEL_CONFIGS[key]
+        cfg = synth.model_config(key)
         ours = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
                                     in_channels=3, classes=cfg['classes'], encoder_weights=None)
         ours.load_state_dict(ref.state_dict(), strict=True)
@@ -70,10 +70,10 @@ def test_fit_is_deterministic():
     assert not bad, f'{len(bad)} tensors differ between two seeded fits, e.g. {bad[:3]}'
 
 
-@pytest.mark.parametrize('key,frames_n', [('VV', 3), ('LM', 4), ('FC_LC', 3)])
+@pytest.mark.parametrize('key,frames_n', [('VV', 3), ('LM', 4), ('FC_LC', 3), ('U_LM', 4)])
 def test_fitted_checkpoint_dice_at_shipped_size(key, frames_n):
     ref, ours, loss = fitted(key)
-    cfg = synth.MODEL_CONFIGS[key]
+    cfg = synth.model_config(key)
     size = cfg['input_size']
     frames = synth.synthetic_frames(5000, frames_n, size)[..., ::-1].copy()        # unseen frames, BGR like predict()
     x = torch.from_numpy(frames).cuda().permute(0, 3, 1, 2).float()

@@ -326,3 +326,20 @@ def test_dicom_front_end_normalises_like_the_reference_and_needs_pydicom_only_fo
             analysis.analyse_volume('/nonexistent/study.dcm', models={})
     with pytest.raises(ValueError):
         analysis.analyse_volume(np.zeros((4, 4), np.uint8), models={})
+
+
+def test_normalisation_constants_match_the_reference_encoders():
+    """smp.encoders.get_preprocessing_params (model.py:60-63) gives the ImageNet statistics for all three shipped
+    encoders; the product returns what the oracle's restatement does, and OCTSegmentationModel registers them."""
+    from oracle import smp_ref, synth
+    for key, cfg in synth.MODEL_CONFIGS.items():
+        ours = smp.encoders.get_preprocessing_params(cfg['encoder'])
+        ref = smp_ref.get_preprocessing_params(cfg['encoder'])
+        assert ours['mean'] == ref['mean'] == [0.485, 0.456, 0.406], key
+        assert ours['std'] == ref['std'] == [0.229, 0.224, 0.225], key
+    cfg = synth.MODEL_CONFIGS['VV']
+    m = OCTSegmentationModel(cfg['architecture'], cfg['encoder'], 'VV', 3, cfg['classes'])
+    assert m.mean.flatten().tolist() == pytest.approx([0.485, 0.456, 0.406])
+    assert m.std.flatten().tolist() == pytest.approx([0.229, 0.224, 0.225])
+    with pytest.raises(KeyError):
+        smp.encoders.get_preprocessing_params('resnet18')

@@ -9,10 +9,11 @@ from oracle import synth
 from tests.cpu_builder import run_lowered
 
 
-@pytest.mark.parametrize('key,size', [('LM', 64), ('VV', 64), ('FC_LC', 96)])
+# the shipped trio, BASELINE.json configs[0] (plain U-Net on resnet101) and two cross pairings of decoders and encoders
+@pytest.mark.parametrize('key,size', [('LM', 64), ('VV', 64), ('FC_LC', 96), ('U_LM', 64), ('LINK_R101', 64), ('UPP_REGNET', 64)])
 def test_lowering_matches_oracle(key, size):
     ref = synth.make_model(key, calib_size=size, calib_frames=4)
-    cfg = synth.MODEL_CONFIGS[key]
+    cfg = synth.model_config(key)
     ours = smp.create_model(cfg['architecture'], cfg['encoder'], classes=len(cfg['classes']))
     ours.load_state_dict(ref.model.state_dict(), strict=True)
     x = torch.from_numpy(synth.synthetic_frames(7, 2, size)[..., ::-1].copy()).permute(0, 3, 1, 2).float()

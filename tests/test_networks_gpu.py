@@ -20,7 +20,10 @@ from tests.checked_builder import CheckedBuilder
 
 pytestmark = pytest.mark.gpu
 
-SIZES = {'LM': 256, 'VV': 256, 'FC_LC': 256}
+SIZES = {'LM': 256, 'VV': 256, 'FC_LC': 256, 'U_LM': 256, 'LINK_R101': 192, 'UPP_REGNET': 192}
+# U_LM = BASELINE.json configs[0] (plain U-Net on resnet101); LINK_R101 / UPP_REGNET = cross pairings of the shipped
+# decoders and encoders (smp.create_model accepts any pairing, model.py:38-44)
+ALL_KEYS = ['LM', 'VV', 'FC_LC', 'U_LM', 'LINK_R101', 'UPP_REGNET']
 
 
 def rel_l2(a, b):
@@ -31,7 +34,7 @@ def build_pair(key):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     ref = synth.make_model(key)
-    cfg = synth.MODEL_CONFIGS[key]
+    cfg = synth.model_config(key)
     ours = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
                                 in_channels=3, classes=cfg['classes'], encoder_weights=None)
     ours.load_state_dict(ref.state_dict(), strict=True)
@@ -43,7 +46,7 @@ def frames_bgr(n, size):
     return f
 
 
-@pytest.mark.parametrize('key', ['LM', 'VV', 'FC_LC'])
+@pytest.mark.parametrize('key', ALL_KEYS)
 def test_every_launch_matches_torch_in_situ(key):
     ref, ours = build_pair(key)
     size = SIZES[key]
@@ -86,7 +89,7 @@ def test_every_launch_matches_torch_in_situ_non_square(key, H, W, N):
     assert not bad, f'{key} {H}x{W}: launches off by more than 1e-2: {bad[:8]}'
 
 
-@pytest.mark.parametrize('key', ['LM', 'VV', 'FC_LC'])
+@pytest.mark.parametrize('key', ['LM', 'VV', 'FC_LC', 'U_LM'])
 def test_network_matches_oracle(key):
     ref, ours = build_pair(key)
     size = SIZES[key]

@@ -303,3 +303,37 @@ def test_preprocess_s2d_equals_cv2_then_stem_pack(Hs, Ws, S):
     g = P.preprocess_s2d(torch.from_numpy(np.ascontiguousarray(frames[..., 0])).to(dev), S)
     want_g = np.stack([R.preprocess_frame(np.repeat(f[..., :1], 3, -1), S) for f in frames])
     assert np.array_equal(P.unpack_s2d(g).float().cpu().numpy(), want_g.astype(np.float32))
+
+
+@pytest.mark.parametrize('in_dtype', ['f32', 'u8'])
+def test_stem_pack_applies_forward_normalisation(in_dtype):
+    """OCTSegmentationModel.forward's (image - mean) / std (model.py:65-71) happens inside octseg_stem_pack: its packed
+    bf16 output equals torch's fp32 normalisation rounded to bf16 (one bf16 ulp of slack for x * (1/std) vs x / std),
+    and a std that is off by 2 % -- the smallest mix-up between the three ImageNet channels -- does NOT pass."""
+    import ctypes as C
+    from oct_segmentation_b200 import _lib
+    from oct_segmentation_b200.smp import _IMAGENET
+    mean, std = _IMAGENET['mean'], _IMAGENET['std']
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 64, 96, generator=g)                          # forward() sees whatever scale the caller uses
+    if in_dtype == 'u8':
+        x = (x * 255).to(torch.uint8)
+    xd = x.cuda()
+    sn, sc, sh, sw = xd.stride()
+    out = torch.full((2, 32, 48, 16), float('nan'), dtype=torch.bfloat16, device='cuda')
+    _lib.check(_lib.load().octseg_stem_pack(xd.data_ptr(), 0 if in_dtype == 'f32' else 1, sn, sc, sh, sw, 2, 64, 96,
+                                            (C.c_float * 3)(*mean), (C.c_float * 3)(*[1.0 / v for v in std]),
+                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream), 'stem_pack')
+    got = P.unpack_s2d(out).float().cpu()                               # (N, H, W, 3)
+    assert (out[..., 12:] == 0).all()
+
+    def want(std_):
+        m = torch.tensor(mean).view(1, 3, 1, 1)
+        sd = torch.tensor(std_).view(1, 3, 1, 1)
+        return ((x.float() - m) / sd).to(torch.bfloat16).float().permute(0, 2, 3, 1)
+    w = want(std)
+    ulp = w.abs().clamp_min(2.0 ** -126) * 2.0 ** -7
+    assert ((got - w).abs() <= ulp).all()
+    assert (got == w).float().mean() > 0.99
+    wrong = want([std[1], std[0], std[2]])                              # 0.229 <-> 0.224
+    assert not ((got - wrong).abs() <= wrong.abs().clamp_min(2.0 ** -126) * 2.0 ** -7).all()

@@ -8,6 +8,9 @@ import torch
 
 from oct_segmentation_b200 import _lib
 
+if os.environ.get('OCTSEG_AB_LIB'):     # A/B builds of the library (tools/ab/*.so)
+    _lib.LIB_PATH = os.path.abspath(os.environ['OCTSEG_AB_LIB'])
+
 CASES = [(3, 1, 288, 224), (5, 1, 480, 112), (5, 1, 1344, 56), (3, 1, 960, 56), (5, 1, 2304, 28), (3, 1, 32, 448),
          (3, 2, 192, 448), (5, 2, 288, 224), (3, 1, 64, 448), (3, 1, 3840, 28)]
 

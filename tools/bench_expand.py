@@ -16,7 +16,7 @@ SHAPES = [(48, 288, 224), (80, 480, 112), (32, 192, 448), (160, 960, 56), (224, 
 def run(cin, cout, H, act, kc_override=None):
     orig = C.choose_kc
     if kc_override:
-        C.choose_kc = lambda c: kc_override
+        C.choose_kc = lambda c, taps=9: kc_override
     try:
         w = torch.randn(cout, cin, 1, 1) * 0.05
         geom, packed = C.plan_conv([((N, H, H, cin, C.pad8(cin)), False)], w)
