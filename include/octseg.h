@@ -110,6 +110,19 @@ typedef struct octseg_conv_desc {
                           weights): one (TW+kw-1) x (TH+kh-1) halo box of A per channel chunk, the kh*kw taps are
                           shifted views of it, and the channel tile's weights (kh*kw*cchunks*BN*kc*2 bytes) stay
                           resident in shared memory; tiles are ordered channel tile slowest                */
+  /* Fused 1x1 segmentation head (smp SegmentationHead with kernel_size 1: LinkNet) applied to this
+     conv's activated output in the epilogue, so the conv's own (wide, full-resolution) output never reaches memory:
+       logit[pixel][j] = head_bias[j] + sum_c act(conv[pixel][c] + bias[c]) * head_weight[j][c],  j < head_classes.
+     Needs an NCHW out_mode (out_ldc = head_classes planes, written as logits or thresholded y > 0), n_tiles_n = 1,
+     no residual, phases = 1, and GEMM columns = out_pack (1 | 2 | 4) packed pixels x head_cmid channels
+     (Cout = out_pack * head_cmid <= BN, head_cmid in {16, 32, 48, 64}).  The three arrays are HOST pointers, read at
+     plan creation: the head's operands travel in the kernel's parameter block (constant-bank FFMA operands), and
+     `bias` (device) is not read by the fused epilogue.  0 = off.                                            */
+  int32_t head_classes;         /* 1..4 */
+  int32_t head_cmid;            /* channels of the conv per pixel */
+  const float* head_weight;     /* host fp32 [head_classes][head_cmid] */
+  const float* head_bias;       /* host fp32 [head_classes] */
+  const float* head_conv_bias;  /* host fp32 [head_cmid]: the conv's own bias per channel */
 } octseg_conv_desc;
 
 typedef struct octseg_conv_plan octseg_conv_plan;

@@ -47,6 +47,8 @@ class ConvDesc(C.Structure):
         ('res_ldc', C.c_int32), ('out', C.c_void_p), ('out_mode', C.c_int32), ('out_H', C.c_int32),
         ('out_W', C.c_int32), ('out_ldc', C.c_int32), ('out_c_off', C.c_int32), ('out_pack', C.c_int32),
         ('d2s', C.c_int32), ('halo', C.c_int32),
+        ('head_classes', C.c_int32), ('head_cmid', C.c_int32), ('head_weight', C.c_void_p), ('head_bias', C.c_void_p),
+        ('head_conv_bias', C.c_void_p),
     ]
 
 

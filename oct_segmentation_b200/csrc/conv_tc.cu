@@ -58,6 +58,13 @@ struct SegK {
   int last_steps;  // K = 16 MMA steps of the LAST chunk that hold real channels (the rest of it is zero padding: skipped)
 };
 
+// 1: one mbarrier arrival per epilogue warp; 0: one per thread (A/B: tools/ab)
+#ifndef OCTSEG_WARP_ARRIVE
+#define OCTSEG_WARP_ARRIVE 1
+#endif
+constexpr int kEpiArrivals = OCTSEG_WARP_ARRIVE ? kEpiWarps : kEpiThreads;
+constexpr int kHeadMaxC = 64;  // channels per pixel a fused 1x1 head can read
+
 struct __align__(64) ConvKParams {
   CUtensorMap tmA[OCTSEG_MAX_SEG];
   CUtensorMap tmB[3];  // weight boxes (kc x BN) for kc = 16, 32, 64
@@ -82,6 +89,13 @@ struct __align__(64) ConvKParams {
   int res_ldc;
   void* out;
   int out_H, out_W, out_ldc, out_c_off, out_pack, d2s;
+  // fused 1x1 head (octseg.h): per packed pixel, head_classes dot products over its head_cmid activated channels
+  // The head's operands live HERE, in the kernel-parameter constant bank: every FFMA of the epilogue reads its weight
+  // as a constant operand (no shared-memory load, and the FMA pipe's two-register form: tools/ab/ffma_rate.cu).
+  int head_classes, head_cmid;
+  float head_w[4 * kHeadMaxC];  // [class][channel], zero padded
+  float head_b[4];
+  float head_cbias[kHeadMaxC];  // the conv's own per-channel bias (the same for every packed pixel)
   FastDiv fd_ntn, fd_phases, fd_tw, fd_th, fd_TW, fd_n, fd_ldc;
 };
 
@@ -301,7 +315,60 @@ __device__ __forceinline__ int tile_at(const ConvKParams& p, int i) {
   return (static_cast<int>(blockIdx.x) + static_cast<int>(q) * static_cast<int>(gridDim.x)) * p.n_tiles_n + r;
 }
 
-template <int ACT, int RES>
+// Fused 1x1 segmentation head (octseg.h `head_classes`): a thread's accumulator row holds `out_pack` packed pixels x
+// `head_cmid` channels, and each of the 4 warps of a lane quarter takes ONE of those pixels (with fewer packed pixels
+// the warps take tiles in rotation).  Activate the pixel's channels (bias + ACT, fp32), fold them into its NC logits
+// and store only those (fp32 logits, or the thresholded mask y > 0) into NCHW planes.  The epilogue is bound by
+// instruction issue (4 warps per scheduler), so: NC is a template parameter (no predicated-off FMAs), channels go
+// two at a time through FADD2 / FFMA2, and all indices into the parameter block are compile-time constants -- the
+// weights are 64-bit constant-bank operands, never loaded into registers.
+template <int ACT, int NC>
+__device__ __forceinline__ void epilogue_head(const ConvKParams& p, uint32_t taddr, size_t idx0, size_t plane, bool valid) {
+  float2 a2[NC];
+#pragma unroll
+  for (int jc = 0; jc < NC; ++jc) a2[jc] = make_float2(p.head_b[jc], 0.f);
+  const float2* cb2 = reinterpret_cast<const float2*>(p.head_cbias);
+  const float2* w2 = reinterpret_cast<const float2*>(p.head_w);
+#pragma unroll
+  for (int cb = 0; cb < kHeadMaxC; cb += 32) {
+    if (cb < p.head_cmid) {  // warp-uniform
+      uint32_t v[32];
+      __syncwarp();  // tcgen05.ld is warp-collective
+      if (p.head_cmid - cb >= 32) {
+        tmem_ld32(taddr + cb, v);
+      } else {
+        uint32_t v16[16];
+        tmem_ld16(taddr + cb, v16);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = v16[e];
+#pragma unroll
+        for (int e = 16; e < 32; ++e) v[e] = 0u;  // (zero bias and zero weights there in the parameter block)
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        float2 y = __fadd2_rn(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), cb2[(cb + e) >> 1]);
+        y.x = apply_act(y.x, ACT);
+        y.y = apply_act(y.y, ACT);
+#pragma unroll
+        for (int jc = 0; jc < NC; ++jc) a2[jc] = __ffma2_rn(y, w2[(jc * kHeadMaxC + cb + e) >> 1], a2[jc]);
+      }
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int jc = 0; jc < NC; ++jc) {
+    if (jc >= p.head_classes) break;  // (NC = 4 also serves 3 classes)
+    const float y = a2[jc].x + a2[jc].y;
+    const size_t idx = idx0 + static_cast<size_t>(jc) * plane;
+    if (p.out_mode == OCTSEG_OUT_F32_NCHW)
+      reinterpret_cast<float*>(p.out)[idx] = y;
+    else
+      reinterpret_cast<uint8_t*>(p.out)[idx] = y > 0.f ? 1 : 0;
+  }
+}
+
+template <int ACT, int RES, bool HEAD = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -331,11 +398,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int a = 0; a < p.n_acc; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, kEpiThreads);
+      mbar_init(bar_tempty + 8 * a, kEpiArrivals);  // one arrival per epilogue WARP (512 per-thread arrivals on one
+                                                 // barrier serialise: ~1000 cycles per tile, the floor of every small tile)
     }
     mbar_init(bar_bres, 1);
     for (int b = 0; b < kOutBufs; ++b) {
-      mbar_init(bar_sfull + 8 * b, kEpiThreads / 2);
+      mbar_init(bar_sfull + 8 * b, kEpiArrivals / 2);
       mbar_init(bar_sfree + 8 * b, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -716,7 +784,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // and hands the buffer back once the store has read it.  Issuing a tensor store costs its thread ~300 cycles
     // (measured, tools/trace_conv.py); on a math warp that sat on the critical path of every 64-channel chunk.
     if (lane == 0 && p.use_tma_store) {
-      uint32_t chunk_ctr = 0, cnt[2] = {0u, 0u};
+      uint32_t chunk_ctr = 0, cnt0 = 0, cnt1 = 0;  // (two scalars, not an array: a dynamically indexed array lives in local memory)
       int pending = -1;  // buffer whose store was issued last (its read may still be in flight)
       for (int it = 0, tile; (tile = tile_at(p, it)) < p.total_tiles; ++it) {
         const TileCoord tc = decode_tile(p, tile);
@@ -725,7 +793,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int n_tma = p.out_grouped ? 1 : ((nvalid >> 6) + (((nvalid & 63) && ch0 + nvalid == p.Cout) ? 1 : 0));
         for (int ck = 0; ck < n_tma; ++ck) {
           const uint32_t g = (chunk_ctr + ck) & 1u;
-          const uint32_t kg = cnt[g]++;
+          const uint32_t kg = g ? cnt1 : cnt0;
+          cnt0 += g ^ 1u;
+          cnt1 += g;
           const int buf = static_cast<int>(g * 2 + (kg & 1u));
           mbar_wait(bar_sfull + 8 * buf, (kg >> 1) & 1u);
           const uint32_t sbuf = smemOut + buf * kOutBytes;
@@ -796,15 +866,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool can_skip = (p.n_tiles_n == 1 || p.out_grouped) && n_tma1 * 64 >= nvalid1;
     // Narrow direct-store tiles (the NCHW heads: <= 32 output columns): one or two warps per lane quarter
     // cover a tile, so the 4 warps of a quarter take tiles in rotation instead of all walking every tile.
-    const bool rot = p.n_tiles_n == 1 && n_tma1 == 0 && nvalid1 <= 2 * kEpiPart;
-    const int rot_np = nvalid1 <= kEpiPart ? 1 : 2, rot_sets = kEpiSplit / rot_np;
+    // (fused-head tiles: one warp per lane quarter and packed pixel -- epilogue_head)
+    constexpr bool headm = HEAD;                // (its own instantiation: the common epilogue keeps its register budget)
+    const bool rot = p.n_tiles_n == 1 && n_tma1 == 0 && (headm || nvalid1 <= 2 * kEpiPart);
+    const int rot_np = headm ? p.out_pack : (nvalid1 <= kEpiPart ? 1 : 2), rot_sets = kEpiSplit / rot_np;
     const int rot_set = part / rot_np, rot_slice = part - rot_set * rot_np;
     for (int tile; (tile = tile_at(p, it)) < p.total_tiles; ++it) {
       if (tracer) OCTSEG_STAMP(tev, it);  // epilogue group ready for this tile
       if ((can_skip && static_cast<int>((group ^ chunk_ctr) & 1u) >= n_tma1) || (rot && (it % rot_sets) != rot_set)) {
         mbar_wait(bar_tfull + 8 * acc, acc_phase);  // stay within the ring: arrivals must land in this tile's phase
         if (tracer) OCTSEG_STAMP(tev + 1, it);
-        mbar_arrive(bar_tempty + 8 * acc);
+        __syncwarp();
+        if (!OCTSEG_WARP_ARRIVE || lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         if (tracer) OCTSEG_STAMP(tev + 2, it);
         chunk_ctr += n_tma1;
         if (++acc == p.n_acc) {
@@ -865,14 +938,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                        "r"(ov[g].z), "r"(ov[g].w)
                        : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(bar_sfull + 8 * sbi);  // 256 arrivals: the store warp issues the TMA store
+        __syncwarp();                                       // every lane's rows written and fenced ...
+        if (!OCTSEG_WARP_ARRIVE || lane == 0) mbar_arrive(bar_sfull + 8 * sbi);    // ... 8 warp arrivals: the store warp issues the TMA store
         ++grp_chunks;
         OCTSEG_CSTAMP(4, ckey);
       }
       chunk_ctr += n_tma;
 
+      if (headm) {
+        const int wfull = p.out_W * p.out_pack;
+        const size_t plane = static_cast<size_t>(p.out_H) * wfull;
+        const size_t base = static_cast<size_t>(tc.n) * p.out_ldc * plane + static_cast<size_t>(oh) * wfull +
+                            static_cast<size_t>(ow) * p.out_pack;
+        OCTSEG_CSTAMP(0, it);
+        OCTSEG_CSTAMP(1, it);
+        OCTSEG_CSTAMP(2, it);
+        const uint32_t ta = taddr + rot_slice * p.head_cmid;
+        if (p.head_classes == 1)  // warp-uniform
+          epilogue_head<ACT, 1>(p, ta, base + rot_slice, plane, valid);
+        else if (p.head_classes == 2)
+          epilogue_head<ACT, 2>(p, ta, base + rot_slice, plane, valid);
+        else
+          epilogue_head<ACT, 4>(p, ta, base + rot_slice, plane, valid);
+        OCTSEG_CSTAMP(3, it);  // (trace columns: "wait_store" = the whole head epilogue of this tile)
+        OCTSEG_CSTAMP(4, it);
+        OCTSEG_CSTAMP(5, it);
+        OCTSEG_CSTAMP(6, it);
+      }
       // remaining channels (and every non-bf16 output): direct stores from registers
-      for (int c0 = n_tma * 64; c0 < nvalid; c0 += 64) {
+      for (int c0 = n_tma * 64; c0 < (headm ? 0 : nvalid); c0 += 64) {
         const int cp = rot ? rot_slice * kEpiPart : c0 + part * kEpiPart;
         if (cp >= nvalid) continue;  // warp-uniform
         uint32_t v[kEpiPart];
@@ -919,9 +1013,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
       }
-      __syncwarp();
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
+      __syncwarp();  // every lane's TMEM reads are complete (tcgen05.wait::ld) before the warp's one arrival
+      if (!OCTSEG_WARP_ARRIVE || lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (tracer) OCTSEG_STAMP(tev + 2, it);  // accumulator released
       if (++acc == p.n_acc) {
         acc = 0;
@@ -965,6 +1059,10 @@ static const ConvKernelFn kConvKernels[3][3] = {
      conv_tc_kernel<OCTSEG_ACT_RELU, OCTSEG_RES_AFTER_ACT>},
     {conv_tc_kernel<OCTSEG_ACT_SWISH, OCTSEG_RES_NONE>, conv_tc_kernel<OCTSEG_ACT_SWISH, OCTSEG_RES_BEFORE_ACT>,
      conv_tc_kernel<OCTSEG_ACT_SWISH, OCTSEG_RES_AFTER_ACT>}};
+// fused 1x1 head (no residual): [activation]
+static const ConvKernelFn kConvHeadKernels[3] = {conv_tc_kernel<OCTSEG_ACT_NONE, OCTSEG_RES_NONE, true>,
+                                                 conv_tc_kernel<OCTSEG_ACT_RELU, OCTSEG_RES_NONE, true>,
+                                                 conv_tc_kernel<OCTSEG_ACT_SWISH, OCTSEG_RES_NONE, true>};
 
 extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_plan** out_plan) {
   if (!d || !out_plan) return fail(OCTSEG_EINVAL, "null argument");
@@ -1107,6 +1205,29 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
     delete pl;
     return fail(OCTSEG_EINVAL, "d2s output needs bf16 NHWC, one phase, no residual and d2s %% 8 == 0");
   }
+  kp.head_classes = kp.head_cmid = 0;
+  memset(kp.head_w, 0, sizeof(kp.head_w));
+  memset(kp.head_b, 0, sizeof(kp.head_b));
+  memset(kp.head_cbias, 0, sizeof(kp.head_cbias));
+  if (d->head_classes) {
+    const int pk = kp.out_pack;
+    if (d->head_classes < 1 || d->head_classes > 4 || d->head_cmid < 16 || d->head_cmid % 16 || d->head_cmid > kHeadMaxC ||
+        !d->head_weight || !d->head_bias || !d->head_conv_bias || (pk != 1 && pk != 2 && pk != 4) || d->n_tiles_n != 1 ||
+        d->phases != 1 || d->res || d->d2s || d->out_mode == OCTSEG_OUT_BF16_NHWC || d->Cout != pk * d->head_cmid ||
+        d->BN < d->Cout || d->out_ldc != d->head_classes || d->out_c_off != 0) {
+      delete pl;
+      return fail(OCTSEG_EINVAL,
+                  "fused head needs 1..4 classes, head_cmid in {16,32,48,64}, an NCHW out_mode with out_ldc = head_classes, "
+                  "one channel tile of out_pack (1|2|4) x head_cmid columns, one phase, no residual");
+    }
+    kp.head_classes = d->head_classes;
+    kp.head_cmid = d->head_cmid;
+    for (int j = 0; j < d->head_classes; ++j) {
+      kp.head_b[j] = d->head_bias[j];
+      for (int c = 0; c < d->head_cmid; ++c) kp.head_w[j * kHeadMaxC + c] = d->head_weight[j * d->head_cmid + c];
+    }
+    for (int c = 0; c < d->head_cmid; ++c) kp.head_cbias[c] = d->head_conv_bias[c];
+  }
   kp.total_tiles = d->phases * d->N * kp.tiles_h * kp.tiles_w * d->n_tiles_n;
   kp.fd_ntn = make_fastdiv(static_cast<uint32_t>(d->n_tiles_n));
   kp.fd_phases = make_fastdiv(static_cast<uint32_t>(d->phases));
@@ -1233,8 +1354,9 @@ extern "C" int octseg_conv_plan_create(const octseg_conv_desc* d, octseg_conv_pl
   static bool attr_set = false;
   if (!attr_set) {
     for (int a = 0; a < 3; ++a)
-      for (int r = 0; r < 3; ++r) {
-        cudaError_t e = cudaFuncSetAttribute(kConvKernels[a][r], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      for (int r = 0; r < 4; ++r) {
+        cudaError_t e = cudaFuncSetAttribute(r < 3 ? kConvKernels[a][r] : kConvHeadKernels[a],
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
           delete pl;
           return fail(OCTSEG_ECUDA, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
@@ -1267,6 +1389,7 @@ extern "C" int octseg_conv_run(const octseg_conv_plan* plan, void* stream) {
   if (plan->kp.total_tiles <= 0) return OCTSEG_OK;
   // sigmoid exists only on the NCHW head paths, which read p.act at run time
   const int a = plan->kp.act == OCTSEG_ACT_RELU ? 1 : (plan->kp.act == OCTSEG_ACT_SWISH ? 2 : 0);
-  kConvKernels[a][plan->kp.res_mode]<<<plan->grid, kThreads, plan->smem, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  const ConvKernelFn fn = plan->kp.head_classes ? kConvHeadKernels[a] : kConvKernels[a][plan->kp.res_mode];
+  fn<<<plan->grid, kThreads, plan->smem, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   return check_launch("conv_tc_kernel");
 }

@@ -193,15 +193,29 @@ class Builder:
              stride: int = 1, pad: Tuple[int, int] = (0, 0), groups: int = 1, transposed: bool = False,
              act: str = 'none', res: Optional[Act] = None, res_mode: str = 'none',
              out_hw: Optional[Tuple[int, int]] = None, out_mode: str = 'bf16_nhwc',
-             out_tensor: Optional[torch.Tensor] = None) -> Optional[Act]:
+             out_tensor: Optional[torch.Tensor] = None,
+             head: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None) -> Optional[Act]:
+        """head = (weight [classes, cout, 1, 1], bias | None) of a 1x1 segmentation head: it is applied to this conv's
+        activated output inside the epilogue (fp32, octseg.h `head_classes`), `out_tensor` (N, classes, H, W) receives the
+        head's logits / masks and the conv's own output is never stored."""
         cout = w.shape[1] if transposed else w.shape[0]
         bf16_out = out_mode == 'bf16_nhwc'
         reads = [a for a, _ in srcs] + [res]
+        head_t, n_planes = None, cout
+        if head is not None:
+            hw = head[0].detach().float().cpu().reshape(head[0].shape[0], -1)
+            assert not bf16_out and res is None and not transposed and hw.shape[1] == cout and cout % 16 == 0 and hw.shape[0] <= 4
+            hb = head[1].detach().float().cpu() if head[1] is not None else torch.zeros(hw.shape[0])
+            cb = b.detach().float().cpu() if b is not None else torch.zeros(cout)
+            assert cout <= 64, 'a fused head reads at most 64 channels per pixel'
+            head_t, n_planes = (hw, hb, cb), hw.shape[0]
         # narrow stride-1 convs: pack f adjacent pixels into one GEMM row (same memory, wider view)
         f = 0
         if (not transposed and groups == 1 and stride == 1 and not any(up for _, up in srcs) and out_hw is None
                 and pad[0] == (w.shape[2] - 1) // 2 and pad[1] == (w.shape[3] - 1) // 2):
             f = pixel_pack_factor([a.Cp for a, _ in srcs], srcs[0][0].W, w.shape[3], pad8(cout) if bf16_out else cout)
+            if head_t is not None and f > 4:
+                f = 4                                         # the fused-head epilogue packs at most 4 pixels per row
         if f:
             a0 = srcs[0][0]
             cout_store = pad8(cout) if bf16_out else cout
@@ -214,7 +228,9 @@ class Builder:
             if bf16_out:
                 out_act = self.new_act(a0.H, a0.W, cout)
             else:
-                assert out_tensor is not None and tuple(out_tensor.shape) == (self.N, cout, a0.H, a0.W) and res is None
+                assert out_tensor is not None and tuple(out_tensor.shape) == (self.N, n_planes, a0.H, a0.W) and res is None
+            if head_t is not None:
+                geom.macs += a0.N * a0.H * a0.W * cout * n_planes
 
             def make_plan():
                 views = [a.t.view(a.N, a.H, a.W // f, f * a.Cp) for a, _ in srcs]
@@ -224,7 +240,7 @@ class Builder:
                     return ConvPlan(geom, packed, bias_rows, views, out_t, out_mode=out_mode, act=act, res=res_t,
                                     res_mode=res_mode, name=name)
                 return ConvPlan(geom, packed, bias_rows, views, out_tensor, out_mode=out_mode, act=act, name=name,
-                                out_pack=f, out_ldc=cout)
+                                out_pack=f, out_ldc=n_planes, head=head_t)
             self._add_conv(name, geom, make_plan, reads, [out_act] if out_act is not None else [],
                            extra_bytes=0 if bf16_out else out_tensor.numel() * out_tensor.element_size())
             return out_act
@@ -265,12 +281,15 @@ class Builder:
         if bf16_out:
             out_act = self.new_act(geom.out_H, geom.out_W, cout)
         else:
-            assert out_tensor is not None and tuple(out_tensor.shape) == (self.N, cout, geom.out_H, geom.out_W)
+            assert out_tensor is not None and tuple(out_tensor.shape) == (self.N, n_planes, geom.out_H, geom.out_W)
+        if head_t is not None:
+            assert geom.n_tiles_n == 1, 'a fused head needs all of a pixel\'s channels in one tile'
+            geom.macs += self.N * geom.out_H * geom.out_W * cout * n_planes
 
         def make_plan():
             return ConvPlan(geom, packed, bias_rows, [a.t for a, _ in srcs], out_act.t if bf16_out else out_tensor,
                             out_mode=out_mode, act=act, res=res.t if res is not None else None, res_mode=res_mode,
-                            name=name)
+                            name=name, out_ldc=None if head_t is None else n_planes, head=head_t)
         self._add_conv(name, geom, make_plan, reads, [out_act] if out_act is not None else [],
                        extra_bytes=0 if bf16_out else out_tensor.numel() * out_tensor.element_size())
         return out_act

@@ -426,7 +426,11 @@ class ConvPlan:
                  out: torch.Tensor, out_mode: str = 'bf16_nhwc', act: str = 'none',
                  res: Optional[torch.Tensor] = None, res_mode: str = 'none', out_c_off: int = 0,
                  per_image_weights: bool = False, name: str = '', out_pack: int = 1,
-                 out_ldc: Optional[int] = None, d2s: int = 0):
+                 out_ldc: Optional[int] = None, d2s: int = 0,
+                 head: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+        """head: (weight fp32 [classes][cmid], bias fp32 [classes], conv bias fp32 [cmid]) of a 1x1 segmentation head
+        fused into the epilogue (octseg.h, `head_classes`): `out` is then the head's NCHW output and the conv's own
+        output is never stored."""
         lib = _lib.load()
         dev = out.device
         self.geom, self.name = geom, name
@@ -457,6 +461,11 @@ class ConvPlan:
         d.out_pack = out_pack
         d.d2s = d2s
         d.halo = geom.halo
+        if head is not None:       # host arrays, copied into the plan's parameter block by plan_create
+            hw, hb, cb = (t.detach().to('cpu', torch.float32).contiguous() for t in head)
+            d.head_classes, d.head_cmid = hw.shape
+            assert hb.numel() == hw.shape[0] and cb.numel() == hw.shape[1]
+            d.head_weight, d.head_bias, d.head_conv_bias = hw.data_ptr(), hb.data_ptr(), cb.data_ptr()
         handle = C.c_void_p()
         _lib.check(lib.octseg_conv_plan_create(C.byref(d), C.byref(handle)), f'conv_plan_create({name})')
         self._lib, self._h = lib, handle

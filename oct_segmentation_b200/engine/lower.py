@@ -159,7 +159,14 @@ def lower_unetpp_decoder(b: Builder, dec, feats: List[Act]) -> Act:
     return _unet_block(b, dec.blocks[key], dense[f'x_0_{depth - 1}'], [], 'decoder.blocks.' + key)
 
 
-def lower_linknet_decoder(b: Builder, dec, feats: List[Act]) -> Act:
+# LinkNet ends in conv1x1+BN+ReLU (16 -> 32 channels at full resolution) followed by a 1x1 segmentation head: fused, the
+# 32-channel full-resolution tensor (the largest activation of the network) is never written or read back.
+FUSE_LINKNET_HEAD = True
+
+
+def lower_linknet_decoder(b: Builder, dec, feats: List[Act], head=None) -> Optional[Act]:
+    """head = (segmentation_head, out tensor, out_mode): fuse the 1x1 head into the last block's final conv; returns
+    None then (there is no decoder output tensor any more)."""
     f = feats[::-1]
     x = f[0]
     skips = f[1:]
@@ -172,6 +179,11 @@ def lower_linknet_decoder(b: Builder, dec, feats: List[Act]) -> Act:
         y = b.conv([(x, False)], w1, b1, name=nm + '.0', act='relu')
         y = b.conv([(y, False)], wt, bt, name=nm + '.1', transposed=True, act='relu')
         skip = skips[i] if i < len(skips) else None
+        if head is not None and i == len(dec.blocks) - 1 and skip is None:
+            hconv = head[0][0]
+            b.conv([(y, False)], w2, b2, name=nm + '.2+segmentation_head.0', act='relu', out_mode=head[2], out_tensor=head[1],
+                   head=(hconv.weight.detach().float().cpu(), hconv.bias))
+            return None
         x = b.conv([(y, False)], w2, b2, name=nm + '.2', act='relu', res=skip,
                    res_mode='after_act' if skip is not None else 'none')
     return x
@@ -185,3 +197,15 @@ def lower_head(b: Builder, head, x: Act, out: torch.Tensor, out_mode: str) -> No
     k = conv.kernel_size[0]
     b.conv([(x, False)], conv.weight.detach().float().cpu(), conv.bias, name='segmentation_head.0',
            pad=(k // 2, k // 2), act='none', out_mode=out_mode, out_tensor=out)
+
+
+def lower_decoder_and_head(b: Builder, model, feats: List[Act], out: torch.Tensor, out_mode: str) -> Optional[Act]:
+    """Decoder + segmentation head into ``out``.  Returns the decoder's output activation, or None when the head was
+    fused into the decoder's last conv (LinkNet: its 1x1 head rides in that conv's epilogue)."""
+    head = model.segmentation_head
+    if (model.decoder.kind == 'linknet' and FUSE_LINKNET_HEAD and tuple(head[0].kernel_size) == (1, 1)
+            and head[0].out_channels <= 4):
+        return lower_linknet_decoder(b, model.decoder, feats, head=(head, out, out_mode))
+    y = DECODER_LOWERING[model.decoder.kind](b, model.decoder, feats)
+    lower_head(b, head, y, out, out_mode)
+    return y

@@ -11,7 +11,7 @@ import torch
 
 from .. import _lib
 from .builder import Builder
-from .lower import DECODER_LOWERING, ENCODER_LOWERING, lower_head
+from .lower import ENCODER_LOWERING, lower_decoder_and_head
 
 
 class CompiledNet:
@@ -42,10 +42,9 @@ class CompiledNet:
             self.out = torch.zeros(N, classes, H, W, dtype=odt, device=self.device)
             b = builder_cls(self.device, N, **builder_kw)
             feats = ENCODER_LOWERING[model.encoder.kind](b, model.encoder, x_view, in_dtype, norm)
-            y = DECODER_LOWERING[model.decoder.kind](b, model.decoder, feats)
-            lower_head(b, model.segmentation_head, y, self.out, out_mode)
-            self.feats, self.dec_out = feats, y        # kept for per-stage parity diagnostics
-            b.pin(list(feats) + [y])                   # (pinned: not recycled by the activation arena)
+            y = lower_decoder_and_head(b, model, feats, self.out, out_mode)
+            self.feats, self.dec_out = feats, y        # kept for per-stage parity diagnostics (dec_out None: head fused)
+            b.pin(list(feats) + ([y] if y is not None else []))   # (pinned: not recycled by the activation arena)
             b.finalize()                               # liveness-based arena, kernel plans with final pointers
         self.builder = b
         self.macs = b.macs

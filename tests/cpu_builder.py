@@ -43,7 +43,7 @@ class CpuBuilder:
         return _act(F.max_pool2d(_nchw(x), 3, 2, 1))
 
     def conv(self, srcs, w, b, *, name, stride=1, pad=(0, 0), groups=1, transposed=False, act='none', res=None,
-             res_mode='none', out_hw=None, out_mode='bf16_nhwc', out_tensor=None):
+             res_mode='none', out_hw=None, out_mode='bf16_nhwc', out_tensor=None, head=None):
         w, b = self._d(w), self._d(b)
         parts = [F.interpolate(_nchw(a), scale_factor=2, mode='nearest') if up else _nchw(a) for a, up in srcs]
         x = torch.cat(parts, 1)
@@ -56,6 +56,8 @@ class CpuBuilder:
         y = act_fn(y, act)
         if res_mode == 'after_act':
             y = y + _nchw(res)
+        if head is not None:                           # fused 1x1 segmentation head: fp32 on the activated output
+            y = F.conv2d(y, self._d(head[0]).float().reshape(head[0].shape[0], -1, 1, 1), self._d(head[1]))
         if out_mode == 'bf16_nhwc':
             return _act(y)
         out_tensor.copy_(y if out_mode == 'f32_nchw' else (y > 0))
@@ -142,13 +144,12 @@ class Bf16Builder(CpuBuilder):
 
 def run_lowered(model, x_nchw: torch.Tensor, norm=None, bf16: bool = False, return_stages: bool = False):
     """Run a product smp model's lowering through the torch-op builder; returns fp32 logits NCHW."""
-    from oct_segmentation_b200.engine.lower import DECODER_LOWERING, ENCODER_LOWERING, lower_head
+    from oct_segmentation_b200.engine.lower import ENCODER_LOWERING, lower_decoder_and_head
     b = (Bf16Builder if bf16 else CpuBuilder)(x_nchw.shape[0], x_nchw.device)
     feats = ENCODER_LOWERING[model.encoder.kind](b, model.encoder, x_nchw, 'f32', norm)
-    y = DECODER_LOWERING[model.decoder.kind](b, model.decoder, feats)
     out = torch.zeros(x_nchw.shape[0], model.segmentation_head[0].out_channels, x_nchw.shape[2], x_nchw.shape[3],
                       device=x_nchw.device)
-    lower_head(b, model.segmentation_head, y, out, 'f32_nchw')
+    y = lower_decoder_and_head(b, model, feats, out, 'f32_nchw')
     if return_stages:
-        return out, [_nchw(f) for f in feats], _nchw(y)
+        return out, [_nchw(f) for f in feats], (_nchw(y) if y is not None else None)      # y None: head fused (LinkNet)
     return out

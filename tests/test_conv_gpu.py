@@ -67,3 +67,43 @@ def test_conv_tc_repeatable():
     a, _, _ = run_case(case, seed=3)
     b, _, _ = run_case(case, seed=3)
     assert torch.equal(a, b)
+
+
+# (cin, cmid, classes, H, W): 16-channel sources pack 4 pixels per GEMM row, 32-channel ones 2, wider ones none
+HEAD_CASES = [(16, 32, 2, 40, 48), (16, 32, 1, 33, 36), (32, 48, 3, 24, 40), (64, 64, 4, 20, 24), (24, 16, 2, 16, 64)]
+
+
+@pytest.mark.parametrize('case', HEAD_CASES, ids=lambda c: 'cin%d_cmid%d_cls%d_%dx%d' % c)
+@pytest.mark.parametrize('out_mode', ['f32_nchw', 'u8_nchw'])
+@pytest.mark.parametrize('act', ['relu', 'swish'])
+def test_conv_with_fused_1x1_head(case, out_mode, act):
+    """conv 1x1 + bias + act with a 1x1 segmentation head folded into the epilogue (octseg.h `head_classes`; LinkNet's
+    last decoder conv + head) against torch fp32: the logits see the UN-rounded fp32 activations, so they are closer to
+    torch than the two-launch path; the u8 planes must equal logit > 0 away from the zero crossing."""
+    import torch.nn.functional as F
+    from oct_segmentation_b200.engine.builder import Builder
+    cin, cmid, classes, H, W = case
+    N = 2
+    g = torch.Generator().manual_seed(cin * 100 + cmid + classes)
+    x = torch.randn(N, cin, H, W, generator=g).to(torch.bfloat16).float()
+    w = torch.randn(cmid, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cmid, generator=g) * 0.2
+    hw = torch.randn(classes, cmid, 1, 1, generator=g) / cmid ** 0.5
+    hb = torch.randn(classes, generator=g) * 0.1
+    bld = Builder(torch.device('cuda'), N, reuse=False)
+    xa = C.Act(dev_nhwc(x), cin)                   # external input buffer (not an arena activation)
+    out = torch.full((N, classes, H, W), 7, dtype=torch.float32 if out_mode == 'f32_nchw' else torch.uint8, device='cuda')
+    assert bld.conv([(xa, False)], w, b, name='fused', act=act, out_mode=out_mode, out_tensor=out, head=(hw, hb)) is None
+    bld.run()
+    torch.cuda.synchronize()
+    y = F.conv2d(x.cuda(), w.to(torch.bfloat16).float().cuda(), b.cuda())
+    y = F.relu(y) if act == 'relu' else y * torch.sigmoid(y)
+    want = F.conv2d(y, hw.cuda(), hb.cuda())
+    if out_mode == 'f32_nchw':
+        assert torch.isfinite(out).all()
+        err = ((out - want).norm() / want.norm()).item()
+        assert err < 3e-3, err                   # bf16 conv weights only (tanh.approx swish: ~1e-3)
+    else:
+        assert out.max() <= 1
+        conf = want.abs() > 0.02
+        assert (out[conf] == (want[conf] > 0).to(torch.uint8)).all() and conf.float().mean() > 0.9

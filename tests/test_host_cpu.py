@@ -272,7 +272,7 @@ def test_activation_arena_of_a_lowered_network_reuses_dead_buffers():
     import torch
     from oct_segmentation_b200 import synthetic
     from oct_segmentation_b200.engine.builder import Builder
-    from oct_segmentation_b200.engine.lower import DECODER_LOWERING, ENCODER_LOWERING, lower_head
+    from oct_segmentation_b200.engine.lower import ENCODER_LOWERING, lower_decoder_and_head
     from oct_segmentation_b200.model import OCTSegmentationModel
     cfg = synthetic.MODEL_CONFIGS['VV']
     m = OCTSegmentationModel(arch=cfg['architecture'], encoder_name=cfg['encoder'], model_name=cfg['model_name'],
@@ -281,8 +281,7 @@ def test_activation_arena_of_a_lowered_network_reuses_dead_buffers():
     S = 64
     x = torch.zeros(1, S, S, 3, dtype=torch.uint8).permute(0, 3, 1, 2)
     feats = ENCODER_LOWERING[m.encoder.kind](b, m.encoder, x, 'u8', None)
-    y = DECODER_LOWERING[m.decoder.kind](b, m.decoder, feats)
-    lower_head(b, m.segmentation_head, y, torch.zeros(1, 1, S, S, dtype=torch.uint8), 'u8_nchw')
+    y = lower_decoder_and_head(b, m, feats, torch.zeros(1, 1, S, S, dtype=torch.uint8), 'u8_nchw')
     b.pin(list(feats) + [y])
     acts, offs, total = b.plan_buffers()
     assert len(acts) == len(b._acts) and total < 0.4 * b.act_bytes

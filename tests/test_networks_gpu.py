@@ -105,9 +105,11 @@ def test_network_matches_oracle(key):
     rep = []
     for i, (a, r) in enumerate(zip(net.feats, feats_ref[1:]), start=1):
         rep.append(f'f{i}:{rel_l2(a.t[..., :a.C].permute(0, 3, 1, 2), r):.1e}')
-    g = net.dec_out.t[..., :net.dec_out.C].permute(0, 3, 1, 2)
     e32 = rel_l2(got, want)
-    rep += [f'dec:{rel_l2(g, dec_ref):.1e}', f'logits:{e32:.1e}']
+    if net.dec_out is not None:              # (LinkNet: the head is fused into the decoder's last conv, no such tensor)
+        g = net.dec_out.t[..., :net.dec_out.C].permute(0, 3, 1, 2)
+        rep.append(f'dec:{rel_l2(g, dec_ref):.1e}')
+    rep.append(f'logits:{e32:.1e}')
     print(f'\n{key} vs fp32 oracle : ' + ' '.join(rep))
     assert got.shape == want.shape and got.dtype == torch.float32
     assert torch.isfinite(got).all()

@@ -7,6 +7,10 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+if os.environ.get('OCTSEG_AB_LIB'):     # A/B builds of the library (tools/ab/*.so)
+    from oct_segmentation_b200 import _lib as _l
+    _l.LIB_PATH = os.path.abspath(os.environ['OCTSEG_AB_LIB'])
+
 from oct_segmentation_b200.model import OCTSegmentationModel
 from oct_segmentation_b200.engine.network import CompiledNet
 from oracle import synth

@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault('CUBLAS_WORKSPACE_CONFIG', ':4096:8')
 import torch
 
-from oct_segmentation_b200.engine.lower import DECODER_LOWERING, ENCODER_LOWERING, lower_head
+from oct_segmentation_b200.engine.lower import ENCODER_LOWERING, lower_decoder_and_head
 from oct_segmentation_b200.model import OCTSegmentationModel
 from oracle import synth
 from tests.cpu_builder import Bf16Builder, CpuBuilder, _r16
@@ -121,9 +121,8 @@ def main():
         b = VarBuilder(nfr, dev, **kw)
         with torch.no_grad():
             feats = ENCODER_LOWERING[ours.model.encoder.kind](b, ours.model.encoder, x, 'f32', None)
-            y = DECODER_LOWERING[ours.model.decoder.kind](b, ours.model.decoder, feats)
             out = torch.zeros_like(want)
-            lower_head(b, ours.model.segmentation_head, y, out, 'f32_nchw')
+            lower_decoder_and_head(b, ours.model, feats, out, 'f32_nchw')
         return out
 
     say('--- against the fp32 oracle')

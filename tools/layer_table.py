@@ -16,7 +16,7 @@ import torch
 
 from oct_segmentation_b200 import synthetic
 from oct_segmentation_b200.engine.builder import Builder
-from oct_segmentation_b200.engine.lower import DECODER_LOWERING, ENCODER_LOWERING, lower_head
+from oct_segmentation_b200.engine.lower import ENCODER_LOWERING, lower_decoder_and_head
 from oct_segmentation_b200.model import OCTSegmentationModel
 
 
@@ -33,8 +33,7 @@ def main():
     b = Builder('cpu', 1)
     x = torch.zeros(1, S, S, 3, dtype=torch.uint8).permute(0, 3, 1, 2)
     feats = ENCODER_LOWERING[m.encoder.kind](b, m.encoder, x, 'u8', None)
-    y = DECODER_LOWERING[m.decoder.kind](b, m.decoder, feats)
-    lower_head(b, m.segmentation_head, y, torch.zeros(1, len(cfg['classes']), S, S, dtype=torch.uint8), 'u8_nchw')
+    lower_decoder_and_head(b, m, feats, torch.zeros(1, len(cfg['classes']), S, S, dtype=torch.uint8), 'u8_nchw')
     times = json.load(open(os.path.join(ROOT, 'gpurun_out', f'ops_{key}.json')))
     rows = []
     for name, kind, macs, byt in zip(b.op_names, b.op_kinds, b.op_macs, b.op_bytes):

@@ -43,6 +43,8 @@ if __name__ == '__main__':
     }
     LAYERS['d2s16'] = ('linknet convT 16->16 @448 (depth-to-space)', [(16, 448, 448)], 16, 4, 16, 'relu')
     LAYERS['vvhead'] = ('unet head 16->1 3x3 @896 (packed f=4, u8 planes)', [(64, 896, 224)], 4, 3, 16, 'none')
+    LAYERS['linkhead'] = ('linknet 1x1 16->32 relu + fused 1x1 head 32->2 @896 (packed f=4, u8 planes)', [(64, 896, 224)], 2, 1, 16, 'relu')
+    LAYERS['linkhead_f32'] = ('the same, fp32 logits', [(64, 896, 224)], 2, 1, 16, 'relu')
     name, srcs, cout, k, n, act = LAYERS[sys.argv[1]]
     spec = [((n, s[1], s[2], s[0], CV.pad8(s[0])), False) for s in srcs]
     seg_t = [torch.randn(n, s[1], s[2], CV.pad8(s[0]), device='cuda').to(torch.bfloat16) for s in srcs]
@@ -53,6 +55,15 @@ if __name__ == '__main__':
         bias = CV.pad_bias(bp, geom, 4 * cs)
         out = torch.empty(n, 2 * srcs[0][1], 2 * srcs[0][2], cs, dtype=torch.bfloat16, device='cuda')
         plan = CV.ConvPlan(geom, packed, bias, seg_t, out, act=act, name=name, out_ldc=cs, d2s=cs)
+    elif sys.argv[1].startswith('linkhead'):
+        w16 = torch.randn(32, 16, 1, 1) * 0.2
+        wp, bp = CV.pack_conv_weights(w16, torch.zeros(32), [16], [16], 4, 0, 32)
+        geom, packed = CV.plan_conv(spec, wp, stride=1, pad=(0, 0), out_bf16=False)
+        bias = CV.pad_bias(bp, geom, 128)
+        f32 = sys.argv[1].endswith('f32')
+        out = torch.empty(n, 2, 896, 896, dtype=torch.float32 if f32 else torch.uint8, device='cuda')
+        plan = CV.ConvPlan(geom, packed, bias, seg_t, out, out_mode='f32_nchw' if f32 else 'u8_nchw', act=act, name=name,
+                           out_pack=4, out_ldc=2, head=(torch.randn(2, 32) * 0.2, torch.zeros(2), torch.zeros(32)))
     elif sys.argv[1] == 'vvhead':
         w16 = torch.randn(1, 16, 3, 3) * 0.05
         wp, bp = CV.pack_conv_weights(w16, torch.zeros(1), [16], [16], 4, 1, 1)
@@ -69,6 +80,13 @@ if __name__ == '__main__':
     for _ in range(3):
         plan.run()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        plan.run()
+    e1.record()
+    torch.cuda.synchronize()
+    print('ms per launch (trace build):', e0.elapsed_time(e1) / 5)
     buf = np.zeros((16, 256), dtype=np.uint64)
     _lib.check(lib.octseg_debug_trace(buf.ctypes.data), 'trace')
     t = buf.astype(np.int64)
