@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define OCTSEG_ABI_VERSION 1
+#define OCTSEG_ABI_VERSION 2
 
 enum {
   OCTSEG_OK = 0,

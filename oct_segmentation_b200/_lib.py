@@ -115,7 +115,7 @@ def load() -> C.CDLL:
     for name in EXPORTS:
         if name not in ('octseg_last_error',):
             getattr(lib, name).restype = C.c_int
-    if lib.octseg_abi_version() != 1:
+    if lib.octseg_abi_version() != 2:
         raise OctsegError('liboctseg.so ABI version mismatch')
     _lib = lib
     return lib
