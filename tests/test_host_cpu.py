@@ -342,3 +342,32 @@ def test_normalisation_constants_match_the_reference_encoders():
     assert m.std.flatten().tolist() == pytest.approx([0.229, 0.224, 0.225])
     with pytest.raises(KeyError):
         smp.encoders.get_preprocessing_params('resnet18')
+
+
+def test_ctypes_conv_desc_layout_matches_the_c_header(tmp_path):
+    """The host side fills octseg_conv_desc through a ctypes mirror: its size and every field offset must equal what a C
+    compiler makes of include/octseg.h (a silent mismatch would hand the planner shifted fields)."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    names = [n for n, _ in _lib.ConvDesc._fields_]
+    seg_names = [n for n, _ in _lib.ConvSeg._fields_]
+    src = ['#include <stddef.h>', '#include <stdio.h>', '#include "octseg.h"', 'int main(void) {',
+           '  printf("sizeof %zu %zu\\n", sizeof(octseg_conv_desc), sizeof(octseg_conv_seg));']
+    src += [f'  printf("d {n} %zu\\n", offsetof(octseg_conv_desc, {n}));' for n in names]
+    src += [f'  printf("s {n} %zu\\n", offsetof(octseg_conv_seg, {n}));' for n in seg_names]
+    src += ['  return 0;', '}']
+    c = tmp_path / 'layout.c'
+    c.write_text('\n'.join(src))
+    exe = tmp_path / 'layout'
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include')
+    subprocess.run(['gcc', '-I', inc, '-o', str(exe), str(c)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split('\n')
+    assert out[0] == f'sizeof {ctypes.sizeof(_lib.ConvDesc)} {ctypes.sizeof(_lib.ConvSeg)}'
+    for line in out[1:]:
+        if not line:
+            continue
+        kind, name, off = line.split()
+        cls = _lib.ConvDesc if kind == 'd' else _lib.ConvSeg
+        assert getattr(cls, name).offset == int(off), (kind, name)
